@@ -1,0 +1,143 @@
+/* lt_b200.h — C-ABI of liblt_b200.so: the B200-native replacement for the Monte Carlo path walk
+ * of zhouyifan233/light-transport.
+ *
+ * The reference has no FFI seam; its boundary is the Python call
+ *     render_scene(scene, primitives, bvh)            R/src/path_tracing.py:371-387
+ *     trace_path(scene, primitives, bvh, ray, ...)    R/src/path_tracing.py:23-159
+ *     intersect_bvh(ray, primitives, linear_bvh)      R/src/bvh_new.py:413-482
+ * (R/ = LightTransportSimulator/light_transport/).  A maintainer binds the entry points below with
+ * ctypes from that Python code (INTEGRATION.md shows the stub); light_transport_b200/host.py is
+ * that binding, shipped.
+ *
+ * Conventions: every function returns 0 (LT_OK) or a negative LT_E_* code; lt_last_error() gives
+ * the message of the calling thread's last failure.  No exceptions cross the boundary.  Pointers
+ * are caller-owned and only need to stay valid for the duration of the call; data pointers of
+ * lt_intersect/lt_render/lt_film_* may be HOST or DEVICE memory (detected per pointer).  Handles are
+ * opaque, freed by the matching *_destroy, not thread-safe individually.  Calls are synchronous.
+ */
+#ifndef LT_B200_H
+#define LT_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LT_OK 0
+#define LT_E_INVALID (-1)      /* bad argument / unsupported combination */
+#define LT_E_CUDA (-2)         /* CUDA runtime failure (message has the CUDA error string) */
+#define LT_E_COMPAT_UNDEFINED (-3) /* COMPAT traversal on a node list where the reference raises IndexError (Q9b) */
+#define LT_E_NO_BVH (-4)       /* traversal needs a structure that was not set/built */
+#define LT_E_OVERFLOW (-5)     /* a capacity was exceeded (details in message) */
+
+/* traversal semantics */
+#define LT_TRAV_COMPAT 0       /* emulate R/src/bvh_new.py:413-482 over the reference's node list, defects included */
+#define LT_TRAV_NEAREST 1      /* true closest hit, EPSILON < t, ties -> lowest primitive index; all-primitive scan */
+#define LT_TRAV_LBVH 2         /* same semantics as NEAREST through the GPU-built LBVH */
+/* integrator semantics */
+#define LT_SEM_REFERENCE 0     /* R/src/path_tracing.py:23-159 (recurse-and-continue) */
+#define LT_SEM_ITERATIVE 1     /* R/src/path_tracing_fix1.py:17-136 */
+/* arithmetic */
+#define LT_REAL_F32 0
+#define LT_REAL_F64 1
+/* path scheduling */
+#define LT_SCHED_MEGAKERNEL 0  /* persistent warps, in-warp regeneration */
+#define LT_SCHED_WAVEFRONT 1   /* generate / extend / shade / shadow queues */
+
+typedef struct lt_ctx lt_ctx;
+typedef struct lt_scene lt_scene;
+
+/* Scene as structure-of-arrays, float64 like the reference's jitclass fields (a11):
+ * PreComputedTriangle R/src/primitives.py:85-113, Material R/src/material.py:18-37,
+ * Light R/src/scene.py:6-17.  3-vectors (the reference's homogeneous w is dropped, Q11). */
+typedef struct {
+    int32_t n_tris, n_mats, n_lights, reserved;
+    const double *tri_v0, *tri_v1, *tri_v2;  /* [n_tris][3] vertex_1..3 */
+    const double *tri_n;                     /* [n_tris][3] geometric unit normal */
+    const int32_t *tri_mat;                  /* [n_tris]    material index */
+    const uint8_t *tri_light;                /* [n_tris]    is_light */
+    const double *mat_kd;                    /* [n_mats][3] color.diffuse */
+    const double *mat_emission, *mat_ior, *mat_transmission; /* [n_mats] */
+    const int32_t *mat_flags;                /* [n_mats] bit0 is_diffuse, bit1 is_mirror */
+    const double *light_pos, *light_n;       /* [n_lights][3] Light.source, Light.normal */
+    const double *light_lekd;                /* [n_lights][3] material.emission * material.color.diffuse */
+    const double *light_area;                /* [n_lights]    Light.total_area */
+} lt_scene_desc;
+
+/* The reference's flattened node list (LinearBVHNode, R/src/bvh_new.py:53-67), for COMPAT. */
+typedef struct {
+    int32_t n_nodes, reserved;
+    const double *bmin, *bmax;               /* [n_nodes][3] bounds.min_point / max_point */
+    const int32_t *prim_off;                 /* primitives_offset   (-1 where None) */
+    const int32_t *second;                   /* second_child_offset (-1 where None) */
+    const int32_t *n_prims;                  /* n_primitives (0 on interior nodes) */
+    const int32_t *axis;                     /* axis (-1 where None) */
+} lt_node_desc;
+
+typedef struct {
+    int32_t width, height;       /* film size; Scene.width/height R/src/scene.py:57-58 */
+    int32_t spp;                 /* samples per pixel of the WHOLE job: path id = (i*W+j)*spp + s */
+    int32_t s0, s1;              /* this call renders samples s in [s0, s1) of every pixel */
+    int32_t max_depth;           /* Scene.max_depth */
+    int32_t semantics, traversal, real, scheduler;
+    int32_t rr_start;            /* roulette when bounce > rr_start: 3 (path_tracing.py:148) / 5 (fix1:126) */
+    int32_t n_light_idx;         /* replay: light picks provided per path (light_idx[...][n_light_idx]) */
+    double rr_floor;             /* 0.05, path_tracing.py:149 */
+    double eps;                  /* EPSILON = 1e-6, constants.py:12 */
+    double camera[3];            /* Scene.camera[:3] */
+    double f_distance;           /* Scene.f_distance */
+    uint64_t seed;               /* Philox4x32-10 key (used when rand0 == NULL) */
+    int32_t pixel0, pixel1;      /* optional pixel sub-range [pixel0,pixel1) in row-major order; 0,0 = all */
+    int32_t paths_per_warp;      /* megakernel work granule; 0 = auto */
+    int32_t flags;               /* reserved, 0 */
+} lt_render_params;
+
+typedef struct {
+    uint64_t paths, rays_ext, rays_shadow, box_tests, tri_tests, max_frames, light_idx_overflow,
+        frame_overflow, lane_steps, lane_slots, kernel_ns, launches;
+} lt_counters;
+
+typedef struct {
+    int32_t n_prims, n_nodes, max_depth, reserved;
+    float build_ms;              /* device time of the whole build */
+    float sort_ms;
+    double root_bmin[3], root_bmax[3];
+    double sah_cost;
+} lt_bvh_stats;
+
+int lt_init(int device, lt_ctx **out);
+void lt_destroy(lt_ctx *);
+int lt_device_info(lt_ctx *, int32_t *sm_count, int32_t *clock_khz, int64_t *global_mem, int32_t *cc_major,
+                   int32_t *cc_minor);
+
+int lt_scene_create(lt_ctx *, const lt_scene_desc *, lt_scene **out);          /* H2D once */
+void lt_scene_destroy(lt_scene *);
+int lt_scene_set_compat_bvh(lt_scene *, const lt_node_desc *);                 /* replaces the bvh argument of render_scene */
+int lt_bvh_build(lt_scene *, int flags, lt_bvh_stats *out);                    /* GPU LBVH: replaces build_bvh/flatten_bvh, bvh_new.py:148-300 */
+
+/* closest hit for an explicit ray batch (replaces intersect_bvh / hit_object for a ray set).
+ * o,d: [n][3] float64; prim_out: -1 on miss; t_out: +inf on miss.  real selects fp32/fp64 arithmetic. */
+int lt_intersect(lt_scene *, int traversal, int real, const double *o, const double *d, int64_t n,
+                 int32_t *prim_out, double *t_out, lt_counters *c);
+
+/* The walk (a1-a10): ray generation, traversal, shading, roulette, tally.
+ * rand0/rand1: [H][W][spp][max_depth] float64 (Scene.rand_0/rand_1) or NULL -> Philox(seed);
+ * light_idx:   [H][W][spp][n_light_idx] int32 replayed light picks or NULL -> Philox stream 1;
+ * film_sum:    [H][W][3] float64, += sum over the rendered samples of per-path radiance;
+ * samples_out: optional [H][W][s1-s0][3] float64 per-path radiance (R/src/path_tracing.py:297). */
+int lt_render(lt_scene *, const lt_render_params *, const double *rand0, const double *rand1,
+              const int32_t *light_idx, double *film_sum, double *samples_out, lt_counters *c);
+
+/* image = clip(film_sum / spp_total, 0, 1)   (R/src/path_tracing.py:304-305) */
+int lt_film_finalize(lt_ctx *, const double *film_sum, int64_t n_values, int64_t spp_total, double *image_out);
+
+/* measured FP32 FMA throughput of this device (TFLOP/s), for the roofline denominator */
+int lt_measure_fp32_peak(lt_ctx *, double *tflops);
+
+const char *lt_last_error(void);
+const char *lt_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -129,7 +129,8 @@ def from_arrays(vertices, *, kd=(0.6, 0.6, 0.6), tri_mat=None, materials=None, l
     v = np.ascontiguousarray(vertices, dtype=np.float64)
     e1, e2 = v[:, 1] - v[:, 0], v[:, 2] - v[:, 0]
     n = np.cross(e1, e2)
-    n /= np.linalg.norm(n, axis=1, keepdims=True)
+    nl = n.astype(np.longdouble)
+    n /= np.sqrt((nl * nl).sum(axis=1, keepdims=True)).astype(np.float64)   # dnrm2-style single rounding
     N = len(v)
     if base is None:
         raise ValueError("from_arrays needs a base scene providing lights (pass base=pack_scene(...))")

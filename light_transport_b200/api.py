@@ -25,6 +25,14 @@ def _f64(v):
     return np.ascontiguousarray(v, dtype=np.float64)
 
 
+def _norm(v):
+    """``np.linalg.norm`` as the reference's jit-compiled constructor evaluates it: numba lowers it to
+    BLAS dnrm2, whose x86-64 kernel accumulates in extended precision and rounds once (DESIGN.md,
+    "numerics"); NumPy's own norm rounds after every step and differs in the last bit."""
+    v = np.asarray(v, dtype=np.longdouble)
+    return float(np.sqrt(np.sum(v * v)))
+
+
 class Color:
     """R/src/material.py:4-13."""
 
@@ -66,7 +74,7 @@ class PreComputedTriangle:
         self.edge_1 = self.vertex_2 - self.vertex_1
         self.edge_2 = self.vertex_3 - self.vertex_1
         n = np.cross(self.edge_1[:3], self.edge_2[:3])
-        self.normal = np.append(n / np.linalg.norm(n), 0.0)
+        self.normal = np.append(n / _norm(n), 0.0)
 
 
 class Light:

@@ -1,0 +1,508 @@
+// lt_api.cu — the C-ABI (include/lt_b200.h): handles, host<->device staging, launches.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+#include <algorithm>
+#include <cmath>
+
+#include "lt_megakernel.cuh"
+#include "lt_host.h"
+
+namespace lt {
+
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+// ---- pointer staging: caller data may live on the host or on the device -------------------------
+static bool is_device_ptr(const void* p) {
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+template <typename T>
+struct InBuf {   // read-only input
+    const T* dev = nullptr;
+    T* owned = nullptr;
+    int init(const T* p, size_t n, cudaStream_t s) {
+        if (!p || n == 0) return LT_OK;
+        if (is_device_ptr(p)) { dev = p; return LT_OK; }
+        LT_CUDA_OK(cudaMalloc(&owned, n * sizeof(T)));
+        LT_CUDA_OK(cudaMemcpyAsync(owned, p, n * sizeof(T), cudaMemcpyHostToDevice, s));
+        dev = owned;
+        return LT_OK;
+    }
+    ~InBuf() { if (owned) cudaFree(owned); }
+};
+template <typename T>
+struct OutBuf {  // output; `accumulate`: host destination receives += instead of =
+    T* dev = nullptr;
+    T* owned = nullptr;
+    T* host = nullptr;
+    size_t n = 0;
+    bool accumulate = false;
+    int init(T* p, size_t n_, bool acc, cudaStream_t s) {
+        if (!p || n_ == 0) return LT_OK;
+        n = n_;
+        accumulate = acc;
+        if (is_device_ptr(p)) { dev = p; return LT_OK; }
+        host = p;
+        LT_CUDA_OK(cudaMalloc(&owned, n * sizeof(T)));
+        if (acc) LT_CUDA_OK(cudaMemsetAsync(owned, 0, n * sizeof(T), s));
+        dev = owned;
+        return LT_OK;
+    }
+    int finish(cudaStream_t s) {
+        if (!owned) return LT_OK;
+        if (!accumulate) {
+            LT_CUDA_OK(cudaMemcpyAsync(host, owned, n * sizeof(T), cudaMemcpyDeviceToHost, s));
+            LT_CUDA_OK(cudaStreamSynchronize(s));
+        } else {
+            std::vector<T> tmp(n);
+            LT_CUDA_OK(cudaMemcpyAsync(tmp.data(), owned, n * sizeof(T), cudaMemcpyDeviceToHost, s));
+            LT_CUDA_OK(cudaStreamSynchronize(s));
+            for (size_t i = 0; i < n; ++i) host[i] += tmp[i];
+        }
+        return LT_OK;
+    }
+    ~OutBuf() { if (owned) cudaFree(owned); }
+};
+
+template <typename T>
+static int upload(T** dst, const std::vector<T>& v) {
+    if (*dst) { cudaFree(*dst); *dst = nullptr; }
+    if (v.empty()) return LT_OK;
+    LT_CUDA_OK(cudaMalloc(dst, v.size() * sizeof(T)));
+    LT_CUDA_OK(cudaMemcpy(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return LT_OK;
+}
+
+template <typename R>
+static void fill_view(const lt_scene* s, SceneView<R>& v) {
+    const SceneArrays<R>& a = s->arrays<R>();
+    v.tris = a.tris; v.mats = a.mats; v.lights = a.lights; v.cnodes = a.cnodes;
+    v.cleaves = reinterpret_cast<const CompatLeaf*>(a.cleaves);
+    v.lbvh = s->lbvh_nodes;
+    v.n_tris = s->n_tris; v.n_mats = s->n_mats; v.n_lights = s->n_lights;
+    v.n_cnodes = s->n_cnodes; v.n_cleaves = s->n_cleaves; v.n_lbvh_nodes = s->n_lbvh_nodes;
+}
+
+template <typename R>
+static int build_scene_arrays(lt_scene* s, const lt_scene_desc* d) {
+    std::vector<TriRec<R>> tris(d->n_tris);
+    for (int i = 0; i < d->n_tris; ++i) {
+        TriRec<R>& t = tris[i];
+        memset(&t, 0, sizeof t);
+        for (int c = 0; c < 3; ++c) {
+            double a = d->tri_v0[3 * i + c], b = d->tri_v1[3 * i + c], cc = d->tri_v2[3 * i + c];
+            t.v0[c] = (R)a;
+            t.ab[c] = (R)(b - a);     // R/src/intersects.py:64-65, formed in float64 like the reference
+            t.ac[c] = (R)(cc - a);
+            t.n[c] = (R)d->tri_n[3 * i + c];
+        }
+        t.mat = d->tri_mat[i];
+        t.is_light = d->tri_light ? d->tri_light[i] : 0;
+    }
+    std::vector<MatRec<R>> mats(d->n_mats);
+    for (int i = 0; i < d->n_mats; ++i) {
+        MatRec<R>& m = mats[i];
+        memset(&m, 0, sizeof m);
+        for (int c = 0; c < 3; ++c) m.kd[c] = (R)d->mat_kd[3 * i + c];
+        m.emission = (R)d->mat_emission[i];
+        m.ior = (R)d->mat_ior[i];
+        m.transmission = (R)d->mat_transmission[i];
+        m.flags = d->mat_flags[i];
+    }
+    std::vector<LightRec<R>> lights(d->n_lights);
+    for (int i = 0; i < d->n_lights; ++i) {
+        LightRec<R>& l = lights[i];
+        memset(&l, 0, sizeof l);
+        for (int c = 0; c < 3; ++c) {
+            l.pos[c] = (R)d->light_pos[3 * i + c];
+            l.n[c] = (R)d->light_n[3 * i + c];
+            l.lekd[c] = (R)d->light_lekd[3 * i + c];
+        }
+        l.area = (R)d->light_area[i];
+    }
+    SceneArrays<R>& a = s->arrays<R>();
+    int rc;
+    if ((rc = upload(&a.tris, tris))) return rc;
+    if ((rc = upload(&a.mats, mats))) return rc;
+    if ((rc = upload(&a.lights, lights))) return rc;
+    return LT_OK;
+}
+
+template <typename R>
+static int build_compat_arrays(lt_scene* s, const lt_node_desc* d) {
+    std::vector<CompatNode<R>> nodes(d->n_nodes), leaves;
+    for (int i = 0; i < d->n_nodes; ++i) {
+        CompatNode<R>& n = nodes[i];
+        for (int c = 0; c < 3; ++c) { n.bmin[c] = (R)d->bmin[3 * i + c]; n.bmax[c] = (R)d->bmax[3 * i + c]; }
+        n.prim_off = d->prim_off[i]; n.second = d->second[i]; n.n_prims = d->n_prims[i]; n.axis = d->axis[i];
+        if (n.n_prims <= 0 && (n.axis < 0 || n.axis > 2)) n.axis = 0;
+    }
+    for (int i = d->n_nodes - 1; i >= 0; --i)
+        if (nodes[i].n_prims > 0) { CompatNode<R> l = nodes[i]; l.second = i; leaves.push_back(l); }
+    SceneArrays<R>& a = s->arrays<R>();
+    int rc;
+    if ((rc = upload(&a.cnodes, nodes))) return rc;
+    if ((rc = upload(&a.cleaves, leaves))) return rc;
+    s->n_cnodes = d->n_nodes;
+    s->n_cleaves = (int)leaves.size();
+    return LT_OK;
+}
+
+static size_t staged_bytes(const lt_scene* s, int trav, int real) {
+    size_t r = real == LT_REAL_F64 ? 8 : 4;
+    auto al = [](size_t x) { return (x + 15) / 16 * 16; };
+    size_t tri = r == 8 ? sizeof(TriRec<double>) : sizeof(TriRec<float>);
+    size_t mat = r == 8 ? sizeof(MatRec<double>) : sizeof(MatRec<float>);
+    size_t nod = r == 8 ? sizeof(CompatNode<double>) : sizeof(CompatNode<float>);
+    if (trav == LT_TRAV_LBVH) return 0;
+    size_t b = al(tri * s->n_tris) + al(mat * s->n_mats);
+    if (trav == LT_TRAV_COMPAT) b += al(nod * s->n_cnodes) + al(nod * s->n_cleaves);
+    return b;
+}
+
+static int check_traversal(const lt_scene* s, int trav) {
+    if (trav == LT_TRAV_COMPAT) {
+        if (s->n_cnodes == 0) { set_error("COMPAT traversal needs lt_scene_set_compat_bvh"); return LT_E_NO_BVH; }
+    } else if (trav == LT_TRAV_LBVH) {
+        if (!s->lbvh_nodes && s->n_tris > 1) { set_error("LBVH traversal needs lt_bvh_build"); return LT_E_NO_BVH; }
+    } else if (trav != LT_TRAV_NEAREST) {
+        set_error("unknown traversal %d", trav);
+        return LT_E_INVALID;
+    }
+    return LT_OK;
+}
+
+template <typename R>
+static int do_intersect(lt_scene* s, int traversal, const double* o, const double* d, int64_t n, int32_t* prim_out, double* t_out,
+                        lt_counters* c) {
+    lt_ctx* ctx = s->ctx;
+    cudaStream_t st = ctx->stream;
+    InBuf<double> bo, bd;
+    OutBuf<int32_t> bp;
+    OutBuf<double> bt;
+    int rc;
+    if ((rc = bo.init(o, (size_t)n * 3, st)) || (rc = bd.init(d, (size_t)n * 3, st)) || (rc = bp.init(prim_out, (size_t)n, false, st)) ||
+        (rc = bt.init(t_out, (size_t)n, false, st)))
+        return rc;
+    LT_CUDA_OK(cudaMemsetAsync(ctx->d_counters, 0, sizeof(lt_counters), st));
+    IntersectParams<R> P;
+    fill_view<R>(s, P.S);
+    P.o = bo.dev; P.d = bd.dev; P.n = n; P.prim = bp.dev; P.t = bt.dev;
+    P.counters = reinterpret_cast<unsigned long long*>(ctx->d_counters);
+    P.eps = 0.000001;
+    P.traversal = traversal;
+    int grid = (int)std::min<int64_t>((n + LT_BLOCK - 1) / LT_BLOCK, (int64_t)ctx->prop.multiProcessorCount * 16);
+    if (grid < 1) grid = 1;
+    if (n > 0 && (rc = launch_intersect<R>(P, s->compat_words, grid, st))) return rc;
+    if ((rc = bp.finish(st)) || (rc = bt.finish(st))) return rc;
+    LT_CUDA_OK(cudaStreamSynchronize(st));
+    if (c) {
+        LT_CUDA_OK(cudaMemcpy(c, ctx->d_counters, sizeof(lt_counters), cudaMemcpyDeviceToHost));
+        c->rays_ext = (uint64_t)n;
+    }
+    return LT_OK;
+}
+
+template <typename R>
+static int do_render(lt_scene* s, const lt_render_params* p, const double* rand0, const double* rand1, const int32_t* light_idx,
+                     double* film_sum, double* samples_out, lt_counters* c) {
+    lt_ctx* ctx = s->ctx;
+    cudaStream_t st = ctx->stream;
+    const int W = p->width, H = p->height, D = p->max_depth;
+    const int64_t pix0 = p->pixel0, pix1 = (p->pixel1 > p->pixel0) ? p->pixel1 : (int64_t)W * H;
+    const int ns = p->s1 - p->s0;
+    const size_t npix_all = (size_t)W * H;
+    InBuf<double> b0, b1;
+    InBuf<int32_t> bl;
+    OutBuf<double> bf, bs;
+    int rc;
+    if ((rc = b0.init(rand0, npix_all * p->spp * D, st)) || (rc = b1.init(rand1, npix_all * p->spp * D, st)) ||
+        (rc = bl.init(light_idx, npix_all * p->spp * (size_t)p->n_light_idx, st)) || (rc = bf.init(film_sum, npix_all * 3, true, st)) ||
+        (rc = bs.init(samples_out, npix_all * ns * 3, false, st)))
+        return rc;
+    if (bs.owned) LT_CUDA_OK(cudaMemsetAsync(bs.owned, 0, npix_all * ns * 3 * sizeof(double), st));
+    LT_CUDA_OK(cudaMemsetAsync(ctx->d_counters, 0, sizeof(lt_counters), st));
+
+    WalkParams<R> P;
+    memset(&P, 0, sizeof P);
+    fill_view<R>(s, P.S);
+    P.width = W; P.height = H; P.spp = p->spp; P.s0 = p->s0; P.ns = ns; P.max_depth = D;
+    P.rr_start = p->rr_start; P.n_light_idx = p->n_light_idx; P.semantics = p->semantics; P.traversal = p->traversal;
+    P.pixel0 = (int32_t)pix0;
+    P.total_paths = (pix1 - pix0) * ns;
+    P.rr_floor = p->rr_floor; P.eps = p->eps;
+    for (int k = 0; k < 3; ++k) P.cam[k] = p->camera[k];
+    P.f_distance = p->f_distance;
+    // Scene.top/bottom/left/right (R/src/scene.py:60-64) and numba's np.linspace step
+    const double aspect = (double)W / (double)H;
+    P.top = 1 / aspect; P.bottom = -1 / aspect;
+    P.step_y = H > 1 ? (P.bottom - P.top) / (double)(H - 1) : 0.0;
+    P.step_x = W > 1 ? (1.0 - (-1.0)) / (double)(W - 1) : 0.0;
+    P.seed = p->seed;
+    P.rand0 = b0.dev; P.rand1 = b1.dev; P.light_idx = bl.dev;
+    P.film = bf.dev; P.samples = bs.dev;
+    P.counters = reinterpret_cast<unsigned long long*>(ctx->d_counters);
+
+    const size_t smem = staged_bytes(s, p->traversal, p->real);
+    if (smem > (size_t)ctx->prop.sharedMemPerBlockOptin) {
+        set_error("scene needs %zu B of shared memory for traversal %d; use LT_TRAV_LBVH for large scenes", smem, p->traversal);
+        return LT_E_OVERFLOW;
+    }
+    int regs = 0, local_bytes = 0, bps = 0;
+    if ((rc = walk_kernel_attrs<R>(p->traversal, p->semantics, s->compat_words, &regs, &local_bytes, &bps, smem))) return rc;
+    if (bps < 1) bps = 1;
+    int grid = ctx->prop.multiProcessorCount * bps;
+    int64_t nwarps = (int64_t)grid * LT_BLOCK / 32;
+    int64_t ppw = p->paths_per_warp;
+    if (ppw <= 0) {
+        ppw = P.total_paths / (nwarps * 6);
+        ppw = std::max<int64_t>(64, std::min<int64_t>(ppw, 4096));
+        ppw = (ppw + 31) / 32 * 32;
+    }
+    P.paths_per_warp = (int32_t)ppw;
+    int64_t granules = (P.total_paths + ppw - 1) / ppw;
+    if (granules < nwarps) { grid = (int)std::max<int64_t>(1, (granules * 32 + LT_BLOCK - 1) / LT_BLOCK); nwarps = (int64_t)grid * LT_BLOCK / 32; }
+    // spilled frame storage for deep REFERENCE walks
+    P.arena = nullptr; P.arena_frames = 0; P.arena_threads = (int64_t)grid * LT_BLOCK;
+    if (p->semantics == LT_SEM_REFERENCE && D - 1 > LT_LOCAL_FRAMES) {
+        P.arena_frames = D - 1 - LT_LOCAL_FRAMES;
+        size_t bytes = (size_t)P.arena_frames * 7 * (size_t)P.arena_threads * sizeof(R);
+        if (bytes > ctx->arena_bytes) {
+            if (ctx->arena) cudaFree(ctx->arena);
+            ctx->arena = nullptr; ctx->arena_bytes = 0;
+            LT_CUDA_OK(cudaMalloc(&ctx->arena, bytes));
+            ctx->arena_bytes = bytes;
+        }
+        P.arena = reinterpret_cast<R*>(ctx->arena);
+    }
+    LT_CUDA_OK(cudaEventRecord(ctx->ev0, st));
+    if (P.total_paths > 0 && (rc = launch_walk<R>(P, s->compat_words, grid, smem, st))) return rc;
+    LT_CUDA_OK(cudaEventRecord(ctx->ev1, st));
+    if ((rc = bf.finish(st)) || (rc = bs.finish(st))) return rc;
+    LT_CUDA_OK(cudaStreamSynchronize(st));
+    lt_counters hc;
+    LT_CUDA_OK(cudaMemcpy(&hc, ctx->d_counters, sizeof hc, cudaMemcpyDeviceToHost));
+    float ms = 0;
+    LT_CUDA_OK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    hc.kernel_ns = (uint64_t)(ms * 1e6);
+    hc.launches = 1;
+    if (c) *c = hc;
+    if (hc.frame_overflow) { set_error("frame stack overflow on %llu pushes", (unsigned long long)hc.frame_overflow); return LT_E_OVERFLOW; }
+    return LT_OK;
+}
+
+__global__ void finalize_kernel(const double* film, int64_t n, double inv_spp, double* image) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double v = film[i] * inv_spp;   // color / spp; np.clip(color, 0, 1)
+        image[i] = v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v);
+    }
+}
+__global__ void finalize_div_kernel(const double* film, int64_t n, double spp, double* image) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double v = film[i] / spp;       // R/src/path_tracing.py:304: color/scene.number_of_samples
+        image[i] = v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v);
+    }
+}
+
+__global__ void fma_peak_kernel(float* out, int iters) {
+    float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const float m = 0.999f, b = 1e-3f;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fmaf(a0, m, b); a1 = fmaf(a1, m, b); a2 = fmaf(a2, m, b); a3 = fmaf(a3, m, b);
+        a4 = fmaf(a4, m, b); a5 = fmaf(a5, m, b); a6 = fmaf(a6, m, b); a7 = fmaf(a7, m, b);
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+}  // namespace lt
+
+using namespace lt;
+
+extern "C" {
+
+const char* lt_last_error(void) { return g_err; }
+const char* lt_version(void) { return "lt_b200 0.1 (sm_100a)"; }
+
+int lt_init(int device, lt_ctx** out) {
+    if (!out) { set_error("lt_init: out is NULL"); return LT_E_INVALID; }
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        set_error("no CUDA device available (%s); this library has no CPU fallback", cudaGetErrorString(e));
+        cudaGetLastError();
+        return LT_E_CUDA;
+    }
+    if (device < 0 || device >= n) { set_error("device %d out of range (have %d)", device, n); return LT_E_INVALID; }
+    LT_CUDA_OK(cudaSetDevice(device));
+    lt_ctx* c = new lt_ctx();
+    c->device = device;
+    LT_CUDA_OK(cudaGetDeviceProperties(&c->prop, device));
+    LT_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    LT_CUDA_OK(cudaMalloc(&c->d_counters, sizeof(lt_counters)));
+    LT_CUDA_OK(cudaEventCreate(&c->ev0));
+    LT_CUDA_OK(cudaEventCreate(&c->ev1));
+    *out = c;
+    return LT_OK;
+}
+
+void lt_destroy(lt_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->arena) cudaFree(c->arena);
+    if (c->d_counters) cudaFree(c->d_counters);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int lt_device_info(lt_ctx* c, int32_t* sm_count, int32_t* clock_khz, int64_t* global_mem, int32_t* cc_major, int32_t* cc_minor) {
+    if (!c) { set_error("null ctx"); return LT_E_INVALID; }
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, c->device);
+    if (sm_count) *sm_count = c->prop.multiProcessorCount;
+    if (clock_khz) *clock_khz = khz;
+    if (global_mem) *global_mem = (int64_t)c->prop.totalGlobalMem;
+    if (cc_major) *cc_major = c->prop.major;
+    if (cc_minor) *cc_minor = c->prop.minor;
+    return LT_OK;
+}
+
+int lt_scene_create(lt_ctx* ctx, const lt_scene_desc* d, lt_scene** out) {
+    if (!ctx || !d || !out) { set_error("lt_scene_create: null argument"); return LT_E_INVALID; }
+    *out = nullptr;
+    if (d->n_tris <= 0 || d->n_mats <= 0 || d->n_lights < 0) { set_error("scene needs >=1 triangle and material"); return LT_E_INVALID; }
+    for (int i = 0; i < d->n_tris; ++i)
+        if (d->tri_mat[i] < 0 || d->tri_mat[i] >= d->n_mats) { set_error("tri_mat[%d]=%d out of range", i, d->tri_mat[i]); return LT_E_INVALID; }
+    LT_CUDA_OK(cudaSetDevice(ctx->device));
+    lt_scene* s = new lt_scene();
+    s->ctx = ctx;
+    s->n_tris = d->n_tris; s->n_mats = d->n_mats; s->n_lights = d->n_lights;
+    s->h_v0.assign(d->tri_v0, d->tri_v0 + 3 * (size_t)d->n_tris);
+    s->h_v1.assign(d->tri_v1, d->tri_v1 + 3 * (size_t)d->n_tris);
+    s->h_v2.assign(d->tri_v2, d->tri_v2 + 3 * (size_t)d->n_tris);
+    int rc;
+    if ((rc = build_scene_arrays<float>(s, d)) || (rc = build_scene_arrays<double>(s, d))) { lt_scene_destroy(s); return rc; }
+    *out = s;
+    return LT_OK;
+}
+
+void lt_scene_destroy(lt_scene* s) {
+    if (!s) return;
+    cudaSetDevice(s->ctx->device);
+    s->f32.release();
+    s->f64.release();
+    if (s->lbvh_nodes) cudaFree(s->lbvh_nodes);
+    delete s;
+}
+
+int lt_scene_set_compat_bvh(lt_scene* s, const lt_node_desc* d) {
+    if (!s || !d || d->n_nodes <= 0) { set_error("lt_scene_set_compat_bvh: bad argument"); return LT_E_INVALID; }
+    if (d->n_nodes > 128) { set_error("COMPAT traversal supports at most 128 nodes (got %d); use LT_TRAV_LBVH", d->n_nodes); return LT_E_INVALID; }
+    for (int i = 0; i < d->n_nodes; ++i) {
+        if (d->n_prims[i] > 0) {
+            if (d->prim_off[i] < 0 || d->prim_off[i] + d->n_prims[i] > s->n_tris) { set_error("node %d: primitive range outside the scene", i); return LT_E_INVALID; }
+            // Q9b: visited[leaf_idx] with leaf_idx >= len(nodes) raises IndexError in the reference
+            if (d->prim_off[i] + d->n_prims[i] > d->n_nodes) {
+                set_error("COMPAT undefined: leaf %d holds primitive index %d >= node count %d (the reference raises IndexError)", i,
+                          d->prim_off[i] + d->n_prims[i] - 1, d->n_nodes);
+                return LT_E_COMPAT_UNDEFINED;
+            }
+        } else {
+            if (d->axis[i] < 0 || d->axis[i] > 2) { set_error("interior node %d: axis %d", i, d->axis[i]); return LT_E_INVALID; }
+            if (d->second[i] <= i || d->second[i] >= d->n_nodes || i + 1 >= d->n_nodes) { set_error("interior node %d: bad child offset", i); return LT_E_INVALID; }
+        }
+    }
+    LT_CUDA_OK(cudaSetDevice(s->ctx->device));
+    int rc;
+    if ((rc = build_compat_arrays<float>(s, d)) || (rc = build_compat_arrays<double>(s, d))) return rc;
+    s->compat_words = d->n_nodes <= 64 ? 1 : 2;
+    return LT_OK;
+}
+
+int lt_intersect(lt_scene* s, int traversal, int real, const double* o, const double* d, int64_t n, int32_t* prim_out, double* t_out,
+                 lt_counters* c) {
+    if (!s || n < 0 || (n > 0 && (!o || !d || !prim_out || !t_out))) { set_error("lt_intersect: bad argument"); return LT_E_INVALID; }
+    LT_CUDA_OK(cudaSetDevice(s->ctx->device));
+    int rc = check_traversal(s, traversal);
+    if (rc) return rc;
+    if (real == LT_REAL_F64) return do_intersect<double>(s, traversal, o, d, n, prim_out, t_out, c);
+    if (real == LT_REAL_F32) return do_intersect<float>(s, traversal, o, d, n, prim_out, t_out, c);
+    set_error("unknown real %d", real);
+    return LT_E_INVALID;
+}
+
+int lt_render(lt_scene* s, const lt_render_params* p, const double* rand0, const double* rand1, const int32_t* light_idx, double* film_sum,
+              double* samples_out, lt_counters* c) {
+    if (!s || !p || !film_sum) { set_error("lt_render: null argument"); return LT_E_INVALID; }
+    if (p->width <= 0 || p->height <= 0 || p->spp <= 0 || p->s0 < 0 || p->s1 > p->spp || p->s1 < p->s0 || p->max_depth < 0) {
+        set_error("lt_render: bad film/sample range");
+        return LT_E_INVALID;
+    }
+    if ((rand0 == nullptr) != (rand1 == nullptr)) { set_error("rand0 and rand1 must both be given or both be NULL"); return LT_E_INVALID; }
+    if (light_idx && p->n_light_idx <= 0) { set_error("light_idx given but n_light_idx == 0"); return LT_E_INVALID; }
+    if (s->n_lights <= 0) { set_error("scene has no Light (next-event estimation needs one)"); return LT_E_INVALID; }
+    if (p->semantics != LT_SEM_REFERENCE && p->semantics != LT_SEM_ITERATIVE) { set_error("unknown semantics"); return LT_E_INVALID; }
+    if (p->scheduler != LT_SCHED_MEGAKERNEL) { set_error("scheduler %d not available in this build", p->scheduler); return LT_E_INVALID; }
+    if (p->pixel1 > p->width * p->height || p->pixel0 < 0) { set_error("bad pixel range"); return LT_E_INVALID; }
+    LT_CUDA_OK(cudaSetDevice(s->ctx->device));
+    int rc = check_traversal(s, p->traversal);
+    if (rc) return rc;
+    if (p->real == LT_REAL_F64) return do_render<double>(s, p, rand0, rand1, light_idx, film_sum, samples_out, c);
+    if (p->real == LT_REAL_F32) return do_render<float>(s, p, rand0, rand1, light_idx, film_sum, samples_out, c);
+    set_error("unknown real %d", p->real);
+    return LT_E_INVALID;
+}
+
+int lt_film_finalize(lt_ctx* ctx, const double* film_sum, int64_t n, int64_t spp_total, double* image_out) {
+    if (!ctx || !film_sum || !image_out || n < 0 || spp_total <= 0) { set_error("lt_film_finalize: bad argument"); return LT_E_INVALID; }
+    LT_CUDA_OK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    InBuf<double> in;
+    OutBuf<double> out;
+    int rc;
+    if ((rc = in.init(film_sum, (size_t)n, st)) || (rc = out.init(image_out, (size_t)n, false, st))) return rc;
+    int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->prop.multiProcessorCount * 8);
+    if (n > 0) finalize_div_kernel<<<std::max(grid, 1), 256, 0, st>>>(in.dev, n, (double)spp_total, out.dev);
+    LT_CUDA_OK(cudaGetLastError());
+    if ((rc = out.finish(st))) return rc;
+    LT_CUDA_OK(cudaStreamSynchronize(st));
+    return LT_OK;
+}
+
+int lt_measure_fp32_peak(lt_ctx* ctx, double* tflops) {
+    if (!ctx || !tflops) { set_error("null argument"); return LT_E_INVALID; }
+    LT_CUDA_OK(cudaSetDevice(ctx->device));
+    const int blocks = ctx->prop.multiProcessorCount * 8, threads = 256, iters = 1 << 15;
+    float* d = nullptr;
+    LT_CUDA_OK(cudaMalloc(&d, (size_t)blocks * threads * sizeof(float)));
+    fma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(d, 1 << 10);
+    double best = 0;
+    for (int rep = 0; rep < 5; ++rep) {
+        LT_CUDA_OK(cudaEventRecord(ctx->ev0, ctx->stream));
+        fma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(d, iters);
+        LT_CUDA_OK(cudaEventRecord(ctx->ev1, ctx->stream));
+        LT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+        float ms = 0;
+        LT_CUDA_OK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        double tf = 2.0 * 8.0 * iters * (double)blocks * threads / (ms * 1e-3) / 1e12;
+        best = std::max(best, tf);
+    }
+    cudaFree(d);
+    *tflops = best;
+    return LT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,53 @@
+// lt_host.h — host-side handle definitions behind the opaque lt_ctx / lt_scene of include/lt_b200.h.
+#pragma once
+#include <vector>
+
+#include "lt_scene.cuh"
+
+namespace lt {
+
+template <typename R>
+struct SceneArrays {
+    TriRec<R>* tris = nullptr;
+    MatRec<R>* mats = nullptr;
+    LightRec<R>* lights = nullptr;
+    CompatNode<R>* cnodes = nullptr;
+    CompatNode<R>* cleaves = nullptr;   // leaves in descending node order; .second = node index
+    void release() {
+        if (tris) cudaFree(tris);
+        if (mats) cudaFree(mats);
+        if (lights) cudaFree(lights);
+        if (cnodes) cudaFree(cnodes);
+        if (cleaves) cudaFree(cleaves);
+        tris = nullptr; mats = nullptr; lights = nullptr; cnodes = nullptr; cleaves = nullptr;
+    }
+};
+
+}  // namespace lt
+
+struct lt_ctx {
+    int device = 0;
+    cudaDeviceProp prop;
+    cudaStream_t stream = nullptr;
+    lt_counters* d_counters = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    void* arena = nullptr;
+    size_t arena_bytes = 0;
+};
+
+struct lt_scene {
+    lt_ctx* ctx = nullptr;
+    int n_tris = 0, n_mats = 0, n_lights = 0;
+    int n_cnodes = 0, n_cleaves = 0, compat_words = 1;
+    int n_lbvh_nodes = 0;
+    lt::SceneArrays<float> f32;
+    lt::SceneArrays<double> f64;
+    lt::LbvhNode* lbvh_nodes = nullptr;
+    std::vector<double> h_v0, h_v1, h_v2;   // host copy of the vertices (LBVH build input)
+    template <typename R> lt::SceneArrays<R>& arrays();
+    template <typename R> const lt::SceneArrays<R>& arrays() const;
+};
+template <> inline lt::SceneArrays<float>& lt_scene::arrays<float>() { return f32; }
+template <> inline lt::SceneArrays<double>& lt_scene::arrays<double>() { return f64; }
+template <> inline const lt::SceneArrays<float>& lt_scene::arrays<float>() const { return f32; }
+template <> inline const lt::SceneArrays<double>& lt_scene::arrays<double>() const { return f64; }

@@ -1,0 +1,217 @@
+// lt_megakernel.cuh — persistent-warp path tracer.
+//
+// Scheduling: the job is the linear range of work indices q = (pixel - pixel0) * ns + (s - s0).
+// Warps take granules of `paths_per_warp` consecutive indices round-robin (persistent grid, a few
+// CTAs per SM).  Inside a granule the lanes REGENERATE: a lane whose path has ended takes the next
+// index of the granule.  The next index is warp-uniform state, handed out with ballot + popc prefix
+// ranks — a warp-aggregated fetch that needs no atomic at all because the counter never leaves the
+// warp.  Consecutive indices are samples of the same pixel, so lanes stay coherent on the camera
+// segment and a lane's film contribution accumulates in registers; it is flushed (fp64 atomicAdd,
+// warp-aggregated across lanes holding the same pixel at granule end) only when the lane's pixel
+// changes.  Small scenes (COMPAT / NEAREST) are staged in shared memory once per CTA.
+#pragma once
+#include "lt_walk.cuh"
+
+namespace lt {
+
+#define LT_BLOCK 128
+
+template <typename T>
+LT_DEVINL const T* stage_array(char*& cursor, const T* src, int n) {
+    T* dst = reinterpret_cast<T*>(cursor);
+    const int4* s4 = reinterpret_cast<const int4*>(src);
+    int4* d4 = reinterpret_cast<int4*>(dst);
+    int n16 = (int)((sizeof(T) * (size_t)n) / 16);
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) d4[i] = __ldg(s4 + i);
+    cursor += ((sizeof(T) * (size_t)n + 15) / 16) * 16;
+    return dst;
+}
+
+LT_DEVINL void flush_film(double* film, int64_t pix, double acc[3]) {
+    if (pix >= 0 && (acc[0] != 0.0 || acc[1] != 0.0 || acc[2] != 0.0)) {
+        atomicAdd(film + pix * 3 + 0, acc[0]);
+        atomicAdd(film + pix * 3 + 1, acc[1]);
+        atomicAdd(film + pix * 3 + 2, acc[2]);
+    }
+    acc[0] = acc[1] = acc[2] = 0.0;
+}
+
+// granule-end flush: lanes holding the same pixel are summed by the lowest such lane (shuffles),
+// which then issues the atomics — one triple per distinct pixel per warp.
+LT_DEVINL void flush_film_warp(double* film, int64_t pix, double acc[3]) {
+    const unsigned full = 0xffffffffu;
+    int lane = threadIdx.x & 31;
+    unsigned same = __match_any_sync(full, pix);
+    bool leader = (__ffs(same) - 1) == lane;
+    double s0 = 0, s1 = 0, s2 = 0;
+    for (int src = 0; src < 32; ++src) {
+        double a = __shfl_sync(full, acc[0], src), b = __shfl_sync(full, acc[1], src), c = __shfl_sync(full, acc[2], src);
+        if ((same >> src) & 1u) { s0 += a; s1 += b; s2 += c; }
+    }
+    if (leader) { acc[0] = s0; acc[1] = s1; acc[2] = s2; flush_film(film, pix, acc); }
+    acc[0] = acc[1] = acc[2] = 0.0;
+}
+
+template <typename R, int TRAV, int SEM, int NW>
+__global__ void __launch_bounds__(LT_BLOCK) walk_megakernel(const WalkParams<R> P) {
+    extern __shared__ __align__(16) char smem[];
+    const TriRec<R>* tris = P.S.tris;
+    const MatRec<R>* mats = P.S.mats;
+    const CompatNode<R>* cnodes = P.S.cnodes;
+    const CompatNode<R>* cleaves = reinterpret_cast<const CompatNode<R>*>(P.S.cleaves);
+    if (TRAV != LT_TRAV_LBVH) {
+        char* cur = smem;
+        tris = stage_array(cur, P.S.tris, P.S.n_tris);
+        mats = stage_array(cur, P.S.mats, P.S.n_mats);
+        if (TRAV == LT_TRAV_COMPAT) {
+            cnodes = stage_array(cur, P.S.cnodes, P.S.n_cnodes);
+            cleaves = stage_array(cur, reinterpret_cast<const CompatNode<R>*>(P.S.cleaves), P.S.n_cleaves);
+        }
+        __syncthreads();
+    }
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t gwarp = gtid >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t ppw = P.paths_per_warp;
+    const R eps = (R)P.eps;
+
+    Frame<R> frames[SEM == LT_SEM_REFERENCE ? LT_LOCAL_FRAMES : 1];
+    Lane<R> ln;
+    ln.qtype = 0;
+    Stats st;
+    uint32_t n_ext = 0, n_shadow = 0, n_paths = 0, lidx_overflow = 0, frame_overflow = 0, max_frames = 0;
+    uint32_t lane_steps = 0, warp_iters = 0;
+    double acc[3] = {0, 0, 0};
+    int64_t acc_pix = -1;
+
+    for (int64_t g = gwarp; g * ppw < P.total_paths; g += nwarps) {
+        int64_t next = g * ppw;
+        const int64_t end = min(P.total_paths, next + ppw);
+        for (;;) {
+            // ---- regeneration: idle lanes take the next indices of the granule
+            bool need = ln.qtype == 0;
+            unsigned m = __ballot_sync(full, need);
+            if (m) {
+                int rank = __popc(m & ((1u << lane) - 1u));
+                int64_t mine = next + rank;
+                next += __popc(m);
+                if (need && mine < end) {
+                    int64_t pix = P.pixel0 + mine / P.ns;
+                    if (pix != acc_pix) { flush_film(P.film, acc_pix, acc); acc_pix = pix; }
+                    start_path<R>(P, ln, mine);
+                    if (ln.qtype == 0) {   // max_depth == 0
+                        n_paths++;
+                        if (P.samples) { double* o = P.samples + (size_t)(pix * P.ns + mine % P.ns) * 3; o[0] = o[1] = o[2] = 0; }
+                    }
+                }
+            }
+            bool active = ln.qtype != 0;
+            unsigned am = __ballot_sync(full, active);
+            if (!am) break;
+            warp_iters++;
+            if (active) {
+                lane_steps++;
+                // ---- the one ray query of this iteration
+                int prim;
+                R t;
+                const bool anyhit = ln.qtype == 2;
+                if (TRAV == LT_TRAV_COMPAT)
+                    compat_query<R, NW>(cnodes, cleaves, P.S.n_cleaves, tris, ln.o, ln.d, eps, ln.tlimit, anyhit, prim, t, st);
+                else if (TRAV == LT_TRAV_NEAREST)
+                    nearest_query<R>(tris, P.S.n_tris, ln.o, ln.d, eps, ln.tlimit, anyhit, prim, t, st);
+                else
+                    lbvh_query<R>(P.S.lbvh, tris, P.S.n_tris, ln.o, ln.d, eps, ln.tlimit, anyhit, prim, t, st);
+                bool alive;
+                if (ln.qtype == 1) {
+                    n_ext++;
+                    alive = shade_extension<R, SEM>(P, ln, frames, gtid, prim, t, tris, mats, lidx_overflow);
+                } else {
+                    n_shadow++;
+                    alive = shade_shadow<R, SEM>(P, ln, frames, gtid, prim >= 0, frame_overflow, max_frames);
+                }
+                if (!alive) {
+                    // ---- tally (R/src/path_tracing.py:297-298)
+                    n_paths++;
+                    acc[0] += (double)ln.L.x; acc[1] += (double)ln.L.y; acc[2] += (double)ln.L.z;
+                    if (P.samples) {
+                        double* o = P.samples + (size_t)((P.pixel0 + ln.q / P.ns) * P.ns + ln.q % P.ns) * 3;
+                        o[0] = (double)ln.L.x; o[1] = (double)ln.L.y; o[2] = (double)ln.L.z;
+                    }
+                    ln.qtype = 0;
+                }
+            }
+        }
+        flush_film_warp(P.film, acc_pix, acc);
+        acc_pix = -1;
+    }
+    // ---- counters: warp-reduced, one atomic per warp and field
+    if (P.counters) {
+        unsigned long long v[10] = {n_paths, n_ext, n_shadow, st.box_tests, st.tri_tests, 0, lidx_overflow, frame_overflow,
+                                    lane_steps, (unsigned long long)warp_iters};
+#pragma unroll
+        for (int k = 0; k < 10; ++k) {
+            if (k == 5) continue;
+            unsigned long long x = v[k];
+            if (k == 9) { x = lane == 0 ? x * 32ull : 0ull; }
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(full, x, o);
+            if (lane == 0 && x) atomicAdd(P.counters + k, x);
+        }
+        if (SEM == LT_SEM_REFERENCE) {
+            uint32_t mf = max(max_frames, 1u);
+            for (int o = 16; o > 0; o >>= 1) mf = max(mf, __shfl_xor_sync(full, mf, o));
+            if (lane == 0) atomicMax(P.counters + 5, (unsigned long long)mf);
+        } else if (lane == 0 && threadIdx.x == 0 && blockIdx.x == 0) {
+            atomicMax(P.counters + 5, 1ull);
+        }
+    }
+}
+
+// ---- explicit-ray closest-hit kernel behind lt_intersect -------------------------------------------
+template <typename R>
+struct IntersectParams {
+    SceneView<R> S;
+    const double* o;
+    const double* d;
+    int64_t n;
+    int32_t* prim;
+    double* t;
+    unsigned long long* counters;
+    double eps;
+    int32_t traversal;
+};
+
+template <typename R, int TRAV, int NW>
+__global__ void __launch_bounds__(LT_BLOCK) intersect_kernel(const IntersectParams<R> P) {
+    Stats st;
+    const unsigned full = 0xffffffffu;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < P.n; r += (int64_t)gridDim.x * blockDim.x) {
+        V3<R> o = mk<R>((R)P.o[3 * r], (R)P.o[3 * r + 1], (R)P.o[3 * r + 2]);
+        V3<R> d = mk<R>((R)P.d[3 * r], (R)P.d[3 * r + 1], (R)P.d[3 * r + 2]);
+        int prim;
+        R t;
+        if (TRAV == LT_TRAV_COMPAT)
+            compat_query<R, NW>(P.S.cnodes, reinterpret_cast<const CompatNode<R>*>(P.S.cleaves), P.S.n_cleaves, P.S.tris, o, d,
+                                (R)P.eps, Lim<R>::inf(), false, prim, t, st);
+        else if (TRAV == LT_TRAV_NEAREST)
+            nearest_query<R>(P.S.tris, P.S.n_tris, o, d, (R)P.eps, Lim<R>::inf(), false, prim, t, st);
+        else
+            lbvh_query<R>(P.S.lbvh, P.S.tris, P.S.n_tris, o, d, (R)P.eps, Lim<R>::inf(), false, prim, t, st);
+        P.prim[r] = prim;
+        P.t[r] = prim >= 0 ? (double)t : (double)Lim<double>::inf();
+    }
+    if (P.counters) {
+        unsigned long long b = st.box_tests, tt = st.tri_tests;
+        unsigned act = __activemask();
+        (void)full;
+        for (int o = 16; o > 0; o >>= 1) { b += __shfl_xor_sync(act, b, o); tt += __shfl_xor_sync(act, tt, o); }
+        if ((threadIdx.x & 31) == 0) { atomicAdd(P.counters + 3, b); atomicAdd(P.counters + 4, tt); }
+    }
+}
+
+// host-side dispatch, instantiated per R in lt_walk_f32.cu / lt_walk_f64.cu
+template <typename R> int launch_walk(const WalkParams<R>& P, int nw, int grid, size_t smem, cudaStream_t stream);
+template <typename R> int launch_intersect(const IntersectParams<R>& P, int nw, int grid, cudaStream_t stream);
+template <typename R> int walk_kernel_attrs(int trav, int sem, int nw, int* regs, int* local_bytes, int* max_blocks_per_sm, size_t smem);
+
+}  // namespace lt

@@ -1,0 +1,357 @@
+"""Python host side of the drop-in: ``render_scene(scene, primitives, bvh)`` on the GPU.
+
+Mirrors the reference's call (``R/src/path_tracing.py:371-387`` /
+``R/src/path_tracing_old.py:142-171`` / ``R/src/path_tracing_fix1.py:139-169``;
+``R/`` = ``LightTransportSimulator/light_transport/``): same positional arguments, same
+side effect on ``scene.image``, plus keyword-only extensions.  Everything numeric happens in
+``liblt_b200.so`` (C-ABI: ``include/lt_b200.h``) through ``ctypes``; there is NO CPU path —
+a missing library or GPU raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _pack, compat_bvh
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liblt_b200.so")
+
+TRAVERSAL = {"compat": 0, "nearest": 1, "lbvh": 2}
+SEMANTICS = {"reference": 0, "iterative": 1}
+REAL = {"f32": 0, "f64": 1}
+
+PD = C.POINTER(C.c_double)
+PI32 = C.POINTER(C.c_int32)
+PU8 = C.POINTER(C.c_uint8)
+
+
+class LtSceneDesc(C.Structure):
+    _fields_ = [("n_tris", C.c_int32), ("n_mats", C.c_int32), ("n_lights", C.c_int32), ("reserved", C.c_int32),
+                ("tri_v0", PD), ("tri_v1", PD), ("tri_v2", PD), ("tri_n", PD), ("tri_mat", PI32), ("tri_light", PU8),
+                ("mat_kd", PD), ("mat_emission", PD), ("mat_ior", PD), ("mat_transmission", PD), ("mat_flags", PI32),
+                ("light_pos", PD), ("light_n", PD), ("light_lekd", PD), ("light_area", PD)]
+
+
+class LtNodeDesc(C.Structure):
+    _fields_ = [("n_nodes", C.c_int32), ("reserved", C.c_int32), ("bmin", PD), ("bmax", PD), ("prim_off", PI32),
+                ("second", PI32), ("n_prims", PI32), ("axis", PI32)]
+
+
+class LtRenderParams(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("spp", C.c_int32), ("s0", C.c_int32), ("s1", C.c_int32),
+                ("max_depth", C.c_int32), ("semantics", C.c_int32), ("traversal", C.c_int32), ("real", C.c_int32),
+                ("scheduler", C.c_int32), ("rr_start", C.c_int32), ("n_light_idx", C.c_int32),
+                ("rr_floor", C.c_double), ("eps", C.c_double), ("camera", C.c_double * 3), ("f_distance", C.c_double),
+                ("seed", C.c_uint64), ("pixel0", C.c_int32), ("pixel1", C.c_int32), ("paths_per_warp", C.c_int32),
+                ("flags", C.c_int32)]
+
+
+class LtCounters(C.Structure):
+    _fields_ = [(k, C.c_uint64) for k in ("paths", "rays_ext", "rays_shadow", "box_tests", "tri_tests", "max_frames",
+                                          "light_idx_overflow", "frame_overflow", "lane_steps", "lane_slots",
+                                          "kernel_ns", "launches")]
+
+    def as_dict(self):
+        return {k: int(getattr(self, k)) for k, _ in self._fields_}
+
+
+class LtBvhStats(C.Structure):
+    _fields_ = [("n_prims", C.c_int32), ("n_nodes", C.c_int32), ("max_depth", C.c_int32), ("reserved", C.c_int32),
+                ("build_ms", C.c_float), ("sort_ms", C.c_float), ("root_bmin", C.c_double * 3),
+                ("root_bmax", C.c_double * 3), ("sah_cost", C.c_double)]
+
+
+class LtError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"lt_b200 error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    """Load liblt_b200.so (built by ``__graft_entry__.build()`` / ``make -C light_transport_b200/csrc``)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: build it with `make -C light_transport_b200/csrc` "
+                              "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.lt_last_error.restype = C.c_char_p
+        L.lt_version.restype = C.c_char_p
+        for name in ("lt_init", "lt_device_info", "lt_scene_create", "lt_scene_set_compat_bvh", "lt_bvh_build",
+                     "lt_intersect", "lt_render", "lt_film_finalize", "lt_measure_fp32_peak"):
+            getattr(L, name).restype = C.c_int
+        L.lt_destroy.restype = None
+        L.lt_scene_destroy.restype = None
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise LtError(rc, lib().lt_last_error().decode())
+
+
+def _ptr(a, typ):
+    """numpy array, torch CUDA tensor (anything with data_ptr), raw int address, or None → pointer."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(typ)
+    if hasattr(a, "data_ptr"):
+        return C.cast(C.c_void_p(a.data_ptr()), typ)
+    return C.cast(C.c_void_p(int(a)), typ)
+
+
+class Renderer:
+    """A device context plus one uploaded scene (the 'H2D once' half of the boundary)."""
+
+    def __init__(self, packed: _pack.PackedScene, nodes: compat_bvh.CompatNodes | None = None, device: int = 0,
+                 build_lbvh: bool = False):
+        L = lib()
+        self._ctx = C.c_void_p()
+        self._scene = C.c_void_p()
+        _check(L.lt_init(C.c_int(device), C.byref(self._ctx)))
+        f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        i = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        self._keep = dict(tri_v0=f(packed.tri_v0), tri_v1=f(packed.tri_v1), tri_v2=f(packed.tri_v2), tri_n=f(packed.tri_n),
+                          tri_mat=i(packed.tri_mat), tri_light=np.ascontiguousarray(packed.tri_light, dtype=np.uint8),
+                          mat_kd=f(packed.mat_kd), mat_emission=f(packed.mat_emission), mat_ior=f(packed.mat_ior),
+                          mat_transmission=f(packed.mat_transmission), mat_flags=i(packed.mat_flags),
+                          light_pos=f(packed.light_pos), light_n=f(packed.light_n), light_lekd=f(packed.light_lekd),
+                          light_area=f(packed.light_area))
+        d = LtSceneDesc()
+        d.n_tris, d.n_mats, d.n_lights = packed.n_tris, len(packed.mat_flags), packed.n_lights
+        types = dict(LtSceneDesc._fields_)
+        for k, v in self._keep.items():
+            setattr(d, k, _ptr(v, types[k]))
+        _check(L.lt_scene_create(self._ctx, C.byref(d), C.byref(self._scene)))
+        self.packed = packed
+        self.n_lights = packed.n_lights
+        self.has_compat = False
+        self.lbvh_stats = None
+        if nodes is not None:
+            self.set_compat_bvh(nodes)
+        if build_lbvh:
+            self.build_lbvh()
+
+    # -- structures --------------------------------------------------------------------------------
+    def set_compat_bvh(self, nodes: compat_bvh.CompatNodes):
+        d = LtNodeDesc()
+        keep = dict(bmin=np.ascontiguousarray(nodes.bmin, np.float64), bmax=np.ascontiguousarray(nodes.bmax, np.float64),
+                    prim_off=np.ascontiguousarray(nodes.prim_off, np.int32), second=np.ascontiguousarray(nodes.second, np.int32),
+                    n_prims=np.ascontiguousarray(nodes.n_prims, np.int32), axis=np.ascontiguousarray(nodes.axis, np.int32))
+        d.n_nodes = len(nodes)
+        types = dict(LtNodeDesc._fields_)
+        for k, v in keep.items():
+            setattr(d, k, _ptr(v, types[k]))
+        _check(lib().lt_scene_set_compat_bvh(self._scene, C.byref(d)))
+        self.has_compat = True
+
+    def build_lbvh(self):
+        st = LtBvhStats()
+        _check(lib().lt_bvh_build(self._scene, C.c_int(0), C.byref(st)))
+        self.lbvh_stats = dict(n_prims=st.n_prims, n_nodes=st.n_nodes, max_depth=st.max_depth, build_ms=st.build_ms,
+                               sort_ms=st.sort_ms, root_bmin=list(st.root_bmin), root_bmax=list(st.root_bmax))
+        return self.lbvh_stats
+
+    # -- queries -----------------------------------------------------------------------------------
+    def intersect(self, o, d, traversal="compat", real="f64"):
+        """Closest hit of explicit rays: ``(prim[n] int32 (-1 = miss), t[n] float64 (inf = miss), counters)``."""
+        o = np.ascontiguousarray(o, dtype=np.float64)
+        d = np.ascontiguousarray(d, dtype=np.float64)
+        if o.shape != d.shape or o.ndim != 2 or o.shape[1] != 3:
+            raise ValueError("o and d must both be [n,3]")
+        n = len(o)
+        prim = np.empty(n, np.int32)
+        t = np.empty(n, np.float64)
+        cnt = LtCounters()
+        _check(lib().lt_intersect(self._scene, C.c_int(TRAVERSAL[traversal]), C.c_int(REAL[real]), _ptr(o, PD), _ptr(d, PD),
+                                  C.c_int64(n), _ptr(prim, PI32), _ptr(t, PD), C.byref(cnt)))
+        return prim, t, cnt.as_dict()
+
+    def render(self, *, width, height, spp, max_depth, camera, f_distance, s0=0, s1=None, semantics="reference",
+               traversal="compat", real="f32", rand0=None, rand1=None, light_idx=None, seed=0, rr_start=None,
+               film=None, return_samples=False, pixel_range=None, paths_per_warp=0):
+        """One pass of the walk over samples ``[s0,s1)`` of every pixel.  Returns
+        ``(film_sum, samples|None, counters)``; ``film`` may be a preallocated float64 buffer (numpy or a
+        CUDA tensor / device address of H*W*3 doubles) that is accumulated into."""
+        p = LtRenderParams()
+        s1 = spp if s1 is None else s1
+        p.width, p.height, p.spp, p.s0, p.s1, p.max_depth = width, height, spp, s0, s1, max_depth
+        p.semantics, p.traversal, p.real, p.scheduler = SEMANTICS[semantics], TRAVERSAL[traversal], REAL[real], 0
+        p.rr_start = (3 if semantics == "reference" else 5) if rr_start is None else rr_start   # path_tracing.py:148 / fix1:126
+        p.rr_floor, p.eps, p.f_distance, p.seed = 0.05, _pack_eps(), float(f_distance), int(seed)
+        p.paths_per_warp = int(paths_per_warp)
+        cam = np.asarray(camera, dtype=np.float64)
+        for k in range(3):
+            p.camera[k] = float(cam[k])
+        if pixel_range is not None:
+            p.pixel0, p.pixel1 = int(pixel_range[0]), int(pixel_range[1])
+        if (rand0 is None) != (rand1 is None):
+            raise ValueError("rand0 and rand1 go together")
+        if isinstance(rand0, np.ndarray):
+            rand0 = np.ascontiguousarray(rand0, dtype=np.float64)
+            rand1 = np.ascontiguousarray(rand1, dtype=np.float64)
+            if rand0.shape != (height, width, spp, max_depth) or rand1.shape != rand0.shape:
+                raise ValueError(f"rand_0/rand_1 must be [H,W,spp,max_depth]={(height, width, spp, max_depth)}, got {rand0.shape}")
+        if isinstance(light_idx, np.ndarray):
+            light_idx = np.ascontiguousarray(light_idx, dtype=np.int32)
+            if light_idx.shape[:3] != (height, width, spp):
+                raise ValueError("light_idx must be [H,W,spp,K]")
+            if light_idx.size and (light_idx.min() < 0 or light_idx.max() >= self.n_lights):
+                raise ValueError("light_idx out of range")
+            p.n_light_idx = light_idx.shape[3]
+        elif light_idx is not None:
+            raise ValueError("light_idx must be a numpy array")
+        film_buf = np.zeros((height, width, 3), np.float64) if film is None else film
+        samples = np.zeros((height, width, s1 - s0, 3), np.float64) if return_samples else None
+        cnt = LtCounters()
+        _check(lib().lt_render(self._scene, C.byref(p), _ptr(rand0, PD), _ptr(rand1, PD), _ptr(light_idx, PI32),
+                               _ptr(film_buf, PD), _ptr(samples, PD), C.byref(cnt)))
+        return film_buf, samples, cnt.as_dict()
+
+    def finalize(self, film_sum, spp_total, out=None):
+        """``image = clip(film_sum / spp, 0, 1)`` (R/src/path_tracing.py:304-305) on the device."""
+        if isinstance(film_sum, np.ndarray):
+            n = film_sum.size
+            out = np.empty_like(film_sum) if out is None else out
+        else:
+            n = int(film_sum.numel())
+            if out is None:
+                raise ValueError("pass out= for device buffers")
+        _check(lib().lt_film_finalize(self._ctx, _ptr(film_sum, PD), C.c_int64(n), C.c_int64(spp_total), _ptr(out, PD)))
+        return out
+
+    def device_info(self):
+        sm, khz, cc0, cc1 = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        mem = C.c_int64()
+        _check(lib().lt_device_info(self._ctx, C.byref(sm), C.byref(khz), C.byref(mem), C.byref(cc0), C.byref(cc1)))
+        return dict(sm_count=sm.value, clock_khz=khz.value, global_mem=mem.value, cc=(cc0.value, cc1.value))
+
+    def measure_fp32_peak(self):
+        v = C.c_double()
+        _check(lib().lt_measure_fp32_peak(self._ctx, C.byref(v)))
+        return v.value
+
+    def close(self):
+        if getattr(self, "_scene", None) and self._scene:
+            lib().lt_scene_destroy(self._scene)
+            self._scene = C.c_void_p()
+        if getattr(self, "_ctx", None) and self._ctx:
+            lib().lt_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _pack_eps():
+    from .api import EPSILON
+    return EPSILON
+
+
+def _nodes_from_bvh(bvh, packed):
+    if bvh is None:
+        return compat_bvh.build_compat_nodes(packed.tri_v0, packed.tri_v1, packed.tri_v2)
+    if isinstance(bvh, compat_bvh.CompatNodes):
+        return bvh
+    return compat_bvh.from_linear_bvh(bvh)
+
+
+def intersect(primitives, bvh, o, d, *, lights=(), traversal="compat", real="f64", device=0):
+    """Batch form of ``intersect_bvh(ray, primitives, linear_bvh)`` (R/src/bvh_new.py:413-482)."""
+    packed = primitives if isinstance(primitives, _pack.PackedScene) else _pack.pack_scene(primitives, lights)
+    r = Renderer(packed, _nodes_from_bvh(bvh, packed) if traversal == "compat" else None, device=device,
+                 build_lbvh=(traversal == "lbvh"))
+    try:
+        return r.intersect(o, d, traversal, real)
+    finally:
+        r.close()
+
+
+def render_scene(scene, primitives, bvh=None, *, spp=None, rng=None, seed=0, semantics="reference", traversal="compat",
+                 light_idx=None, real=None, return_samples=False, world=None, device=None, return_info=False):
+    """Drop-in for ``render_scene(scene, primitives, bvh)``.
+
+    ``scene``/``primitives``/``bvh`` are the reference's objects (or the ``api`` mirrors / a
+    ``PackedScene`` / ``CompatNodes``).  Returns the image ``clip(mean radiance, 0, 1)`` as float64
+    ``[H,W,3]`` and writes it to ``scene.image`` like the reference does.
+
+    rng="replay" (default when ``scene.rand_0`` exists and ``spp`` is not overridden) consumes
+    ``scene.rand_0/rand_1`` and optional ``light_idx[H,W,spp,K]``; rng="philox" draws counter-based
+    numbers keyed by ``seed`` (needed for configs whose ``Scene`` arrays cannot exist, Q15).
+    ``real`` defaults to "f64" for replay and "f32" for philox.
+    ``world=(rank, world_size)`` or an initialised ``torch.distributed`` group shards the samples
+    ``[r*spp/R, (r+1)*spp/R)`` across ranks and sums the film with ONE reduce (NCCL on GPUs).
+    """
+    H, W, D = int(scene.height), int(scene.width), int(scene.max_depth)
+    n_spp = int(scene.number_of_samples) if spp is None else int(spp)
+    have_rand = getattr(scene, "rand_0", None) is not None
+    if rng is None:
+        rng = "replay" if (have_rand and spp is None) else "philox"
+    if real is None:
+        real = "f64" if rng == "replay" else "f32"
+    rand0 = rand1 = None
+    if rng == "replay":
+        if not have_rand:
+            raise ValueError("rng='replay' needs scene.rand_0/rand_1")
+        rand0, rand1 = np.asarray(scene.rand_0), np.asarray(scene.rand_1)
+        if rand0.shape[2] != n_spp:
+            raise ValueError("spp must equal scene.number_of_samples in replay mode")
+    elif rng != "philox":
+        raise ValueError("rng must be 'replay' or 'philox'")
+    packed = primitives if isinstance(primitives, _pack.PackedScene) else _pack.pack_scene(primitives, scene.lights)
+    nodes = _nodes_from_bvh(bvh, packed) if traversal == "compat" else None
+
+    from . import parallel
+    rank, size, group, use_dist = 0, 1, None, False
+    if world is not None:
+        if isinstance(world, tuple):
+            rank, size = world                                   # virtual rank: renders its share, no reduce
+        else:
+            import torch.distributed as dist
+            group = None if world is True else world
+            rank, size, use_dist = dist.get_rank(group), dist.get_world_size(group), True
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0")) if use_dist else 0
+    s0, s1 = parallel.sample_range(rank, size, n_spp)
+
+    r = Renderer(packed, nodes, device=device, build_lbvh=(traversal == "lbvh"))
+    try:
+        film = None
+        if use_dist:
+            import torch
+            film = torch.zeros(H * W * 3, dtype=torch.float64, device=f"cuda:{device}")
+        film_out, samples, info = r.render(width=W, height=H, spp=n_spp, max_depth=D, camera=scene.camera,
+                                           f_distance=scene.f_distance, s0=s0, s1=s1, semantics=semantics, traversal=traversal,
+                                           real=real, rand0=rand0, rand1=rand1, light_idx=light_idx, seed=seed, film=film,
+                                           return_samples=return_samples)
+        if use_dist:
+            parallel.reduce_film(film, group)                    # the single collective of a pass (NCCL)
+            image_t = torch.empty_like(film)
+            r.finalize(film, n_spp, out=image_t)
+            image = image_t.cpu().numpy().reshape(H, W, 3)
+        else:
+            image = r.finalize(film_out, s1 - s0)
+    finally:
+        r.close()
+    if getattr(scene, "image", None) is not None and (size == 1 or use_dist):
+        try:
+            scene.image[...] = image
+        except Exception:
+            scene.image = image
+    out = (image,)
+    if return_samples:
+        out += (samples,)
+    if return_info:
+        out += (info,)
+    return out[0] if len(out) == 1 else out

@@ -1,0 +1,183 @@
+"""GPU (B200): the path walk through the C-ABI (lt_render).
+ * replayed-RNG mode: per-path radiance within 1e-5 relative of the reference's trace_path
+   (golden vectors) — north_star's second correctness check;
+ * Philox mode: the oracle draws the same counter-based streams, so float64 GPU paths replay it
+   path by path; float32 agrees within 3 sigma of the Monte Carlo standard error per pixel;
+ * size-independent properties at larger sizes (sample-range additivity = virtual ranks, film = sum of
+   samples, determinism)."""
+import numpy as np
+import pytest
+
+from conftest import PATH_SETS, load_paths, load_scene, rel_err
+
+pytestmark = pytest.mark.gpu
+REL_TOL = 1e-5          # BASELINE.json north_star: "per-path radiance must agree within 1e-5 relative"
+
+
+@pytest.fixture(scope="module")
+def R_lts():
+    from light_transport_b200 import host
+    ps, nodes, cam, f = load_scene("lts_scene.npz")
+    r = host.Renderer(ps, nodes, build_lbvh=True)
+    yield r
+    r.close()
+
+
+@pytest.fixture(scope="module")
+def R_mirror():
+    from light_transport_b200 import host
+    ps, nodes, cam, f = load_scene("mirror_scene.npz")
+    r = host.Renderer(ps, nodes, build_lbvh=True)
+    yield r
+    r.close()
+
+
+def _renderer(scene_file, R_lts, R_mirror):
+    return R_lts if scene_file.startswith("lts") else R_mirror
+
+
+@pytest.mark.parametrize("scene_file,path_file", PATH_SETS)
+def test_replay_f64_matches_reference(R_lts, R_mirror, scene_file, path_file):
+    R = _renderer(scene_file, R_lts, R_mirror)
+    g = load_paths(path_file)
+    film, samples, cnt = R.render(width=g["W"], height=g["H"], spp=g["spp"], max_depth=g["D"], camera=g["camera"],
+                                  f_distance=g["f_distance"], semantics=g["semantics"], traversal="compat", real="f64",
+                                  rand0=g["rand0"], rand1=g["rand1"], light_idx=g["light_idx"], return_samples=True)
+    err = rel_err(samples, g["radiance"])
+    n_bad = int((err > REL_TOL).any(axis=-1).sum())
+    print(f"{path_file}: max rel err {err.max():.3g}, paths beyond 1e-5: {n_bad} / {err.shape[0]*err.shape[1]*err.shape[2]}")
+    assert n_bad == 0
+    assert cnt["light_idx_overflow"] == 0 and cnt["frame_overflow"] == 0
+    assert cnt["paths"] == g["W"] * g["H"] * g["spp"]
+    assert np.allclose(film, samples.sum(axis=2), rtol=1e-12, atol=1e-12)
+    img = R.finalize(film, g["spp"])
+    assert np.allclose(img, g["image"], rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.parametrize("scene_file,path_file", PATH_SETS)
+def test_replay_control_flow_equals_oracle(R_lts, R_mirror, oracle, scene_file, path_file):
+    """identical ray counts => identical control flow (every roulette, every recursion) on every path"""
+    R = _renderer(scene_file, R_lts, R_mirror)
+    ps, nodes, _, _ = load_scene(scene_file)
+    g = load_paths(path_file)
+    kw = dict(width=g["W"], height=g["H"], spp=g["spp"], max_depth=g["D"], camera=g["camera"], f_distance=g["f_distance"],
+              semantics=g["semantics"], traversal="compat", rand0=g["rand0"], rand1=g["rand1"], light_idx=g["light_idx"])
+    _, _, c_gpu = R.render(real="f64", **kw)
+    _, _, c_cpu = oracle.render(oracle.OracleScene(ps, nodes), **kw)
+    for k in ("paths", "rays_ext", "rays_shadow", "max_frames"):
+        assert c_gpu[k] == c_cpu[k], k
+
+
+@pytest.mark.parametrize("semantics", ["reference", "iterative"])
+@pytest.mark.parametrize("trav", ["compat", "nearest", "lbvh"])
+def test_philox_f64_replays_oracle(R_lts, oracle, trav, semantics):
+    ps, nodes, cam, f = load_scene("lts_scene.npz")
+    kw = dict(width=40, height=24, spp=6, max_depth=8, camera=cam, f_distance=f, semantics=semantics, seed=11)
+    film, samples, cnt = R_lts.render(traversal=trav, real="f64", return_samples=True, **kw)
+    S = oracle.OracleScene(ps, nodes)
+    o_film, o_samples, o_cnt = oracle.render(S, traversal="compat" if trav == "compat" else "nearest", return_samples=True, **kw)
+    err = rel_err(samples, o_samples)
+    assert (err > REL_TOL).sum() == 0, f"max {err.max()}"
+    assert cnt["rays_ext"] == o_cnt["rays_ext"] and cnt["rays_shadow"] == o_cnt["rays_shadow"]
+
+
+def test_deep_walk_frame_arena(R_mirror, oracle):
+    """C4a: max depth 256 — frames beyond the in-kernel stack spill to the arena and still replay."""
+    ps, nodes, cam, f = load_scene("mirror_scene.npz")
+    kw = dict(width=32, height=32, spp=4, max_depth=256, camera=cam, f_distance=f, semantics="reference", seed=5)
+    film, samples, cnt = R_mirror.render(traversal="compat", real="f64", return_samples=True, **kw)
+    _, o_samples, o_cnt = oracle.render(oracle.OracleScene(ps, nodes), traversal="compat", return_samples=True, **kw)
+    assert (rel_err(samples, o_samples) > REL_TOL).sum() == 0
+    assert cnt["max_frames"] == o_cnt["max_frames"] and cnt["rays_ext"] == o_cnt["rays_ext"]
+
+
+@pytest.mark.parametrize("trav", ["compat", "lbvh"])
+def test_philox_f32_within_3_sigma(R_lts, oracle, trav):
+    """independent check #3 of north_star: per-pixel estimates within 3 sigma of the MC standard error.
+    GPU float32 Philox seed A vs oracle float64 Philox seed B (independent streams)."""
+    ps, nodes, cam, f = load_scene("lts_scene.npz")
+    W, H, spp = 32, 32, 256
+    kw = dict(width=W, height=H, spp=spp, max_depth=8, camera=cam, f_distance=f, semantics="reference")
+    _, g_s, _ = R_lts.render(traversal=trav, real="f32", seed=101, return_samples=True, **kw)
+    _, o_s, _ = oracle.render(oracle.OracleScene(ps, nodes), traversal="compat" if trav == "compat" else "nearest",
+                              seed=202, return_samples=True, **kw)
+    gm, om = g_s.mean(axis=2), o_s.mean(axis=2)
+    se = np.sqrt(g_s.var(axis=2, ddof=1) / spp + o_s.var(axis=2, ddof=1) / spp)
+    z = np.abs(gm - om) / np.maximum(se, 1e-9)
+    valid = se > 1e-9
+    frac = (z[valid] > 3).mean()
+    print(f"{trav}: {valid.sum()} pixel-channels, {frac*100:.2f}% beyond 3 sigma (expect ~0.3-1% for heavy tails), max z {z[valid].max():.2f}")
+    assert frac < 0.02
+    assert abs(gm.mean() - om.mean()) < 4 * np.sqrt((se ** 2).mean() / valid.sum()) + 1e-3
+
+
+def test_f32_same_stream_close_to_f64(R_lts):
+    """float32 walks the same Philox numbers (top 24 bits); most paths take the same decisions."""
+    ps, nodes, cam, f = load_scene("lts_scene.npz")
+    kw = dict(width=48, height=48, spp=4, max_depth=8, camera=cam, f_distance=f, seed=3, traversal="compat", return_samples=True)
+    _, s32, c32 = R_lts.render(real="f32", **kw)
+    _, s64, c64 = R_lts.render(real="f64", **kw)
+    close = (rel_err(s32, s64, floor=1e-2) < 1e-3).all(axis=-1)
+    print(f"f32 vs f64 same stream: {close.mean()*100:.2f}% of paths within 1e-3")
+    assert close.mean() > 0.97
+    assert abs(c32["rays_ext"] - c64["rays_ext"]) / c64["rays_ext"] < 0.01
+
+
+def test_virtual_ranks_equal_full(R_lts):
+    """multi-GPU semantics on one GPU: disjoint sample ranges rendered separately and summed == one render
+    (SURVEY.md §4).  Also: deterministic per-path results, order-independent film within fp-sum tolerance."""
+    ps, nodes, cam, f = load_scene("lts_scene.npz")
+    from light_transport_b200 import parallel
+    kw = dict(width=64, height=40, spp=16, max_depth=8, camera=cam, f_distance=f, seed=9, traversal="lbvh", real="f32")
+    full, s_full, c_full = R_lts.render(return_samples=True, **kw)
+    for world in (2, 4, 8):
+        acc = np.zeros_like(full)
+        rays = 0
+        for r in range(world):
+            s0, s1 = parallel.sample_range(r, world, 16)
+            part, s_part, c = R_lts.render(s0=s0, s1=s1, return_samples=True, **kw)
+            assert np.array_equal(s_part, s_full[:, :, s0:s1])          # same Philox counters => same paths
+            acc += part
+            rays += c["rays_ext"] + c["rays_shadow"]
+        assert np.allclose(acc, full, rtol=1e-12, atol=1e-12)
+        assert rays == c_full["rays_ext"] + c_full["rays_shadow"]
+    again, s_again, _ = R_lts.render(return_samples=True, **kw)
+    assert np.array_equal(s_again, s_full)
+
+
+def test_film_accumulates_and_pixel_ranges(R_lts):
+    ps, nodes, cam, f = load_scene("lts_scene.npz")
+    kw = dict(width=32, height=20, spp=8, max_depth=8, camera=cam, f_distance=f, seed=2, traversal="nearest", real="f32")
+    full, _, _ = R_lts.render(**kw)
+    film = np.zeros_like(full)
+    R_lts.render(film=film, pixel_range=(0, 300), **kw)
+    R_lts.render(film=film, pixel_range=(300, 640), **kw)
+    assert np.allclose(film, full, rtol=1e-12, atol=1e-12)
+    z, _, c = R_lts.render(s0=3, s1=3, **kw)                   # empty sample range
+    assert not z.any() and c["paths"] == 0
+    z, _, _ = R_lts.render(**{**kw, "max_depth": 0})
+    assert not z.any()
+    one, _, c = R_lts.render(**{**kw, "width": 1, "height": 1, "spp": 1})   # 1x1 film: linspace degenerates to start
+    assert c["paths"] == 1
+
+
+def test_render_scene_drop_in(oracle):
+    """the reference-facing call: render_scene(scene, primitives, bvh) with the mirrors, replay mode"""
+    import light_transport_b200 as lt
+    from light_transport_b200 import api, scenes
+    objs, lights, cam, depth = scenes.lts_scene(api)
+    np.random.seed(1)
+    sc = api.Scene(camera=cam, lights=lights, width=24, height=24, max_depth=4, f_distance=depth, number_of_samples=2)
+    img, samples, info = lt.render_scene(sc, objs, None, light_idx=np.zeros((24, 24, 2, 32), np.int32), return_samples=True,
+                                         return_info=True)
+    assert img.shape == (24, 24, 3) and np.array_equal(sc.image, img) and img.min() >= 0 and img.max() <= 1
+    ps = lt.pack_scene(objs, lights)
+    S = oracle.OracleScene(ps, lt.compat_bvh.build_compat_nodes(ps.tri_v0, ps.tri_v1, ps.tri_v2))
+    _, o_s, _ = oracle.render(S, width=24, height=24, spp=2, max_depth=4, camera=cam, f_distance=depth, rand0=sc.rand_0,
+                              rand1=sc.rand_1, light_idx=np.zeros((24, 24, 2, 32), np.int32), return_samples=True)
+    assert (rel_err(samples, o_s) > REL_TOL).sum() == 0
+    # philox path for configs whose Scene arrays cannot exist (Q15)
+    big = api.Scene(camera=cam, lights=lights, width=64, height=64, max_depth=8, f_distance=depth, number_of_samples=1,
+                    allocate=False)
+    img2 = lt.render_scene(big, objs, None, spp=32, rng="philox", seed=4, traversal="lbvh")
+    assert img2.shape == (64, 64, 3) and 0.05 < img2.mean() < 0.9

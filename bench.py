@@ -1,0 +1,274 @@
+#!/usr/bin/env python
+"""bench.py — the reference's headline metric (Mrays/s, path segments per second) on config C2 of
+BASELINE.json: the LTS example scene (Cornell box + glass cone, analytic triangles) at 1024x1024,
+1024 spp, max depth 16, REFERENCE integrator semantics, COMPAT traversal (the reference's own
+intersect_bvh results), float32 arithmetic, Philox4x32-10 random numbers.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step = one full pass of the walk over the film (1024 spp of every pixel).  A ray = one path
+segment = one closest-hit or shadow query (R/src/utils.py:59 + R/src/light_samples.py:48).
+N > 1: weak scaling — every rank renders 1024 spp of every pixel of a job that has 1024*N spp
+(disjoint Philox counters), then ONE NCCL all-reduce of the float64 film inside the timed region.
+--impl reference: the CPU oracle (C port of the reference's path, all host threads) on a bounded
+sample of the same workload; the reference itself is numba-Python and cannot travel to the GPU box.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(width=1024, height=1024, spp=1024, max_depth=16, semantics="reference")
+METRIC = "Mrays/s (path segments/s)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--traversal", default="compat", choices=["compat", "nearest", "lbvh"])
+    ap.add_argument("--real", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--spp", type=int, default=WORKLOAD["spp"], help="override samples per pixel (dev only; invalidates the number)")
+    ap.add_argument("--size", type=int, default=WORKLOAD["width"], help="override film size (dev only)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def scene_arrays():
+    from light_transport_b200 import api, compat_bvh, pack_scene, scenes
+    objs, lights, cam, depth = scenes.lts_scene(api)
+    ps = pack_scene(objs, lights)
+    nodes = compat_bvh.build_compat_nodes(ps.tri_v0, ps.tri_v1, ps.tri_v2)
+    return objs, lights, ps, nodes, cam, depth
+
+
+def flops_per_launch(c):
+    """algorithmic FP32 work, SURVEY.md 8(d): F_ray = 21*N_box + 48*N_tri + F_shade,
+    F_shade = 150 per extension ray, 40 per shadow ray; counts from the kernel's own counters."""
+    return 21.0 * c["box_tests"] + 48.0 * c["tri_tests"] + 150.0 * c["rays_ext"] + 40.0 * c["rays_shadow"]
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = []
+        for k, name in enumerate(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")):
+            if any(len(r) > 3 + k and r[3 + k].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def cpu_baseline(ps, nodes, cam, depth, args, sample_spp=2, repeats=1):
+    """the oracle (kind "port") on a bounded sample: every pixel of the film x `sample_spp` of the spp"""
+    from oracle import oracle as O
+    S = O.OracleScene(ps, nodes)
+    threads = os.cpu_count() or 1
+    kw = dict(width=args.size, height=args.size, spp=args.spp, s0=0, s1=min(sample_spp, args.spp), max_depth=WORKLOAD["max_depth"],
+              camera=cam, f_distance=depth, semantics=WORKLOAD["semantics"],
+              traversal="compat" if args.traversal == "compat" else "nearest", seed=1, n_threads=threads)
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        _, _, c = O.render(S, **kw)
+        dt = time.perf_counter() - t0
+        rays = c["rays_ext"] + c["rays_shadow"]
+        if best is None or dt < best[0]:
+            best = (dt, rays, c)
+    dt, rays, c = best
+    return {"value": rays / dt / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "port",
+            "sample": f"{args.size}x{args.size} pixels x {kw['s1']} of {args.spp} spp ({c['paths']} paths, {rays} rays, {dt:.2f} s, "
+                      f"OpenMP {threads} threads, oracle/lt_oracle.c)"}, dt, rays
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    objs, lights, ps, nodes, cam, depth = scene_arrays()
+    for _ in range(max(args.warmup, 0)):
+        cpu_baseline(ps, nodes, cam, depth, args, sample_spp=1)
+    tot_t, tot_r, cb = 0.0, 0, None
+    for _ in range(max(args.steps, 1)):
+        cb, dt, rays = cpu_baseline(ps, nodes, cam, depth, args, sample_spp=2)
+        tot_t += dt
+        tot_r += rays
+    v = tot_r / tot_t / 1e6
+    cb["value"] = v
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": "Mrays/s", "n_gpus": args.gpus,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_t / max(args.steps, 1) * 1e3,
+                      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                      "config": config_dict(args, 1), "cpu_baseline": cb,
+                      "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                      "gpu_launches": 0}))
+
+
+def config_dict(args, n):
+    return {"workload": f"C2: LTS example scene (Cornell box + glass cone, 28 triangles, 2000 light samples), {args.size}x{args.size}, "
+                        f"{args.spp} spp per GPU, max depth {WORKLOAD['max_depth']}, {WORKLOAD['semantics']} semantics, "
+                        f"{args.traversal} traversal, Philox4x32-10",
+            "film": [args.size, args.size], "spp_per_gpu": args.spp, "spp_total": args.spp * n, "max_depth": WORKLOAD["max_depth"],
+            "semantics": WORKLOAD["semantics"], "traversal": args.traversal, "rng": "philox", "parallelism": f"photon-sharded x{n}",
+            "l2": "flushed between timed steps (256 MiB write)"}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from light_transport_b200 import host, parallel
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the b200 arm has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    objs, lights, ps, nodes, cam, depth = scene_arrays()
+    R = host.Renderer(ps, nodes, device=local, build_lbvh=(args.traversal == "lbvh"))
+    stream = torch.cuda.current_stream()
+    R.set_stream(stream.cuda_stream)
+    W = H = args.size
+    spp_total = args.spp * world
+    s0, s1 = parallel.sample_range(rank, world, spp_total)
+    film = torch.zeros(H * W * 3, dtype=torch.float64, device="cuda")
+    image = torch.empty_like(film)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    kw = dict(width=W, height=H, spp=spp_total, s0=s0, s1=s1, max_depth=WORKLOAD["max_depth"], camera=cam, f_distance=depth,
+              semantics=WORKLOAD["semantics"], traversal=args.traversal, real=args.real)
+
+    def step(i, timed):
+        """one pass: clear film, walk, (reduce), finalize.  Returns (event ms, counters)."""
+        flush.fill_(i & 0xff)                         # L2 flush, outside the timed events
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        film.zero_()
+        _, _, c = R.render(film=film, seed=1 + i, **kw)
+        if world > 1:
+            parallel.reduce_film(film)                # the single collective of a pass
+        R.finalize(film, spp_total, out=image)
+        e1.record(stream)
+        e1.synchronize()
+        return e0.elapsed_time(e1), c
+
+    for i in range(args.warmup):
+        step(i, False)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms, rays, paths, kernel_ns, flops, last = 0.0, 0, 0, 0, 0.0, None
+    for i in range(args.steps):
+        t, c = step(100 + i, True)
+        ms += t
+        rays += c["rays_ext"] + c["rays_shadow"]
+        paths += c["paths"]
+        kernel_ns += c["kernel_ns"]
+        flops += flops_per_launch(c)
+        last = c
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    tm = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    tr = torch.tensor([float(rays), float(paths)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tr, op=dist.ReduceOp.SUM)
+    ms_max, rays_all, paths_all = float(tm[0]), float(tr[0]), float(tr[1])
+    value = rays_all / (ms_max * 1e-3) / 1e6
+
+    # ---- e2e: the reference-facing call with HOST buffers (scene objects in, image array out)
+    import light_transport_b200 as lt
+    from light_transport_b200 import api
+    e2e_steps = max(1, min(args.steps, 2))
+    sc = api.Scene(camera=cam, lights=lights, width=W, height=H, max_depth=WORKLOAD["max_depth"], f_distance=depth,
+                   number_of_samples=1, allocate=False)
+    h2d = sum(v.nbytes for v in ps.to_npz_dict().values()) + sum(getattr(nodes, k).nbytes for k in ("bmin", "bmax", "prim_off", "second", "n_prims", "axis"))
+    d2h = H * W * 3 * 8
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    e_rays = 0
+    for i in range(e2e_steps):
+        img, info = lt.render_scene(sc, ps, nodes, spp=spp_total, rng="philox", seed=500 + i, semantics=WORKLOAD["semantics"],
+                                    traversal=args.traversal, real=args.real, world=(True if world > 1 else None), device=local,
+                                    return_info=True)
+        e_rays += info["rays_ext"] + info["rays_shadow"]
+    torch.cuda.synchronize()
+    et = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    er = torch.tensor([float(e_rays)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(et, op=dist.ReduceOp.MAX)
+        dist.all_reduce(er, op=dist.ReduceOp.SUM)
+    e2e_value = float(er[0]) / float(et[0]) / 1e6
+
+    if rank == 0:
+        peak_tf = R.measure_fp32_peak()
+        achieved_tf = flops / (kernel_ns * 1e-9) / 1e12
+        out = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": args.real, "data": "synthetic", "config": config_dict(args, world),
+               "mpaths_per_s": paths_all / (ms_max * 1e-3) / 1e6, "rays_per_path": rays_all / max(paths_all, 1),
+               "clocks": clocks,
+               "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                       "api": "light_transport_b200.render_scene(scene, primitives, bvh, spp=, rng='philox')", "steps": e2e_steps},
+               "gpu_launches": int(args.steps * 2),
+               "roofline": {"bound": "fp32", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
+                            "traffic": None, "kernel": "lt::walk_megakernel",
+                            "peak_source": "FP32 FMA micro-benchmark run in this process (lt_measure_fp32_peak); MEASURED_PEAKS.json has "
+                                           "no FP32 figure (nominal 148 SM x 128 x 2 x 1.965 GHz = 74.4)",
+                            "flops_model": "21*box_tests + 48*tri_tests + 150*ext_rays + 40*shadow_rays (SURVEY.md 8d)",
+                            "kernel_ms_per_launch": kernel_ns / 1e6 / args.steps,
+                            "box_tests_per_ray": last["box_tests"] / max(last["rays_ext"] + last["rays_shadow"], 1),
+                            "tri_tests_per_ray": last["tri_tests"] / max(last["rays_ext"] + last["rays_shadow"], 1),
+                            "lane_utilisation": last["lane_steps"] / max(last["lane_slots"], 1)}}
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"], _, _ = cpu_baseline(ps, nodes, cam, depth, args, sample_spp=8)
+        print(json.dumps(out))
+    R.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -107,6 +107,9 @@ typedef struct {
 
 int lt_init(int device, lt_ctx **out);
 void lt_destroy(lt_ctx *);
+/* Run all subsequent work of this context on `cuda_stream` (a cudaStream_t, e.g. torch's current
+ * stream) so callers can bracket it with their own events; NULL restores the context's own stream. */
+int lt_set_stream(lt_ctx *, void *cuda_stream);
 int lt_device_info(lt_ctx *, int32_t *sm_count, int32_t *clock_khz, int64_t *global_mem, int32_t *cc_major,
                    int32_t *cc_minor);
 

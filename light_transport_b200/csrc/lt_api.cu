@@ -149,7 +149,12 @@ static int build_compat_arrays(lt_scene* s, const lt_node_desc* d) {
         if (n.n_prims <= 0 && (n.axis < 0 || n.axis > 2)) n.axis = 0;
     }
     for (int i = d->n_nodes - 1; i >= 0; --i)
-        if (nodes[i].n_prims > 0) { CompatNode<R> l = nodes[i]; l.second = i; leaves.push_back(l); }
+        if (nodes[i].n_prims > 0) {
+            CompatNode<R> l = nodes[i];
+            l.second = i;                          // leaf record: its node index
+            nodes[i].axis = (int)leaves.size();    // node record of a leaf: its position in `leaves`
+            leaves.push_back(l);
+        }
     SceneArrays<R>& a = s->arrays<R>();
     int rc;
     if ((rc = upload(&a.cnodes, nodes))) return rc;
@@ -275,8 +280,9 @@ static int do_render(lt_scene* s, const lt_render_params* p, const double* rand0
     if (granules < nwarps) { grid = (int)std::max<int64_t>(1, (granules * 32 + LT_BLOCK - 1) / LT_BLOCK); nwarps = (int64_t)grid * LT_BLOCK / 32; }
     // spilled frame storage for deep REFERENCE walks
     P.arena = nullptr; P.arena_frames = 0; P.arena_threads = (int64_t)grid * LT_BLOCK;
-    if (p->semantics == LT_SEM_REFERENCE && D - 1 > LT_LOCAL_FRAMES) {
-        P.arena_frames = D - 1 - LT_LOCAL_FRAMES;
+    // a frame at stack depth k has bounce >= k and can still recurse at bounce D-1: up to D suspended frames
+    if (p->semantics == LT_SEM_REFERENCE && D > LT_LOCAL_FRAMES) {
+        P.arena_frames = D - LT_LOCAL_FRAMES;
         size_t bytes = (size_t)P.arena_frames * 7 * (size_t)P.arena_threads * sizeof(R);
         if (bytes > ctx->arena_bytes) {
             if (ctx->arena) cudaFree(ctx->arena);
@@ -349,7 +355,8 @@ int lt_init(int device, lt_ctx** out) {
     lt_ctx* c = new lt_ctx();
     c->device = device;
     LT_CUDA_OK(cudaGetDeviceProperties(&c->prop, device));
-    LT_CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    LT_CUDA_OK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
     LT_CUDA_OK(cudaMalloc(&c->d_counters, sizeof(lt_counters)));
     LT_CUDA_OK(cudaEventCreate(&c->ev0));
     LT_CUDA_OK(cudaEventCreate(&c->ev1));
@@ -364,8 +371,14 @@ void lt_destroy(lt_ctx* c) {
     if (c->d_counters) cudaFree(c->d_counters);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
-    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
+}
+
+int lt_set_stream(lt_ctx* c, void* cuda_stream) {
+    if (!c) { set_error("null ctx"); return LT_E_INVALID; }
+    c->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : c->own_stream;
+    return LT_OK;
 }
 
 int lt_device_info(lt_ctx* c, int32_t* sm_count, int32_t* clock_khz, int64_t* global_mem, int32_t* cc_major, int32_t* cc_minor) {

@@ -28,7 +28,8 @@ struct SceneArrays {
 struct lt_ctx {
     int device = 0;
     cudaDeviceProp prop;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;       // stream in use
+    cudaStream_t own_stream = nullptr;   // created by lt_init
     lt_counters* d_counters = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     void* arena = nullptr;

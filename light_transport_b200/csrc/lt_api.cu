@@ -283,7 +283,7 @@ static int do_render(lt_scene* s, const lt_render_params* p, const double* rand0
     // a frame at stack depth k has bounce >= k and can still recurse at bounce D-1: up to D suspended frames
     if (p->semantics == LT_SEM_REFERENCE && D > LT_LOCAL_FRAMES) {
         P.arena_frames = D - LT_LOCAL_FRAMES;
-        size_t bytes = (size_t)P.arena_frames * 7 * (size_t)P.arena_threads * sizeof(R);
+        size_t bytes = (size_t)P.arena_frames * LT_ARENA_VALUES * (size_t)P.arena_threads * sizeof(R);
         if (bytes > ctx->arena_bytes) {
             if (ctx->arena) cudaFree(ctx->arena);
             ctx->arena = nullptr; ctx->arena_bytes = 0;

@@ -70,6 +70,19 @@ LT_DEVINL bool slab(const R* bmin, const R* bmax, V3<R> o, V3<R> inv) {
     return !(t0 > t1);
 }
 
+// float32 overload: min/max instructions instead of compare+select (6 FMNMX fewer per axis).  Differs
+// from the form above only when a slab distance is NaN (origin exactly on a box plane AND a direction
+// component exactly zero): fminf/fmaxf drop the NaN operand, the reference keeps its swap order.
+LT_DEVINL bool slab(const float* bmin, const float* bmax, V3<float> o, V3<float> inv) {
+    const float widen = 1.0f + 2.0f * ((3.0f * 5.9604644775390625e-08f) / (1.0f - 3.0f * 5.9604644775390625e-08f));
+    float ax = (bmin[0] - o.x) * inv.x, bx = (bmax[0] - o.x) * inv.x;
+    float ay = (bmin[1] - o.y) * inv.y, by = (bmax[1] - o.y) * inv.y;
+    float az = (bmin[2] - o.z) * inv.z, bz = (bmax[2] - o.z) * inv.z;
+    float t0 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
+    float t1 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)) * widen;
+    return !(t0 > t1);
+}
+
 template <int NW> struct Bits {
     uint64_t w[NW];
     LT_DEVINL void clear() {

@@ -95,6 +95,10 @@ __global__ void __launch_bounds__(LT_BLOCK, sizeof(R) == 4 ? LT_MIN_BLOCKS_F32 :
     for (int64_t g = gwarp; g * ppw < P.total_paths; g += nwarps) {
         int64_t next = g * ppw;
         const int64_t end = min(P.total_paths, next + ppw);
+        // (pixel, sample) of the granule's first index: one 64-bit division per granule, 32-bit ones per path
+        const int64_t g_pix = next / P.ns;
+        const uint32_t g_s = (uint32_t)(next - g_pix * P.ns);
+        const int64_t g_first = next;
         for (;;) {
             // ---- regeneration: idle lanes take the next indices of the granule
             bool need = ln.qtype == 0;
@@ -104,12 +108,17 @@ __global__ void __launch_bounds__(LT_BLOCK, sizeof(R) == 4 ? LT_MIN_BLOCKS_F32 :
                 int64_t mine = next + rank;
                 next += __popc(m);
                 if (need && mine < end) {
-                    int64_t pix = P.pixel0 + mine / P.ns;
+                    uint32_t off = (uint32_t)(mine - g_first) + g_s;
+                    uint32_t dp = off / (uint32_t)P.ns;
+                    int64_t pix = P.pixel0 + g_pix + dp;
+                    int s_rel = (int)(off - dp * (uint32_t)P.ns);
                     if (pix != acc_pix) { flush_film(P.film, acc_pix, acc); acc_pix = pix; }
-                    start_path<R>(P, ln, mine);
+                    start_path<R>(P, ln, mine, pix, s_rel);
+                    ln.pix = (int32_t)pix;
+                    ln.s_rel = s_rel;
                     if (ln.qtype == 0) {   // max_depth == 0
                         n_paths++;
-                        if (P.samples) { double* o = P.samples + (size_t)(pix * P.ns + mine % P.ns) * 3; o[0] = o[1] = o[2] = 0; }
+                        if (P.samples) { double* o = P.samples + ((size_t)pix * P.ns + s_rel) * 3; o[0] = o[1] = o[2] = 0; }
                     }
                 }
             }
@@ -142,7 +151,7 @@ __global__ void __launch_bounds__(LT_BLOCK, sizeof(R) == 4 ? LT_MIN_BLOCKS_F32 :
                     n_paths++;
                     acc[0] += (double)ln.L.x; acc[1] += (double)ln.L.y; acc[2] += (double)ln.L.z;
                     if (P.samples) {
-                        double* o = P.samples + (size_t)((P.pixel0 + ln.q / P.ns) * P.ns + ln.q % P.ns) * 3;
+                        double* o = P.samples + ((size_t)ln.pix * P.ns + ln.s_rel) * 3;
                         o[0] = (double)ln.L.x; o[1] = (double)ln.L.y; o[2] = (double)ln.L.z;
                     }
                     ln.qtype = 0;

@@ -17,6 +17,7 @@
 namespace lt {
 
 #define LT_LOCAL_FRAMES 12
+#define LT_ARENA_VALUES 8    // T[3], W[3], bounce, rand0 per spilled frame
 
 template <typename R>
 struct WalkParams {
@@ -32,7 +33,7 @@ struct WalkParams {
     double* film;                 // [H][W][3]
     double* samples;              // [H][W][ns][3] or null
     unsigned long long* counters; // lt_counters as u64[12]
-    R* arena;                     // spilled frames: [(frame - LOCAL) * 7 + k][n_threads]
+    R* arena;                     // spilled frames: [(frame - LOCAL) * LT_ARENA_VALUES + k][n_threads]
     int64_t arena_threads;
     int32_t arena_frames;
 };
@@ -40,6 +41,7 @@ struct WalkParams {
 template <typename R>
 struct Frame {
     R T[3], W[3];
+    R rand0;                      // rand_0 of the bounce at which the frame recursed (its roulette reuses it, Q6)
     int32_t bounce;
 };
 
@@ -52,6 +54,7 @@ struct Lane {
     int qtype;                    // 0 idle, 1 extension, 2 shadow
     // path
     int64_t q;                    // linear work index: (pixel - pixel0) * ns + (s - s0)
+    int32_t pix, s_rel;           // pixel (row-major) and s - s0
     uint64_t path_id;             // (pixel * spp + s): Philox counter / replay row
     int32_t bounce, nframes, nee;
     V3<R> T, W, L;
@@ -141,28 +144,32 @@ template <typename R> LT_DEVINL void frame_store(const WalkParams<R>& P, Frame<R
         f.T[0] = ln.T.x; f.T[1] = ln.T.y; f.T[2] = ln.T.z;
         f.W[0] = ln.W.x; f.W[1] = ln.W.y; f.W[2] = ln.W.z;
         f.bounce = ln.bounce;
+        f.rand0 = ln.rand0_pending;
     } else if (idx - LT_LOCAL_FRAMES < P.arena_frames) {
-        R* a = P.arena + ((int64_t)(idx - LT_LOCAL_FRAMES) * 7) * P.arena_threads + gtid;
+        R* a = P.arena + ((int64_t)(idx - LT_LOCAL_FRAMES) * LT_ARENA_VALUES) * P.arena_threads + gtid;
         int64_t s = P.arena_threads;
         a[0] = ln.T.x; a[s] = ln.T.y; a[2 * s] = ln.T.z;
         a[3 * s] = ln.W.x; a[4 * s] = ln.W.y; a[5 * s] = ln.W.z;
         a[6 * s] = (R)ln.bounce;
+        a[7 * s] = ln.rand0_pending;
     } else {
         overflow++;
     }
 }
-template <typename R> LT_DEVINL void frame_load(const WalkParams<R>& P, const Frame<R>* local, int64_t gtid, int idx, Lane<R>& ln) {
+template <typename R> LT_DEVINL void frame_load(const WalkParams<R>& P, const Frame<R>* local, int64_t gtid, int idx, Lane<R>& ln, R& rand0) {
     if (idx < LT_LOCAL_FRAMES) {
         const Frame<R>& f = local[idx];
         ln.T = mk<R>(f.T[0], f.T[1], f.T[2]);
         ln.W = mk<R>(f.W[0], f.W[1], f.W[2]);
         ln.bounce = f.bounce;
+        rand0 = f.rand0;
     } else if (idx - LT_LOCAL_FRAMES < P.arena_frames) {
-        const R* a = P.arena + ((int64_t)(idx - LT_LOCAL_FRAMES) * 7) * P.arena_threads + gtid;
+        const R* a = P.arena + ((int64_t)(idx - LT_LOCAL_FRAMES) * LT_ARENA_VALUES) * P.arena_threads + gtid;
         int64_t s = P.arena_threads;
         ln.T = mk<R>(a[0], a[s], a[2 * s]);
         ln.W = mk<R>(a[3 * s], a[4 * s], a[5 * s]);
         ln.bounce = (int)a[6 * s];
+        rand0 = a[7 * s];
     }
 }
 
@@ -190,8 +197,7 @@ LT_DEVINL bool advance(const WalkParams<R>& P, Lane<R>& ln, const Frame<R>* fram
         // this frame is over
         if (SEM == LT_SEM_ITERATIVE || ln.nframes == 0) return false;
         ln.nframes -= 1;
-        frame_load<R>(P, frames, gtid, ln.nframes, ln);
-        rand_0 = get_rand0<R>(P, ln.path_id, ln.bounce);
+        frame_load<R>(P, frames, gtid, ln.nframes, ln, rand_0);
         ended = false;
     }
 }
@@ -326,10 +332,9 @@ LT_DEVINL bool shade_shadow(const WalkParams<R>& P, Lane<R>& ln, Frame<R>* frame
 
 // R/src/path_tracing.py:263-286: camera ray of (pixel, sample); Q13: the same number jitters x and y.
 template <typename R>
-LT_DEVINL void start_path(const WalkParams<R>& P, Lane<R>& ln, int64_t q) {
-    int64_t pix = P.pixel0 + q / P.ns;
-    int s = P.s0 + (int)(q % P.ns);
-    int i = (int)(pix / P.width), j = (int)(pix % P.width);
+LT_DEVINL void start_path(const WalkParams<R>& P, Lane<R>& ln, int64_t q, int64_t pix, int s_rel) {
+    int s = P.s0 + s_rel;
+    int i = (int)((uint32_t)pix / (uint32_t)P.width), j = (int)((uint32_t)pix % (uint32_t)P.width);
     ln.q = q;
     ln.path_id = (uint64_t)pix * (uint64_t)P.spp + (uint64_t)s;
     ln.bounce = 0; ln.nframes = 0; ln.nee = 0;

@@ -17,7 +17,7 @@ import numpy as np
 from . import _pack, compat_bvh
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblt_b200.so")
+LIB_PATH = os.environ.get("LT_B200_LIB", os.path.join(_HERE, "liblt_b200.so"))   # env override: A/B builds only
 
 TRAVERSAL = {"compat": 0, "nearest": 1, "lbvh": 2}
 SEMANTICS = {"reference": 0, "iterative": 1}

@@ -131,6 +131,12 @@ int lt_intersect(lt_scene *, int traversal, int real, const double *o, const dou
 int lt_render(lt_scene *, const lt_render_params *, const double *rand0, const double *rand1,
               const int32_t *light_idx, double *film_sum, double *samples_out, lt_counters *c);
 
+/* lt_render + lt_film_finalize in one call with the film kept on the device: renders samples
+ * [s0,s1), writes image_out[H][W][3] = clip(film / (s1-s0), 0, 1) (host or device pointer).  This is
+ * the whole of the reference's render_scene for one GPU: scene in (lt_scene_create), image out. */
+int lt_render_image(lt_scene *, const lt_render_params *, const double *rand0, const double *rand1,
+                    const int32_t *light_idx, double *image_out, double *samples_out, lt_counters *c);
+
 /* image = clip(film_sum / spp_total, 0, 1)   (R/src/path_tracing.py:304-305) */
 int lt_film_finalize(lt_ctx *, const double *film_sum, int64_t n_values, int64_t spp_total, double *image_out);
 

@@ -88,7 +88,7 @@ template <typename R>
 static void fill_view(const lt_scene* s, SceneView<R>& v) {
     const SceneArrays<R>& a = s->arrays<R>();
     v.tris = a.tris; v.mats = a.mats; v.lights = a.lights; v.cnodes = a.cnodes;
-    v.cleaves = reinterpret_cast<const CompatLeaf*>(a.cleaves);
+    v.cleaves = a.cleaves;
     v.lbvh = s->lbvh_nodes;
     v.n_tris = s->n_tris; v.n_mats = s->n_mats; v.n_lights = s->n_lights;
     v.n_cnodes = s->n_cnodes; v.n_cleaves = s->n_cleaves; v.n_lbvh_nodes = s->n_lbvh_nodes;
@@ -141,19 +141,29 @@ static int build_scene_arrays(lt_scene* s, const lt_scene_desc* d) {
 
 template <typename R>
 static int build_compat_arrays(lt_scene* s, const lt_node_desc* d) {
-    std::vector<CompatNode<R>> nodes(d->n_nodes), leaves;
+    std::vector<CompatNode<R>> nodes(d->n_nodes);
+    std::vector<CompatLeaf<R>> leaves;
+    std::vector<int> leafpos(d->n_nodes, -1);
     for (int i = 0; i < d->n_nodes; ++i) {
         CompatNode<R>& n = nodes[i];
         for (int c = 0; c < 3; ++c) { n.bmin[c] = (R)d->bmin[3 * i + c]; n.bmax[c] = (R)d->bmax[3 * i + c]; }
         n.prim_off = d->prim_off[i]; n.second = d->second[i]; n.n_prims = d->n_prims[i]; n.axis = d->axis[i];
-        if (n.n_prims <= 0 && (n.axis < 0 || n.axis > 2)) n.axis = 0;
     }
     for (int i = d->n_nodes - 1; i >= 0; --i)
         if (nodes[i].n_prims > 0) {
-            CompatNode<R> l = nodes[i];
-            l.second = i;                          // leaf record: its node index
-            nodes[i].axis = (int)leaves.size();    // node record of a leaf: its position in `leaves`
+            CompatLeaf<R> l;
+            memset(&l, 0, sizeof l);
+            for (int c = 0; c < 3; ++c) { l.bmin[c] = nodes[i].bmin[c]; l.bmax[c] = nodes[i].bmax[c]; }
+            l.prim_off = nodes[i].prim_off; l.n_prims = nodes[i].n_prims;
+            leafpos[i] = (int)leaves.size();
+            nodes[i].axis = leafpos[i];            // node record of a leaf: its position in `leaves`
             leaves.push_back(l);
+        }
+    if (leaves.size() > 64) { set_error("COMPAT traversal supports at most 64 leaves (got %zu)", leaves.size()); return LT_E_INVALID; }
+    for (auto& l : leaves)                          // R/src/bvh_new.py:436: visited[leaf_idx] = True on the NODE list
+        for (int k = 0; k < l.n_prims; ++k) {
+            int p = l.prim_off + k;
+            if (p < d->n_nodes && leafpos[p] >= 0) l.kill |= 1ull << leafpos[p];
         }
     SceneArrays<R>& a = s->arrays<R>();
     int rc;
@@ -170,9 +180,10 @@ static size_t staged_bytes(const lt_scene* s, int trav, int real) {
     size_t tri = r == 8 ? sizeof(TriRec<double>) : sizeof(TriRec<float>);
     size_t mat = r == 8 ? sizeof(MatRec<double>) : sizeof(MatRec<float>);
     size_t nod = r == 8 ? sizeof(CompatNode<double>) : sizeof(CompatNode<float>);
+    size_t lef = r == 8 ? sizeof(CompatLeaf<double>) : sizeof(CompatLeaf<float>);
     if (trav == LT_TRAV_LBVH) return 0;
     size_t b = al(tri * s->n_tris) + al(mat * s->n_mats);
-    if (trav == LT_TRAV_COMPAT) b += al(nod * s->n_cnodes) + al(nod * s->n_cleaves);
+    if (trav == LT_TRAV_COMPAT) b += al(nod * s->n_cnodes) + al(lef * s->n_cleaves);
     return b;
 }
 
@@ -209,7 +220,7 @@ static int do_intersect(lt_scene* s, int traversal, const double* o, const doubl
     P.traversal = traversal;
     int grid = (int)std::min<int64_t>((n + LT_BLOCK - 1) / LT_BLOCK, (int64_t)ctx->prop.multiProcessorCount * 16);
     if (grid < 1) grid = 1;
-    if (n > 0 && (rc = launch_intersect<R>(P, s->compat_words, grid, st))) return rc;
+    if (n > 0 && (rc = launch_intersect<R>(P, grid, st))) return rc;
     if ((rc = bp.finish(st)) || (rc = bt.finish(st))) return rc;
     LT_CUDA_OK(cudaStreamSynchronize(st));
     if (c) {
@@ -265,7 +276,7 @@ static int do_render(lt_scene* s, const lt_render_params* p, const double* rand0
         return LT_E_OVERFLOW;
     }
     int regs = 0, local_bytes = 0, bps = 0;
-    if ((rc = walk_kernel_attrs<R>(p->traversal, p->semantics, s->compat_words, &regs, &local_bytes, &bps, smem))) return rc;
+    if ((rc = walk_kernel_attrs<R>(p->traversal, p->semantics, &regs, &local_bytes, &bps, smem))) return rc;
     if (bps < 1) bps = 1;
     int grid = ctx->prop.multiProcessorCount * bps;
     int64_t nwarps = (int64_t)grid * LT_BLOCK / 32;
@@ -293,7 +304,7 @@ static int do_render(lt_scene* s, const lt_render_params* p, const double* rand0
         P.arena = reinterpret_cast<R*>(ctx->arena);
     }
     LT_CUDA_OK(cudaEventRecord(ctx->ev0, st));
-    if (P.total_paths > 0 && (rc = launch_walk<R>(P, s->compat_words, grid, smem, st))) return rc;
+    if (P.total_paths > 0 && (rc = launch_walk<R>(P, grid, smem, st))) return rc;
     LT_CUDA_OK(cudaEventRecord(ctx->ev1, st));
     if ((rc = bf.finish(st)) || (rc = bs.finish(st))) return rc;
     LT_CUDA_OK(cudaStreamSynchronize(st));
@@ -368,6 +379,7 @@ void lt_destroy(lt_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->arena) cudaFree(c->arena);
+    if (c->film) cudaFree(c->film);
     if (c->d_counters) cudaFree(c->d_counters);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -441,7 +453,6 @@ int lt_scene_set_compat_bvh(lt_scene* s, const lt_node_desc* d) {
     LT_CUDA_OK(cudaSetDevice(s->ctx->device));
     int rc;
     if ((rc = build_compat_arrays<float>(s, d)) || (rc = build_compat_arrays<double>(s, d))) return rc;
-    s->compat_words = d->n_nodes <= 64 ? 1 : 2;
     return LT_OK;
 }
 
@@ -477,6 +488,33 @@ int lt_render(lt_scene* s, const lt_render_params* p, const double* rand0, const
     if (p->real == LT_REAL_F32) return do_render<float>(s, p, rand0, rand1, light_idx, film_sum, samples_out, c);
     set_error("unknown real %d", p->real);
     return LT_E_INVALID;
+}
+
+int lt_render_image(lt_scene* s, const lt_render_params* p, const double* rand0, const double* rand1, const int32_t* light_idx,
+                    double* image_out, double* samples_out, lt_counters* c) {
+    if (!s || !p || !image_out) { set_error("lt_render_image: null argument"); return LT_E_INVALID; }
+    lt_ctx* ctx = s->ctx;
+    LT_CUDA_OK(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)p->width * p->height * 3;
+    if (n > ctx->film_values) {
+        if (ctx->film) cudaFree(ctx->film);
+        ctx->film = nullptr; ctx->film_values = 0;
+        LT_CUDA_OK(cudaMalloc(&ctx->film, n * sizeof(double)));
+        ctx->film_values = n;
+    }
+    LT_CUDA_OK(cudaMemsetAsync(ctx->film, 0, n * sizeof(double), ctx->stream));
+    int rc = lt_render(s, p, rand0, rand1, light_idx, ctx->film, samples_out, c);
+    if (rc) return rc;
+    OutBuf<double> out;
+    if ((rc = out.init(image_out, n, false, ctx->stream))) return rc;
+    const int ns = p->s1 - p->s0;
+    int grid = (int)std::min<int64_t>(((int64_t)n + 255) / 256, (int64_t)ctx->prop.multiProcessorCount * 8);
+    finalize_div_kernel<<<std::max(grid, 1), 256, 0, ctx->stream>>>(ctx->film, (int64_t)n, (double)std::max(ns, 1), out.dev);
+    LT_CUDA_OK(cudaGetLastError());
+    if ((rc = out.finish(ctx->stream))) return rc;
+    LT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    if (c) c->launches += 1;
+    return LT_OK;
 }
 
 int lt_film_finalize(lt_ctx* ctx, const double* film_sum, int64_t n, int64_t spp_total, double* image_out) {

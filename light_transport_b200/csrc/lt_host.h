@@ -12,7 +12,7 @@ struct SceneArrays {
     MatRec<R>* mats = nullptr;
     LightRec<R>* lights = nullptr;
     CompatNode<R>* cnodes = nullptr;
-    CompatNode<R>* cleaves = nullptr;   // leaves in descending node order; .second = node index
+    CompatLeaf<R>* cleaves = nullptr;   // leaves in descending node order
     void release() {
         if (tris) cudaFree(tris);
         if (mats) cudaFree(mats);
@@ -34,12 +34,14 @@ struct lt_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     void* arena = nullptr;
     size_t arena_bytes = 0;
+    double* film = nullptr;              // device film of lt_render_image
+    size_t film_values = 0;
 };
 
 struct lt_scene {
     lt_ctx* ctx = nullptr;
     int n_tris = 0, n_mats = 0, n_lights = 0;
-    int n_cnodes = 0, n_cleaves = 0, compat_words = 1;
+    int n_cnodes = 0, n_cleaves = 0;
     int n_lbvh_nodes = 0;
     lt::SceneArrays<float> f32;
     lt::SceneArrays<double> f64;

@@ -83,113 +83,86 @@ LT_DEVINL bool slab(const float* bmin, const float* bmax, V3<float> o, V3<float>
     return !(t0 > t1);
 }
 
-template <int NW> struct Bits {
-    uint64_t w[NW];
-    LT_DEVINL void clear() {
-#pragma unroll
-        for (int i = 0; i < NW; ++i) w[i] = 0;
-    }
-    LT_DEVINL bool test(int i) const {
-        if (NW == 1) return (w[0] >> i) & 1ull;
-        uint64_t v = w[0];
-#pragma unroll
-        for (int k = 1; k < NW; ++k) v = (i >> 6) == k ? w[k] : v;
-        return (v >> (i & 63)) & 1ull;
-    }
-    LT_DEVINL void set(int i) {
-        if (NW == 1) { w[0] |= 1ull << i; return; }
-#pragma unroll
-        for (int k = 0; k < NW; ++k) w[k] |= (i >> 6) == k ? (1ull << (i & 63)) : 0ull;
-    }
-    LT_DEVINL bool any() const {
-        uint64_t v = 0;
-#pragma unroll
-        for (int k = 0; k < NW; ++k) v |= w[k];
-        return v != 0;
-    }
-    // index of the lowest set bit, cleared on return (caller guarantees any())
-    LT_DEVINL int pop_lowest() {
-#pragma unroll
-        for (int k = 0; k < NW; ++k) {
-            if (w[k]) {
-                int b = __ffsll((long long)w[k]) - 1;
-                w[k] &= w[k] - 1;
-                return k * 64 + b;
-            }
-        }
-        return -1;
-    }
-};
-
 // ---- COMPAT --------------------------------------------------------------------------------------
 // intersect_bvh keeps a `visited` list over NODES, starts at the root and (a) follows near children
 // while interior bounds are hit, then (b) repeatedly jumps to the LAST unvisited index (its scan has
 // no break, :445-449).  In phase (b) an interior node can only jump to an index above itself, which
 // is already visited, so interior bounds tests have no effect there; what remains is: walk the
-// LEAVES in descending node order, skipping those whose node bit is set, and for a leaf whose bounds
-// are hit mark visited[primitive index] (:436 indexes the node list with a primitive index) and test
-// its primitives with EPSILON < t < best, first found wins ties.
+// LEAVES in descending node order, skipping visited ones, and for a leaf whose bounds are hit mark
+// visited[primitive index] (:436 indexes the NODE list with a PRIMITIVE index) and test its
+// primitives with EPSILON < t < best, first found wins ties.
 //
-// `leaves` is that descending list (field `second` = the leaf's node index; in `nodes`, a leaf's
-// `axis` field holds its position in `leaves`).  Bounds tests are pure functions of (leaf, ray), so
-// they are all evaluated first in one converged loop into a bit mask; the lanes then walk their own
-// set bits in list order, every lane running the same leaf code.  Same hits, same ties.
-template <typename R, int NW>
-LT_DEVINL void compat_query(const CompatNode<R>* nodes, const CompatNode<R>* leaves, int n_leaves, const TriRec<R>* tris,
-                            V3<R> o, V3<R> d, R eps, R tlimit, bool anyhit, int skip, int& prim, R& best, Stats& st) {
-    Bits<NW> vis;
-    vis.clear();
+// Only the visited state of LEAVES can change the result, so it is kept as one 64-bit mask over
+// positions in `leaves` (the descending list; at most 64 leaves for the <=128 nodes COMPAT accepts):
+//   * a node record of a leaf carries its list position in `axis`;
+//   * a leaf record carries `kill` = the list positions of the leaves whose NODE index equals one of
+//     its PRIMITIVE indices — processing the leaf ORs it into the visited mask (that is :436).
+// Bounds tests are pure functions of (leaf, ray): they are all evaluated first, converged, into a hit
+// mask; then every lane repeatedly takes its lowest hit-and-unvisited position.  Loops are
+// warp-uniform (`amask` = the lanes running this query together) so the lanes stay in lock step.
+template <typename R>
+LT_DEVINL void compat_query(unsigned amask, const CompatNode<R>* nodes, const CompatLeaf<R>* leaves, int n_leaves,
+                            const TriRec<R>* tris, V3<R> o, V3<R> d, R eps, R tlimit, bool anyhit, int skip, int& prim, R& best,
+                            Stats& st) {
     V3<R> inv = mk<R>((R)1 / d.x, (R)1 / d.y, (R)1 / d.z);
     prim = -1;
     best = tlimit;
-    // phase (a): the initial descent.  Ends at a missed node, or at a leaf whose bounds are hit
-    // (`first` = that leaf's position in `leaves`; it is processed before every other leaf).
+    // phase (a): the initial descent.  Ends at a missed node, or at a leaf (`first` = its list position
+    // if its bounds are hit: it is processed before every other leaf).
     int cur = 0, first = -1;
+    uint64_t lvis = 0;
     bool done = false, descending = true;
-    while (descending) {
-        vis.set(cur);
-        const CompatNode<R>& nd = nodes[cur];
-        st.box_tests++;
-        bool hit = slab(nd.bmin, nd.bmax, o, inv);
-        bool leaf = nd.n_prims > 0;
-        if (!hit || leaf) {
-            done = (cur == 0);
-            first = (hit && leaf) ? nd.axis : -1;
-            descending = false;
-        } else {
-            cur = (comp(inv, nd.axis) < 0) ? nd.second : cur + 1;
-            descending = !vis.test(cur);
+    while (__any_sync(amask, descending)) {
+        if (descending) {
+            const CompatNode<R>& nd = nodes[cur];
+            st.box_tests++;
+            bool hit = slab(nd.bmin, nd.bmax, o, inv);
+            bool leaf = nd.n_prims > 0;
+            if (leaf) lvis |= 1ull << nd.axis;
+            if (!hit || leaf) {
+                done = (cur == 0);
+                first = (hit && leaf) ? nd.axis : -1;
+                descending = false;
+            } else {
+                cur = (comp(inv, nd.axis) < 0) ? nd.second : cur + 1;   // strictly increasing: never revisits
+            }
         }
     }
-    // phase (b) part 1: bounds of all leaves, converged (a root that ends the walk needs none)
-    Bits<NW> hitmask;
-    hitmask.clear();
+    // phase (b) part 1: bounds of all leaves (a root that ends the walk needs none)
+    uint64_t hm = 0;
     if (!done) {
         for (int li = 0; li < n_leaves; ++li) {
-            const CompatNode<R>& nd = leaves[li];
-            if (slab(nd.bmin, nd.bmax, o, inv)) hitmask.set(li);
+            const CompatLeaf<R>& lf = leaves[li];
+            hm |= (uint64_t)slab(lf.bmin, lf.bmax, o, inv) << li;
         }
         st.box_tests += n_leaves;
     }
-    // phase (b) part 2: each lane walks its own hit leaves in list (= descending node) order
+    // phase (b) part 2: every lane walks its own hit leaves in list (= descending node) order
     for (;;) {
-        int li;
-        bool forced = first >= 0;
-        if (forced) { li = first; first = -1; }
-        else {
-            if (!hitmask.any() || (anyhit && prim >= 0)) break;
-            li = hitmask.pop_lowest();
+        int li = first;
+        first = -1;
+        if (li < 0 && !(anyhit && prim >= 0)) {
+            uint64_t cand = hm & ~lvis;
+            if (cand) li = __ffsll((long long)cand) - 1;
         }
-        const CompatNode<R>& nd = leaves[li];
-        if (!forced && vis.test(nd.second)) continue;      // visited earlier, or marked through a primitive index
-        vis.set(nd.second);
-        for (int i = 0; i < nd.n_prims; ++i) {
-            int leaf_idx = nd.prim_off + i;
-            vis.set(leaf_idx);
-            R t;
-            st.tri_tests++;
-            bool h = tri_intersect(tris[leaf_idx], o, d, t);
-            if (h & (leaf_idx != skip) & (eps < t) & (t < best)) { best = t; prim = leaf_idx; }
+        const bool have = li >= 0;
+        if (!__any_sync(amask, have)) break;
+        int np = 0, off = 0;
+        if (have) {
+            const CompatLeaf<R>& lf = leaves[li];
+            lvis |= (1ull << li) | lf.kill;
+            np = lf.n_prims;
+            off = lf.prim_off;
+        }
+        const int npmax = __reduce_max_sync(amask, np);
+        for (int i = 0; i < npmax; ++i) {
+            if (i < np) {
+                int leaf_idx = off + i;
+                R t;
+                st.tri_tests++;
+                bool h = tri_intersect(tris[leaf_idx], o, d, t);
+                if (h & (leaf_idx != skip) & (eps < t) & (t < best)) { best = t; prim = leaf_idx; }
+            }
         }
     }
 }

@@ -59,20 +59,20 @@ LT_DEVINL void flush_film_warp(double* film, int64_t pix, double acc[3]) {
 #define LT_MIN_BLOCKS_F64 3
 #endif
 
-template <typename R, int TRAV, int SEM, int NW>
+template <typename R, int TRAV, int SEM>
 __global__ void __launch_bounds__(LT_BLOCK, sizeof(R) == 4 ? LT_MIN_BLOCKS_F32 : LT_MIN_BLOCKS_F64) walk_megakernel(const WalkParams<R> P) {
     extern __shared__ __align__(16) char smem[];
     const TriRec<R>* tris = P.S.tris;
     const MatRec<R>* mats = P.S.mats;
     const CompatNode<R>* cnodes = P.S.cnodes;
-    const CompatNode<R>* cleaves = reinterpret_cast<const CompatNode<R>*>(P.S.cleaves);
+    const CompatLeaf<R>* cleaves = P.S.cleaves;
     if (TRAV != LT_TRAV_LBVH) {
         char* cur = smem;
         tris = stage_array(cur, P.S.tris, P.S.n_tris);
         mats = stage_array(cur, P.S.mats, P.S.n_mats);
         if (TRAV == LT_TRAV_COMPAT) {
             cnodes = stage_array(cur, P.S.cnodes, P.S.n_cnodes);
-            cleaves = stage_array(cur, reinterpret_cast<const CompatNode<R>*>(P.S.cleaves), P.S.n_cleaves);
+            cleaves = stage_array(cur, P.S.cleaves, P.S.n_cleaves);
         }
         __syncthreads();
     }
@@ -133,18 +133,25 @@ __global__ void __launch_bounds__(LT_BLOCK, sizeof(R) == 4 ? LT_MIN_BLOCKS_F32 :
                 R t;
                 const bool anyhit = ln.qtype == 2;
                 if (TRAV == LT_TRAV_COMPAT)
-                    compat_query<R, NW>(cnodes, cleaves, P.S.n_cleaves, tris, ln.o, ln.d, eps, ln.tlimit, anyhit, ln.skip, prim, t, st);
+                    compat_query<R>(am, cnodes, cleaves, P.S.n_cleaves, tris, ln.o, ln.d, eps, ln.tlimit, anyhit, ln.skip, prim, t, st);
                 else if (TRAV == LT_TRAV_NEAREST)
                     nearest_query<R>(tris, P.S.n_tris, ln.o, ln.d, eps, ln.tlimit, anyhit, ln.skip, prim, t, st);
                 else
                     lbvh_query<R>(P.S.lbvh, tris, P.S.n_tris, ln.o, ln.d, eps, ln.tlimit, anyhit, ln.skip, prim, t, st);
-                bool alive;
+                int stt;
+                R adv_rand0 = (R)0;
                 if (ln.qtype == 1) {
                     n_ext++;
-                    alive = shade_extension<R, SEM>(P, ln, frames, gtid, prim, t, tris, mats, lidx_overflow);
+                    stt = shade_extension<R, SEM>(P, ln, prim, t, tris, mats, lidx_overflow, adv_rand0);
                 } else {
                     n_shadow++;
-                    alive = shade_shadow<R, SEM>(P, ln, frames, gtid, prim >= 0, frame_overflow, max_frames);
+                    stt = shade_shadow<R, SEM>(P, ln, frames, gtid, prim >= 0, frame_overflow, max_frames, adv_rand0);
+                }
+                bool alive = true;
+                if (stt != ST_QUERY) {      // roulette / bounce++ / frame pops: one shared copy for every branch
+                    alive = advance<R, SEM>(P, ln, frames, gtid, stt == ST_ADVANCE_ENDED, adv_rand0);
+                    ln.qtype = 1;
+                    ln.tlimit = Lim<R>::inf();
                 }
                 if (!alive) {
                     // ---- tally (R/src/path_tracing.py:297-298)
@@ -197,37 +204,42 @@ struct IntersectParams {
     int32_t traversal;
 };
 
-template <typename R, int TRAV, int NW>
+template <typename R, int TRAV>
 __global__ void __launch_bounds__(LT_BLOCK) intersect_kernel(const IntersectParams<R> P) {
     Stats st;
     const unsigned full = 0xffffffffu;
-    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < P.n; r += (int64_t)gridDim.x * blockDim.x) {
-        V3<R> o = mk<R>((R)P.o[3 * r], (R)P.o[3 * r + 1], (R)P.o[3 * r + 2]);
-        V3<R> d = mk<R>((R)P.d[3 * r], (R)P.d[3 * r + 1], (R)P.d[3 * r + 2]);
-        int prim;
-        R t;
-        if (TRAV == LT_TRAV_COMPAT)
-            compat_query<R, NW>(P.S.cnodes, reinterpret_cast<const CompatNode<R>*>(P.S.cleaves), P.S.n_cleaves, P.S.tris, o, d,
-                                (R)P.eps, Lim<R>::inf(), false, -1, prim, t, st);
-        else if (TRAV == LT_TRAV_NEAREST)
-            nearest_query<R>(P.S.tris, P.S.n_tris, o, d, (R)P.eps, Lim<R>::inf(), false, -1, prim, t, st);
-        else
-            lbvh_query<R>(P.S.lbvh, P.S.tris, P.S.n_tris, o, d, (R)P.eps, Lim<R>::inf(), false, -1, prim, t, st);
-        P.prim[r] = prim;
-        P.t[r] = prim >= 0 ? (double)t : (double)Lim<double>::inf();
+    const int lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    // warp-uniform loop bound so that the ballot below is executed by whole warps
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < P.n; base += stride) {
+        const int64_t r = base + lane;
+        const bool valid = r < P.n;
+        const unsigned am = __ballot_sync(full, valid);
+        if (valid) {
+            V3<R> o = mk<R>((R)P.o[3 * r], (R)P.o[3 * r + 1], (R)P.o[3 * r + 2]);
+            V3<R> d = mk<R>((R)P.d[3 * r], (R)P.d[3 * r + 1], (R)P.d[3 * r + 2]);
+            int prim;
+            R t;
+            if (TRAV == LT_TRAV_COMPAT)
+                compat_query<R>(am, P.S.cnodes, P.S.cleaves, P.S.n_cleaves, P.S.tris, o, d, (R)P.eps, Lim<R>::inf(), false, -1, prim, t, st);
+            else if (TRAV == LT_TRAV_NEAREST)
+                nearest_query<R>(P.S.tris, P.S.n_tris, o, d, (R)P.eps, Lim<R>::inf(), false, -1, prim, t, st);
+            else
+                lbvh_query<R>(P.S.lbvh, P.S.tris, P.S.n_tris, o, d, (R)P.eps, Lim<R>::inf(), false, -1, prim, t, st);
+            P.prim[r] = prim;
+            P.t[r] = prim >= 0 ? (double)t : (double)Lim<double>::inf();
+        }
     }
     if (P.counters) {
         unsigned long long b = st.box_tests, tt = st.tri_tests;
-        unsigned act = __activemask();
-        (void)full;
-        for (int o = 16; o > 0; o >>= 1) { b += __shfl_xor_sync(act, b, o); tt += __shfl_xor_sync(act, tt, o); }
-        if ((threadIdx.x & 31) == 0) { atomicAdd(P.counters + 3, b); atomicAdd(P.counters + 4, tt); }
+        for (int o = 16; o > 0; o >>= 1) { b += __shfl_xor_sync(full, b, o); tt += __shfl_xor_sync(full, tt, o); }
+        if (lane == 0) { atomicAdd(P.counters + 3, b); atomicAdd(P.counters + 4, tt); }
     }
 }
 
 // host-side dispatch, instantiated per R in lt_walk_f32.cu / lt_walk_f64.cu
-template <typename R> int launch_walk(const WalkParams<R>& P, int nw, int grid, size_t smem, cudaStream_t stream);
-template <typename R> int launch_intersect(const IntersectParams<R>& P, int nw, int grid, cudaStream_t stream);
-template <typename R> int walk_kernel_attrs(int trav, int sem, int nw, int* regs, int* local_bytes, int* max_blocks_per_sm, size_t smem);
+template <typename R> int launch_walk(const WalkParams<R>& P, int grid, size_t smem, cudaStream_t stream);
+template <typename R> int launch_intersect(const IntersectParams<R>& P, int grid, cudaStream_t stream);
+template <typename R> int walk_kernel_attrs(int trav, int sem, int* regs, int* local_bytes, int* max_blocks_per_sm, size_t smem);
 
 }  // namespace lt

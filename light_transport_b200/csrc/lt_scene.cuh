@@ -7,7 +7,7 @@
 //   MatRec<R>   kd[3], emission, ior, transmission, flags                           32 B / 64 B
 //   LightRec<R> pos[3], area, n[3], pad, lekd[3], pad                               48 B / 96 B
 //   CompatNode<R> bmin[3], bmax[3], prim_off, second, n_prims, axis  (reference LinearBVHNode)
-//   CompatLeaf  node index, prim_off, n_prims   — the leaves in DESCENDING node order (see
+//   CompatLeaf<R> bounds, prim_off, n_prims, kill mask — the leaves in DESCENDING node order (see
 //               lt_intersect.cuh: only leaves matter once the initial descent is over)
 //   LbvhNode    2 child boxes (fp32, conservatively rounded outwards) + 2 child refs   64 B = 4 x 128-bit
 #pragma once
@@ -37,8 +37,11 @@ struct alignas(16) CompatNode {
     R bmin[3], bmax[3];
     int32_t prim_off, second, n_prims, axis;
 };
-struct CompatLeaf {
-    int32_t node, prim_off, n_prims, pad;
+template <typename R>
+struct alignas(16) CompatLeaf {
+    R bmin[3], bmax[3];
+    int32_t prim_off, n_prims;
+    uint64_t kill;     // list positions of the leaves this leaf marks visited through its primitive indices (Q9)
 };
 // BVH2 node for the GPU LBVH: child boxes live in the parent so that one 64-byte fetch decides both
 // children.  ref >= 0: interior node index; ref < 0: leaf holding primitive ~ref.
@@ -57,7 +60,7 @@ struct SceneView {
     const MatRec<R>* mats;
     const LightRec<R>* lights;
     const CompatNode<R>* cnodes;
-    const CompatLeaf* cleaves;
+    const CompatLeaf<R>* cleaves;
     const LbvhNode* lbvh;         // root = node 0
     int32_t n_tris, n_mats, n_lights, n_cnodes, n_cleaves, n_lbvh_nodes;
 };

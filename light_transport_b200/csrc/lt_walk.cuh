@@ -202,18 +202,20 @@ LT_DEVINL bool advance(const WalkParams<R>& P, Lane<R>& ln, const Frame<R>* fram
     }
 }
 
-// Shading after an EXTENSION query.  Returns true if the lane has a next query (ln.qtype set).
+// What a shading step leaves behind: a new query in the lane (ST_QUERY), or a request for the shared
+// bounce tail advance() — kept in ONE place in the kernel so that lanes arriving from different
+// branches (miss, specular, shadow resolve) run it together instead of through five inlined copies.
+enum { ST_QUERY = 0, ST_ADVANCE = 1, ST_ADVANCE_ENDED = 2 };
+
+// Shading after an EXTENSION query.
 template <typename R, int SEM>
-LT_DEVINL bool shade_extension(const WalkParams<R>& P, Lane<R>& ln, Frame<R>* frames, int64_t gtid, int prim, R t,
-                               const TriRec<R>* tris, const MatRec<R>* mats, uint32_t& lidx_overflow) {
+LT_DEVINL int shade_extension(const WalkParams<R>& P, Lane<R>& ln, int prim, R t, const TriRec<R>* tris, const MatRec<R>* mats,
+                              uint32_t& lidx_overflow, R& adv_rand0) {
     const R eps = (R)P.eps;
     const R inv_pi = (R)(1 / 3.141592653589793);
     if (sizeof(R) == 4 && prim >= 0) ln.skip = prim;   // every continuation ray below starts on `prim`;
                                                        // on a miss the (unchanged) ray keeps its own skip
-    if (prim < 0) {                                                    // miss: frame ends (:48-53)
-        if (advance<R, SEM>(P, ln, frames, gtid, true, (R)0)) { ln.qtype = 1; ln.tlimit = Lim<R>::inf(); return true; }
-        return false;
-    }
+    if (prim < 0) return ST_ADVANCE_ENDED;                             // miss: frame ends (:48-53)
     R rand_0, rand_1;
     get_rand<R>(P, ln.path_id, ln.bounce, rand_0, rand_1);
     const TriRec<R>& tr = tris[prim];
@@ -256,7 +258,7 @@ LT_DEVINL bool shade_extension(const WalkParams<R>& P, Lane<R>& ln, Frame<R>* fr
         // cannot resolve 1e-6 at r ~ 10 and needs a margin relative to r.
         ln.tlimit = sizeof(R) == 4 ? mag - fmax(eps, mag * (R)4e-6) : mag - eps;
         ln.qtype = 2;
-        return true;
+        return ST_QUERY;
     }
     bool ok = true;
     if (m.flags & 2) {                                                  // mirror, :103-106
@@ -288,31 +290,24 @@ LT_DEVINL bool shade_extension(const WalkParams<R>& P, Lane<R>& ln, Frame<R>* fr
     } else {
         ok = false;                                                     // "error" branch, :143-145
     }
-    if (advance<R, SEM>(P, ln, frames, gtid, !ok, rand_0)) { ln.qtype = 1; ln.tlimit = Lim<R>::inf(); return true; }
-    return false;
+    adv_rand0 = rand_0;
+    return ok ? ST_ADVANCE : ST_ADVANCE_ENDED;
 }
 
 // After the SHADOW query.  occluded = a hit was found in (eps, r - eps).
 template <typename R, int SEM>
-LT_DEVINL bool shade_shadow(const WalkParams<R>& P, Lane<R>& ln, Frame<R>* frames, int64_t gtid, bool occluded,
-                            uint32_t& frame_overflow, uint32_t& max_frames) {
+LT_DEVINL int shade_shadow(const WalkParams<R>& P, Lane<R>& ln, Frame<R>* frames, int64_t gtid, bool occluded,
+                           uint32_t& frame_overflow, uint32_t& max_frames, R& adv_rand0) {
     if (SEM == LT_SEM_ITERATIVE) {
         if (!occluded) ln.L = ln.L + ln.T * ln.contrib;                 // fix1:59
-        bool ended = ln.pdf_zero;                                       // fix1:64-67
-        R rand_0 = (R)0;
-        if (!ended) {
-            ln.T = ln.T * ln.tfac;
-            ln.o = ln.new_o;
-            ln.d = ln.new_d;
-            rand_0 = ln.rand0_pending;
-        }
-        if (advance<R, SEM>(P, ln, frames, gtid, ended, rand_0)) { ln.qtype = 1; ln.tlimit = Lim<R>::inf(); return true; }
-        return false;
+        if (ln.pdf_zero) return ST_ADVANCE_ENDED;                       // fix1:64-67
+        ln.T = ln.T * ln.tfac;
+        ln.o = ln.new_o;
+        ln.d = ln.new_d;
+        adv_rand0 = ln.rand0_pending;
+        return ST_ADVANCE;
     }
-    if (ln.pdf_zero) {                                                  // :76-80 — direct light is dropped
-        if (advance<R, SEM>(P, ln, frames, gtid, true, (R)0)) { ln.qtype = 1; ln.tlimit = Lim<R>::inf(); return true; }
-        return false;
-    }
+    if (ln.pdf_zero) return ST_ADVANCE_ENDED;                           // :76-80 — direct light is dropped
     ln.T = ln.T * ln.tfac;                                              // :92
     if (!occluded) ln.L = ln.L + ln.W * ln.contrib;                     // direct enters un-weighted by T (Q2)
     // recursion (:93): suspend this frame, open the child at bounce+1 on the new ray
@@ -324,10 +319,8 @@ LT_DEVINL bool shade_shadow(const WalkParams<R>& P, Lane<R>& ln, Frame<R>* frame
     ln.o = ln.new_o;
     ln.d = ln.new_d;
     ln.bounce += 1;
-    if (ln.bounce < P.max_depth) { ln.qtype = 1; ln.tlimit = Lim<R>::inf(); return true; }
-    // child frame ends immediately at the depth test (:41)
-    if (advance<R, SEM>(P, ln, frames, gtid, true, (R)0)) { ln.qtype = 1; ln.tlimit = Lim<R>::inf(); return true; }
-    return false;
+    if (ln.bounce < P.max_depth) { ln.qtype = 1; ln.tlimit = Lim<R>::inf(); return ST_QUERY; }
+    return ST_ADVANCE_ENDED;                                            // child frame ends at the depth test (:41)
 }
 
 // R/src/path_tracing.py:263-286: camera ray of (pixel, sample); Q13: the same number jitters x and y.

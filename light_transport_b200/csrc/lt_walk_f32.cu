@@ -1,7 +1,7 @@
 // float32 instantiation of the walk / intersect kernels (throughput path).
 #include "lt_walk_inst.cuh"
 namespace lt {
-template int launch_walk<float>(const WalkParams<float>&, int, int, size_t, cudaStream_t);
-template int launch_intersect<float>(const IntersectParams<float>&, int, int, cudaStream_t);
-template int walk_kernel_attrs<float>(int, int, int, int*, int*, int*, size_t);
+template int launch_walk<float>(const WalkParams<float>&, int, size_t, cudaStream_t);
+template int launch_intersect<float>(const IntersectParams<float>&, int, cudaStream_t);
+template int walk_kernel_attrs<float>(int, int, int*, int*, int*, size_t);
 }

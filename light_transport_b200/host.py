@@ -84,7 +84,7 @@ def lib():
         L.lt_last_error.restype = C.c_char_p
         L.lt_version.restype = C.c_char_p
         for name in ("lt_init", "lt_set_stream", "lt_device_info", "lt_scene_create", "lt_scene_set_compat_bvh", "lt_bvh_build",
-                     "lt_intersect", "lt_render", "lt_film_finalize", "lt_measure_fp32_peak"):
+                     "lt_intersect", "lt_render", "lt_render_image", "lt_film_finalize", "lt_measure_fp32_peak"):
             getattr(L, name).restype = C.c_int
         L.lt_destroy.restype = None
         L.lt_scene_destroy.restype = None
@@ -177,7 +177,7 @@ class Renderer:
 
     def render(self, *, width, height, spp, max_depth, camera, f_distance, s0=0, s1=None, semantics="reference",
                traversal="compat", real="f32", rand0=None, rand1=None, light_idx=None, seed=0, rr_start=None,
-               film=None, return_samples=False, pixel_range=None, paths_per_warp=0):
+               film=None, return_samples=False, pixel_range=None, paths_per_warp=0, image=None):
         """One pass of the walk over samples ``[s0,s1)`` of every pixel.  Returns
         ``(film_sum, samples|None, counters)``; ``film`` may be a preallocated float64 buffer (numpy or a
         CUDA tensor / device address of H*W*3 doubles) that is accumulated into."""
@@ -209,9 +209,14 @@ class Renderer:
             p.n_light_idx = light_idx.shape[3]
         elif light_idx is not None:
             raise ValueError("light_idx must be a numpy array")
-        film_buf = np.zeros((height, width, 3), np.float64) if film is None else film
         samples = np.zeros((height, width, s1 - s0, 3), np.float64) if return_samples else None
         cnt = LtCounters()
+        if image is not None:
+            # film stays on the device; one D2H of the finished image (lt_render_image)
+            _check(lib().lt_render_image(self._scene, C.byref(p), _ptr(rand0, PD), _ptr(rand1, PD), _ptr(light_idx, PI32),
+                                         _ptr(image, PD), _ptr(samples, PD), C.byref(cnt)))
+            return image, samples, cnt.as_dict()
+        film_buf = np.zeros((height, width, 3), np.float64) if film is None else film
         _check(lib().lt_render(self._scene, C.byref(p), _ptr(rand0, PD), _ptr(rand1, PD), _ptr(light_idx, PI32),
                                _ptr(film_buf, PD), _ptr(samples, PD), C.byref(cnt)))
         return film_buf, samples, cnt.as_dict()
@@ -338,17 +343,16 @@ def render_scene(scene, primitives, bvh=None, *, spp=None, rng=None, seed=0, sem
             torch.cuda.set_device(device)
             r.set_stream(torch.cuda.current_stream().cuda_stream)   # one stream: zero-fill → walk → reduce → finalize
             film = torch.zeros(H * W * 3, dtype=torch.float64, device=f"cuda:{device}")
+        image = None if use_dist else np.empty((H, W, 3), np.float64)
         film_out, samples, info = r.render(width=W, height=H, spp=n_spp, max_depth=D, camera=scene.camera,
                                            f_distance=scene.f_distance, s0=s0, s1=s1, semantics=semantics, traversal=traversal,
                                            real=real, rand0=rand0, rand1=rand1, light_idx=light_idx, seed=seed, film=film,
-                                           return_samples=return_samples)
+                                           return_samples=return_samples, image=image)
         if use_dist:
             parallel.reduce_film(film, group)                    # the single collective of a pass (NCCL)
             image_t = torch.empty_like(film)
             r.finalize(film, n_spp, out=image_t)
             image = image_t.cpu().numpy().reshape(H, W, 3)
-        else:
-            image = r.finalize(film_out, s1 - s0)
     finally:
         r.close()
     if getattr(scene, "image", None) is not None and (size == 1 or use_dist):

@@ -7,6 +7,7 @@
 #include <cmath>
 
 #include "lt_megakernel.cuh"
+#include "lt_wavefront.cuh"
 #include "lt_host.h"
 
 namespace lt {
@@ -270,30 +271,45 @@ static int do_render(lt_scene* s, const lt_render_params* p, const double* rand0
     P.film = bf.dev; P.samples = bs.dev;
     P.counters = reinterpret_cast<unsigned long long*>(ctx->d_counters);
 
-    const size_t smem = staged_bytes(s, p->traversal, p->real);
+    const size_t staged = staged_bytes(s, p->traversal, p->real);
+    const bool wavefront = p->scheduler == LT_SCHED_WAVEFRONT;
+    const size_t smem = wavefront ? wavefront_smem_bytes<R>(staged) : staged;
     if (smem > (size_t)ctx->prop.sharedMemPerBlockOptin) {
         set_error("scene needs %zu B of shared memory for traversal %d; use LT_TRAV_LBVH for large scenes", smem, p->traversal);
         return LT_E_OVERFLOW;
     }
     int regs = 0, local_bytes = 0, bps = 0;
-    if ((rc = walk_kernel_attrs<R>(p->traversal, p->semantics, &regs, &local_bytes, &bps, smem))) return rc;
+    if (wavefront) { if ((rc = wavefront_kernel_attrs<R>(p->traversal, p->semantics, &regs, &bps, smem))) return rc; }
+    else if ((rc = walk_kernel_attrs<R>(p->traversal, p->semantics, &regs, &local_bytes, &bps, smem))) return rc;
     if (bps < 1) bps = 1;
+    const int block = wavefront ? WfCfg<R>::NT : LT_BLOCK;
     int grid = ctx->prop.multiProcessorCount * bps;
-    int64_t nwarps = (int64_t)grid * LT_BLOCK / 32;
     int64_t ppw = p->paths_per_warp;
-    if (ppw <= 0) {
-        ppw = P.total_paths / (nwarps * 6);
-        ppw = std::max<int64_t>(64, std::min<int64_t>(ppw, 4096));
-        ppw = (ppw + 31) / 32 * 32;
+    if (wavefront) {
+        // granule = consecutive indices pulled by one CTA at a time
+        if (ppw <= 0) {
+            ppw = P.total_paths / ((int64_t)grid * 12);
+            ppw = std::max<int64_t>(block * 4, std::min<int64_t>(ppw, 1 << 16));
+        }
+        int64_t granules = (P.total_paths + ppw - 1) / ppw;
+        if (granules < grid) grid = (int)std::max<int64_t>(1, granules);
+    } else {
+        int64_t nwarps = (int64_t)grid * block / 32;
+        if (ppw <= 0) {
+            ppw = P.total_paths / (nwarps * 6);
+            ppw = std::max<int64_t>(64, std::min<int64_t>(ppw, 4096));
+            ppw = (ppw + 31) / 32 * 32;
+        }
+        int64_t granules = (P.total_paths + ppw - 1) / ppw;
+        if (granules < nwarps) grid = (int)std::max<int64_t>(1, (granules * 32 + block - 1) / block);
     }
     P.paths_per_warp = (int32_t)ppw;
-    int64_t granules = (P.total_paths + ppw - 1) / ppw;
-    if (granules < nwarps) { grid = (int)std::max<int64_t>(1, (granules * 32 + LT_BLOCK - 1) / LT_BLOCK); nwarps = (int64_t)grid * LT_BLOCK / 32; }
-    // spilled frame storage for deep REFERENCE walks
-    P.arena = nullptr; P.arena_frames = 0; P.arena_threads = (int64_t)grid * LT_BLOCK;
-    // a frame at stack depth k has bounce >= k and can still recurse at bounce D-1: up to D suspended frames
-    if (p->semantics == LT_SEM_REFERENCE && D > LT_LOCAL_FRAMES) {
-        P.arena_frames = D - LT_LOCAL_FRAMES;
+    // suspended-frame storage for REFERENCE walks: a frame at stack depth k has bounce >= k and can still
+    // recurse at bounce D-1, so up to D suspended frames; the megakernel keeps the first LT_LOCAL_FRAMES locally
+    P.arena = nullptr; P.arena_frames = 0; P.arena_threads = (int64_t)grid * block;
+    const int local_frames = wavefront ? 0 : LT_LOCAL_FRAMES;
+    if (p->semantics == LT_SEM_REFERENCE && D > local_frames) {
+        P.arena_frames = D - local_frames;
         size_t bytes = (size_t)P.arena_frames * LT_ARENA_VALUES * (size_t)P.arena_threads * sizeof(R);
         if (bytes > ctx->arena_bytes) {
             if (ctx->arena) cudaFree(ctx->arena);
@@ -303,8 +319,12 @@ static int do_render(lt_scene* s, const lt_render_params* p, const double* rand0
         }
         P.arena = reinterpret_cast<R*>(ctx->arena);
     }
+    if (wavefront) LT_CUDA_OK(cudaMemsetAsync(ctx->d_granule, 0, sizeof(unsigned long long), st));
     LT_CUDA_OK(cudaEventRecord(ctx->ev0, st));
-    if (P.total_paths > 0 && (rc = launch_walk<R>(P, grid, smem, st))) return rc;
+    if (P.total_paths > 0) {
+        rc = wavefront ? launch_wavefront<R>(P, ctx->d_granule, grid, smem, st) : launch_walk<R>(P, grid, smem, st);
+        if (rc) return rc;
+    }
     LT_CUDA_OK(cudaEventRecord(ctx->ev1, st));
     if ((rc = bf.finish(st)) || (rc = bs.finish(st))) return rc;
     LT_CUDA_OK(cudaStreamSynchronize(st));
@@ -369,6 +389,7 @@ int lt_init(int device, lt_ctx** out) {
     LT_CUDA_OK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     LT_CUDA_OK(cudaMalloc(&c->d_counters, sizeof(lt_counters)));
+    LT_CUDA_OK(cudaMalloc(&c->d_granule, sizeof(unsigned long long)));
     LT_CUDA_OK(cudaEventCreate(&c->ev0));
     LT_CUDA_OK(cudaEventCreate(&c->ev1));
     *out = c;
@@ -381,6 +402,7 @@ void lt_destroy(lt_ctx* c) {
     if (c->arena) cudaFree(c->arena);
     if (c->film) cudaFree(c->film);
     if (c->d_counters) cudaFree(c->d_counters);
+    if (c->d_granule) cudaFree(c->d_granule);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -479,7 +501,7 @@ int lt_render(lt_scene* s, const lt_render_params* p, const double* rand0, const
     if (light_idx && p->n_light_idx <= 0) { set_error("light_idx given but n_light_idx == 0"); return LT_E_INVALID; }
     if (s->n_lights <= 0) { set_error("scene has no Light (next-event estimation needs one)"); return LT_E_INVALID; }
     if (p->semantics != LT_SEM_REFERENCE && p->semantics != LT_SEM_ITERATIVE) { set_error("unknown semantics"); return LT_E_INVALID; }
-    if (p->scheduler != LT_SCHED_MEGAKERNEL) { set_error("scheduler %d not available in this build", p->scheduler); return LT_E_INVALID; }
+    if (p->scheduler != LT_SCHED_MEGAKERNEL && p->scheduler != LT_SCHED_WAVEFRONT) { set_error("unknown scheduler %d", p->scheduler); return LT_E_INVALID; }
     if (p->pixel1 > p->width * p->height || p->pixel0 < 0) { set_error("bad pixel range"); return LT_E_INVALID; }
     LT_CUDA_OK(cudaSetDevice(s->ctx->device));
     int rc = check_traversal(s, p->traversal);

@@ -31,6 +31,7 @@ struct lt_ctx {
     cudaStream_t stream = nullptr;       // stream in use
     cudaStream_t own_stream = nullptr;   // created by lt_init
     lt_counters* d_counters = nullptr;
+    unsigned long long* d_granule = nullptr;   // wavefront scheduler: global granule counter
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     void* arena = nullptr;
     size_t arena_bytes = 0;

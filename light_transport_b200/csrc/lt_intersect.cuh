@@ -131,9 +131,19 @@ LT_DEVINL void compat_query(unsigned amask, const CompatNode<R>* nodes, const Co
     // phase (b) part 1: bounds of all leaves (a root that ends the walk needs none)
     uint64_t hm = 0;
     if (!done) {
-        for (int li = 0; li < n_leaves; ++li) {
-            const CompatLeaf<R>& lf = leaves[li];
-            hm |= (uint64_t)slab(lf.bmin, lf.bmax, o, inv) << li;
+        if (n_leaves <= 32) {                       // the usual case: 32-bit mask arithmetic
+            uint32_t m = 0;
+#pragma unroll 4
+            for (int li = 0; li < n_leaves; ++li) {
+                const CompatLeaf<R>& lf = leaves[li];
+                m |= (uint32_t)slab(lf.bmin, lf.bmax, o, inv) << li;
+            }
+            hm = m;
+        } else {
+            for (int li = 0; li < n_leaves; ++li) {
+                const CompatLeaf<R>& lf = leaves[li];
+                hm |= (uint64_t)slab(lf.bmin, lf.bmax, o, inv) << li;
+            }
         }
         st.box_tests += n_leaves;
     }

@@ -113,9 +113,7 @@ __global__ void __launch_bounds__(LT_BLOCK, sizeof(R) == 4 ? LT_MIN_BLOCKS_F32 :
                     int64_t pix = P.pixel0 + g_pix + dp;
                     int s_rel = (int)(off - dp * (uint32_t)P.ns);
                     if (pix != acc_pix) { flush_film(P.film, acc_pix, acc); acc_pix = pix; }
-                    start_path<R>(P, ln, mine, pix, s_rel);
-                    ln.pix = (int32_t)pix;
-                    ln.s_rel = s_rel;
+                    start_path<R>(P, ln, pix, s_rel);
                     if (ln.qtype == 0) {   // max_depth == 0
                         n_paths++;
                         if (P.samples) { double* o = P.samples + ((size_t)pix * P.ns + s_rel) * 3; o[0] = o[1] = o[2] = 0; }
@@ -145,11 +143,11 @@ __global__ void __launch_bounds__(LT_BLOCK, sizeof(R) == 4 ? LT_MIN_BLOCKS_F32 :
                     stt = shade_extension<R, SEM>(P, ln, prim, t, tris, mats, lidx_overflow, adv_rand0);
                 } else {
                     n_shadow++;
-                    stt = shade_shadow<R, SEM>(P, ln, frames, gtid, prim >= 0, frame_overflow, max_frames, adv_rand0);
+                    stt = shade_shadow<R, SEM, LT_LOCAL_FRAMES>(P, ln, frames, gtid, prim >= 0, frame_overflow, max_frames, adv_rand0);
                 }
                 bool alive = true;
                 if (stt != ST_QUERY) {      // roulette / bounce++ / frame pops: one shared copy for every branch
-                    alive = advance<R, SEM>(P, ln, frames, gtid, stt == ST_ADVANCE_ENDED, adv_rand0);
+                    alive = advance<R, SEM, LT_LOCAL_FRAMES>(P, ln, frames, gtid, stt == ST_ADVANCE_ENDED, adv_rand0);
                     ln.qtype = 1;
                     ln.tlimit = Lim<R>::inf();
                 }

@@ -47,21 +47,23 @@ struct Frame {
 
 template <typename R>
 struct Lane {
-    // query
+    // query (the wavefront scheduler loads only this head for its trace stage)
     V3<R> o, d;
     R tlimit;
-    int skip;                     // primitive the query ray starts on (float32 walk only), else -1
-    int qtype;                    // 0 idle, 1 extension, 2 shadow
+    int32_t skip;                 // primitive the query ray starts on (float32 walk only), else -1
+    int32_t qtype;                // 0 idle, 1 extension, 2 shadow
+    // result of the query (wavefront scheduler only; the megakernel keeps it in registers)
+    int32_t hit_prim, hit_pad;
+    R hit_t;
     // path
-    int64_t q;                    // linear work index: (pixel - pixel0) * ns + (s - s0)
     int32_t pix, s_rel;           // pixel (row-major) and s - s0
     uint64_t path_id;             // (pixel * spp + s): Philox counter / replay row
     int32_t bounce, nframes, nee;
+    int32_t pdf_zero;
     V3<R> T, W, L;
     // pending across the shadow query
     V3<R> contrib, new_o, new_d, tfac;
     R rand0_pending;
-    bool pdf_zero;
 };
 
 // random numbers of (path, bounce): replayed Scene.rand_0/rand_1 rows or Philox stream 0
@@ -138,15 +140,16 @@ template <typename R> LT_DEVINL V3<R> reflect_dir(V3<R> v, V3<R> n) {
     return normalize(mk<R>(v.x - k * n.x, v.y - k * n.y, v.z - k * n.z));
 }
 
-template <typename R> LT_DEVINL void frame_store(const WalkParams<R>& P, Frame<R>* local, int64_t gtid, int idx, const Lane<R>& ln, uint32_t& overflow) {
-    if (idx < LT_LOCAL_FRAMES) {
+// LF = frames kept in the caller's local array (megakernel: LT_LOCAL_FRAMES; wavefront: 0, all in the arena)
+template <typename R, int LF> LT_DEVINL void frame_store(const WalkParams<R>& P, Frame<R>* local, int64_t gtid, int idx, const Lane<R>& ln, uint32_t& overflow) {
+    if (idx < LF) {
         Frame<R>& f = local[idx];
         f.T[0] = ln.T.x; f.T[1] = ln.T.y; f.T[2] = ln.T.z;
         f.W[0] = ln.W.x; f.W[1] = ln.W.y; f.W[2] = ln.W.z;
         f.bounce = ln.bounce;
         f.rand0 = ln.rand0_pending;
-    } else if (idx - LT_LOCAL_FRAMES < P.arena_frames) {
-        R* a = P.arena + ((int64_t)(idx - LT_LOCAL_FRAMES) * LT_ARENA_VALUES) * P.arena_threads + gtid;
+    } else if (idx - LF < P.arena_frames) {
+        R* a = P.arena + ((int64_t)(idx - LF) * LT_ARENA_VALUES) * P.arena_threads + gtid;
         int64_t s = P.arena_threads;
         a[0] = ln.T.x; a[s] = ln.T.y; a[2 * s] = ln.T.z;
         a[3 * s] = ln.W.x; a[4 * s] = ln.W.y; a[5 * s] = ln.W.z;
@@ -156,15 +159,15 @@ template <typename R> LT_DEVINL void frame_store(const WalkParams<R>& P, Frame<R
         overflow++;
     }
 }
-template <typename R> LT_DEVINL void frame_load(const WalkParams<R>& P, const Frame<R>* local, int64_t gtid, int idx, Lane<R>& ln, R& rand0) {
-    if (idx < LT_LOCAL_FRAMES) {
+template <typename R, int LF> LT_DEVINL void frame_load(const WalkParams<R>& P, const Frame<R>* local, int64_t gtid, int idx, Lane<R>& ln, R& rand0) {
+    if (idx < LF) {
         const Frame<R>& f = local[idx];
         ln.T = mk<R>(f.T[0], f.T[1], f.T[2]);
         ln.W = mk<R>(f.W[0], f.W[1], f.W[2]);
         ln.bounce = f.bounce;
         rand0 = f.rand0;
-    } else if (idx - LT_LOCAL_FRAMES < P.arena_frames) {
-        const R* a = P.arena + ((int64_t)(idx - LT_LOCAL_FRAMES) * LT_ARENA_VALUES) * P.arena_threads + gtid;
+    } else if (idx - LF < P.arena_frames) {
+        const R* a = P.arena + ((int64_t)(idx - LF) * LT_ARENA_VALUES) * P.arena_threads + gtid;
         int64_t s = P.arena_threads;
         ln.T = mk<R>(a[0], a[s], a[2 * s]);
         ln.W = mk<R>(a[3 * s], a[4 * s], a[5 * s]);
@@ -178,7 +181,7 @@ template <typename R> LT_DEVINL void frame_load(const WalkParams<R>& P, const Fr
 // (:41), and — whenever a frame ends — resumption of its parent at the roulette (Q1).
 // `ended` = the current frame has already ended (miss / pdf==0 / malformed material).
 // Returns true when the lane has a new extension ray to trace, false when the whole path is over.
-template <typename R, int SEM>
+template <typename R, int SEM, int LF>
 LT_DEVINL bool advance(const WalkParams<R>& P, Lane<R>& ln, const Frame<R>* frames, int64_t gtid, bool ended, R rand_0) {
     for (;;) {
         if (!ended) {
@@ -197,7 +200,7 @@ LT_DEVINL bool advance(const WalkParams<R>& P, Lane<R>& ln, const Frame<R>* fram
         // this frame is over
         if (SEM == LT_SEM_ITERATIVE || ln.nframes == 0) return false;
         ln.nframes -= 1;
-        frame_load<R>(P, frames, gtid, ln.nframes, ln, rand_0);
+        frame_load<R, LF>(P, frames, gtid, ln.nframes, ln, rand_0);
         ended = false;
     }
 }
@@ -245,7 +248,7 @@ LT_DEVINL int shade_extension(const WalkParams<R>& P, Lane<R>& ln, int prim, R t
         // thing left between here and the recursion point
         V3<R> dir;
         R pdf = cosine_sample<R>(n, ln.d, rand_0, rand_1, dir);
-        ln.pdf_zero = (pdf == 0);
+        ln.pdf_zero = (pdf == 0) ? 1 : 0;
         ln.rand0_pending = rand_0;
         R ct = dot(dir, n);
         ln.tfac = mk<R>((m.kd[0] * inv_pi) * ct / pdf, (m.kd[1] * inv_pi) * ct / pdf, (m.kd[2] * inv_pi) * ct / pdf);
@@ -295,7 +298,7 @@ LT_DEVINL int shade_extension(const WalkParams<R>& P, Lane<R>& ln, int prim, R t
 }
 
 // After the SHADOW query.  occluded = a hit was found in (eps, r - eps).
-template <typename R, int SEM>
+template <typename R, int SEM, int LF>
 LT_DEVINL int shade_shadow(const WalkParams<R>& P, Lane<R>& ln, Frame<R>* frames, int64_t gtid, bool occluded,
                            uint32_t& frame_overflow, uint32_t& max_frames, R& adv_rand0) {
     if (SEM == LT_SEM_ITERATIVE) {
@@ -311,7 +314,7 @@ LT_DEVINL int shade_shadow(const WalkParams<R>& P, Lane<R>& ln, Frame<R>* frames
     ln.T = ln.T * ln.tfac;                                              // :92
     if (!occluded) ln.L = ln.L + ln.W * ln.contrib;                     // direct enters un-weighted by T (Q2)
     // recursion (:93): suspend this frame, open the child at bounce+1 on the new ray
-    frame_store<R>(P, frames, gtid, ln.nframes, ln, frame_overflow);
+    frame_store<R, LF>(P, frames, gtid, ln.nframes, ln, frame_overflow);
     ln.nframes += 1;
     if ((uint32_t)ln.nframes + 1 > max_frames) max_frames = (uint32_t)ln.nframes + 1;
     ln.W = ln.W * ln.T;
@@ -325,10 +328,11 @@ LT_DEVINL int shade_shadow(const WalkParams<R>& P, Lane<R>& ln, Frame<R>* frames
 
 // R/src/path_tracing.py:263-286: camera ray of (pixel, sample); Q13: the same number jitters x and y.
 template <typename R>
-LT_DEVINL void start_path(const WalkParams<R>& P, Lane<R>& ln, int64_t q, int64_t pix, int s_rel) {
+LT_DEVINL void start_path(const WalkParams<R>& P, Lane<R>& ln, int64_t pix, int s_rel) {
     int s = P.s0 + s_rel;
     int i = (int)((uint32_t)pix / (uint32_t)P.width), j = (int)((uint32_t)pix % (uint32_t)P.width);
-    ln.q = q;
+    ln.pix = (int32_t)pix;
+    ln.s_rel = s_rel;
     ln.path_id = (uint64_t)pix * (uint64_t)P.spp + (uint64_t)s;
     ln.bounce = 0; ln.nframes = 0; ln.nee = 0;
     ln.T = mk<R>((R)1, (R)1, (R)1);

@@ -4,6 +4,7 @@
 // separate NumPy operations, see DESIGN.md "numerics").
 #pragma once
 #include "lt_megakernel.cuh"
+#include "lt_wavefront.cuh"
 
 namespace lt {
 
@@ -57,6 +58,50 @@ int walk_kernel_attrs(int trav, int sem, int* regs, int* local_bytes, int* max_b
     LT_ATTR(LT_TRAV_LBVH, LT_SEM_ITERATIVE)
 #undef LT_ATTR
     set_error("unknown kernel variant");
+    return LT_E_INVALID;
+}
+
+template <typename R, int TRAV, int SEM>
+static int wf_launch_one(const WalkParams<R>& P, unsigned long long* gc, int grid, size_t smem, cudaStream_t stream) {
+    auto k = walk_wavefront<R, TRAV, SEM>;
+    if (smem > 48 * 1024) LT_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, WfCfg<R>::NT, smem, stream>>>(P, gc);
+    LT_CUDA_OK(cudaGetLastError());
+    return LT_OK;
+}
+template <typename R, int TRAV, int SEM>
+static int wf_attrs_one(int* regs, int* max_blocks, size_t smem) {
+    auto k = walk_wavefront<R, TRAV, SEM>;
+    cudaFuncAttributes a;
+    LT_CUDA_OK(cudaFuncGetAttributes(&a, k));
+    if (smem > 48 * 1024) LT_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    *regs = a.numRegs;
+    LT_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(max_blocks, k, WfCfg<R>::NT, smem));
+    return LT_OK;
+}
+#define LT_WF_DISPATCH(CALL)                                                                              \
+    if (trav == LT_TRAV_COMPAT && sem == LT_SEM_REFERENCE) return CALL(LT_TRAV_COMPAT, LT_SEM_REFERENCE);   \
+    if (trav == LT_TRAV_COMPAT && sem == LT_SEM_ITERATIVE) return CALL(LT_TRAV_COMPAT, LT_SEM_ITERATIVE);   \
+    if (trav == LT_TRAV_NEAREST && sem == LT_SEM_REFERENCE) return CALL(LT_TRAV_NEAREST, LT_SEM_REFERENCE); \
+    if (trav == LT_TRAV_NEAREST && sem == LT_SEM_ITERATIVE) return CALL(LT_TRAV_NEAREST, LT_SEM_ITERATIVE); \
+    if (trav == LT_TRAV_LBVH && sem == LT_SEM_REFERENCE) return CALL(LT_TRAV_LBVH, LT_SEM_REFERENCE);       \
+    if (trav == LT_TRAV_LBVH && sem == LT_SEM_ITERATIVE) return CALL(LT_TRAV_LBVH, LT_SEM_ITERATIVE);
+
+template <typename R>
+int launch_wavefront(const WalkParams<R>& P, unsigned long long* gc, int grid, size_t smem, cudaStream_t stream) {
+    const int trav = P.traversal, sem = P.semantics;
+#define LT_WF_L(T, S) wf_launch_one<R, T, S>(P, gc, grid, smem, stream)
+    LT_WF_DISPATCH(LT_WF_L)
+#undef LT_WF_L
+    set_error("unknown wavefront kernel variant");
+    return LT_E_INVALID;
+}
+template <typename R>
+int wavefront_kernel_attrs(int trav, int sem, int* regs, int* max_blocks, size_t smem) {
+#define LT_WF_A(T, S) wf_attrs_one<R, T, S>(regs, max_blocks, smem)
+    LT_WF_DISPATCH(LT_WF_A)
+#undef LT_WF_A
+    set_error("unknown wavefront kernel variant");
     return LT_E_INVALID;
 }
 

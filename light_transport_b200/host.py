@@ -22,6 +22,7 @@ LIB_PATH = os.environ.get("LT_B200_LIB", os.path.join(_HERE, "liblt_b200.so"))  
 TRAVERSAL = {"compat": 0, "nearest": 1, "lbvh": 2}
 SEMANTICS = {"reference": 0, "iterative": 1}
 REAL = {"f32": 0, "f64": 1}
+SCHEDULER = {"megakernel": 0, "wavefront": 1}
 
 PD = C.POINTER(C.c_double)
 PI32 = C.POINTER(C.c_int32)
@@ -177,14 +178,14 @@ class Renderer:
 
     def render(self, *, width, height, spp, max_depth, camera, f_distance, s0=0, s1=None, semantics="reference",
                traversal="compat", real="f32", rand0=None, rand1=None, light_idx=None, seed=0, rr_start=None,
-               film=None, return_samples=False, pixel_range=None, paths_per_warp=0, image=None):
+               film=None, return_samples=False, pixel_range=None, paths_per_warp=0, image=None, scheduler="megakernel"):
         """One pass of the walk over samples ``[s0,s1)`` of every pixel.  Returns
         ``(film_sum, samples|None, counters)``; ``film`` may be a preallocated float64 buffer (numpy or a
         CUDA tensor / device address of H*W*3 doubles) that is accumulated into."""
         p = LtRenderParams()
         s1 = spp if s1 is None else s1
         p.width, p.height, p.spp, p.s0, p.s1, p.max_depth = width, height, spp, s0, s1, max_depth
-        p.semantics, p.traversal, p.real, p.scheduler = SEMANTICS[semantics], TRAVERSAL[traversal], REAL[real], 0
+        p.semantics, p.traversal, p.real, p.scheduler = SEMANTICS[semantics], TRAVERSAL[traversal], REAL[real], SCHEDULER[scheduler]
         p.rr_start = (3 if semantics == "reference" else 5) if rr_start is None else rr_start   # path_tracing.py:148 / fix1:126
         p.rr_floor, p.eps, p.f_distance, p.seed = 0.05, _pack_eps(), float(f_distance), int(seed)
         p.paths_per_warp = int(paths_per_warp)
@@ -289,7 +290,8 @@ def intersect(primitives, bvh, o, d, *, lights=(), traversal="compat", real="f64
 
 
 def render_scene(scene, primitives, bvh=None, *, spp=None, rng=None, seed=0, semantics="reference", traversal="compat",
-                 light_idx=None, real=None, return_samples=False, world=None, device=None, return_info=False):
+                 light_idx=None, real=None, return_samples=False, world=None, device=None, return_info=False,
+                 scheduler="megakernel"):
     """Drop-in for ``render_scene(scene, primitives, bvh)``.
 
     ``scene``/``primitives``/``bvh`` are the reference's objects (or the ``api`` mirrors / a
@@ -347,7 +349,7 @@ def render_scene(scene, primitives, bvh=None, *, spp=None, rng=None, seed=0, sem
         film_out, samples, info = r.render(width=W, height=H, spp=n_spp, max_depth=D, camera=scene.camera,
                                            f_distance=scene.f_distance, s0=s0, s1=s1, semantics=semantics, traversal=traversal,
                                            real=real, rand0=rand0, rand1=rand1, light_idx=light_idx, seed=seed, film=film,
-                                           return_samples=return_samples, image=image)
+                                           return_samples=return_samples, image=image, scheduler=scheduler)
         if use_dist:
             parallel.reduce_film(film, group)                    # the single collective of a pass (NCCL)
             image_t = torch.empty_like(film)

@@ -205,3 +205,52 @@ def test_render_scene_drop_in(oracle):
                     allocate=False)
     img2 = lt.render_scene(big, objs, None, spp=32, rng="philox", seed=4, traversal="lbvh")
     assert img2.shape == (64, 64, 3) and 0.05 < img2.mean() < 0.9
+
+
+# ---------------------------------------------------------------- wavefront scheduler (LT_SCHED_WAVEFRONT)
+@pytest.mark.parametrize("scene_file,path_file", PATH_SETS)
+def test_wavefront_replay_f64_matches_reference(R_lts, R_mirror, scene_file, path_file):
+    """the CTA-resident wavefront scheduler runs the same per-path arithmetic: replay parity holds"""
+    R = _renderer(scene_file, R_lts, R_mirror)
+    g = load_paths(path_file)
+    kw = dict(width=g["W"], height=g["H"], spp=g["spp"], max_depth=g["D"], camera=g["camera"], f_distance=g["f_distance"],
+              semantics=g["semantics"], traversal="compat", real="f64", rand0=g["rand0"], rand1=g["rand1"],
+              light_idx=g["light_idx"], return_samples=True)
+    film, samples, cnt = R.render(scheduler="wavefront", **kw)
+    assert (rel_err(samples, g["radiance"]) > REL_TOL).sum() == 0
+    assert cnt["paths"] == g["W"] * g["H"] * g["spp"] and cnt["frame_overflow"] == 0
+    assert np.allclose(film, samples.sum(axis=2), rtol=1e-12, atol=1e-12)
+    _, s_mk, c_mk = R.render(scheduler="megakernel", **kw)
+    assert np.array_equal(samples, s_mk)                      # identical per-path results, bit for bit
+    for k in ("rays_ext", "rays_shadow", "max_frames", "tri_tests"):
+        assert cnt[k] == c_mk[k], k
+
+
+@pytest.mark.parametrize("real", ["f32", "f64"])
+@pytest.mark.parametrize("semantics", ["reference", "iterative"])
+@pytest.mark.parametrize("trav", ["compat", "nearest", "lbvh"])
+def test_wavefront_equals_megakernel(R_lts, trav, semantics, real):
+    ps, nodes, cam, f = load_scene("lts_scene.npz")
+    kw = dict(width=96, height=64, spp=12, max_depth=16, camera=cam, f_distance=f, semantics=semantics, seed=21,
+              traversal=trav, real=real, return_samples=True)
+    f_w, s_w, c_w = R_lts.render(scheduler="wavefront", **kw)
+    f_m, s_m, c_m = R_lts.render(scheduler="megakernel", **kw)
+
+    def same(a, b):
+        if real == "f64":            # built with -fmad=false: both kernels round identically
+            return np.array_equal(a, b)
+        # the fast-math float32 unit may contract/reorder differently per kernel: equal up to rare decision flips
+        return (rel_err(a, b, floor=1e-2) < 1e-3).all(axis=-1).mean() > 0.995
+
+    assert same(s_w, s_m)
+    assert c_w["paths"] == c_m["paths"]
+    if real == "f64":
+        assert np.allclose(f_w, f_m, rtol=1e-12, atol=1e-12)
+        assert c_w["rays_ext"] == c_m["rays_ext"] and c_w["rays_shadow"] == c_m["rays_shadow"]
+    else:
+        assert abs(c_w["rays_ext"] - c_m["rays_ext"]) < 2e-3 * c_m["rays_ext"]
+    # ragged job sizes: fewer paths than one CTA pool, sample sub-range, pixel sub-range
+    for extra in (dict(width=5, height=3, spp=2), dict(s0=5, s1=7), dict(pixel_range=(100, 1000))):
+        a = R_lts.render(scheduler="wavefront", **{**kw, **extra})
+        b = R_lts.render(scheduler="megakernel", **{**kw, **extra})
+        assert same(a[1], b[1]) and a[2]["paths"] == b[2]["paths"]

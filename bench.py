@@ -27,8 +27,20 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = dict(width=1024, height=1024, spp=1024, max_depth=16, semantics="reference")
+# BASELINE.json configs.  c2 is the headline (the config the metric is quoted on); the others are reachable
+# with --config for the per-config table in DESIGN.md.  c5 is the strong-scaling sweep (fixed total work).
+CONFIGS = {
+    "c1": dict(scene="lts", width=256, height=256, spp=16, max_depth=8, semantics="reference", traversal="compat", scaling="weak"),
+    "c2": dict(scene="lts", width=1024, height=1024, spp=1024, max_depth=16, semantics="reference", traversal="compat", scaling="weak"),
+    "c3": dict(scene="mesh", width=1920, height=1080, spp=256, max_depth=8, semantics="iterative", traversal="lbvh", scaling="weak"),
+    "c4": dict(scene="mirror", width=512, height=512, spp=64, max_depth=256, semantics="reference", traversal="compat", scaling="weak"),
+    "c5": dict(scene="lts", width=4096, height=4096, spp=4096, max_depth=8, semantics="reference", traversal="lbvh", scaling="strong"),
+}
+WORKLOAD = dict(CONFIGS["c2"])
 METRIC = "Mrays/s (path segments/s)"
+SCENE_DESC = {"lts": "LTS example scene (Cornell box + glass cone, 28 triangles, 2000 light samples)",
+              "mesh": "Cornell box + 1,000,000-triangle displaced-grid mesh (1,000,028 triangles, GPU LBVH)",
+              "mirror": "closed mirror box (26 triangles, one Light; C4a)"}
 
 
 def parse():
@@ -37,19 +49,36 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--traversal", default="compat", choices=["compat", "nearest", "lbvh"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--traversal", default=None, choices=["compat", "nearest", "lbvh"])
+    ap.add_argument("--scheduler", default="megakernel", choices=["megakernel", "wavefront"])
     ap.add_argument("--real", default="f32", choices=["f32", "f64"])
-    ap.add_argument("--spp", type=int, default=WORKLOAD["spp"], help="override samples per pixel (dev only; invalidates the number)")
-    ap.add_argument("--size", type=int, default=WORKLOAD["width"], help="override film size (dev only)")
+    ap.add_argument("--spp", type=int, default=None, help="override samples per pixel (dev only; invalidates the number)")
+    ap.add_argument("--size", type=int, default=None, help="override film size (dev only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--no-rmse", action="store_true")
+    a = ap.parse_args()
+    WORKLOAD.clear()
+    WORKLOAD.update(CONFIGS[a.config])
+    if a.traversal is None:
+        a.traversal = WORKLOAD["traversal"]
+    if a.spp is None:
+        a.spp = WORKLOAD["spp"]
+    a.width, a.height = (WORKLOAD["width"], WORKLOAD["height"]) if a.size is None else (a.size, a.size)
+    return a
 
 
 def scene_arrays():
-    from light_transport_b200 import api, compat_bvh, pack_scene, scenes
-    objs, lights, cam, depth = scenes.lts_scene(api)
+    from light_transport_b200 import api, compat_bvh, from_arrays, pack_scene, scenes
+    if WORKLOAD["scene"] == "mirror":
+        objs, lights, cam, depth = scenes.mirror_box(api)
+    else:
+        objs, lights, cam, depth = scenes.lts_scene(api)
     ps = pack_scene(objs, lights)
     nodes = compat_bvh.build_compat_nodes(ps.tri_v0, ps.tri_v1, ps.tri_v2)
+    if WORKLOAD["scene"] == "mesh":
+        ps = from_arrays(scenes.heightfield(nx=1000, ny=500), base=ps)
+        nodes = None
     return objs, lights, ps, nodes, cam, depth
 
 
@@ -96,7 +125,7 @@ def cpu_baseline(ps, nodes, cam, depth, args, sample_spp=2, repeats=1):
     from oracle import oracle as O
     S = O.OracleScene(ps, nodes)
     threads = os.cpu_count() or 1
-    kw = dict(width=args.size, height=args.size, spp=args.spp, s0=0, s1=min(sample_spp, args.spp), max_depth=WORKLOAD["max_depth"],
+    kw = dict(width=args.width, height=args.height, spp=args.spp, s0=0, s1=min(sample_spp, args.spp), max_depth=WORKLOAD["max_depth"],
               camera=cam, f_distance=depth, semantics=WORKLOAD["semantics"],
               traversal="compat" if args.traversal == "compat" else "nearest", seed=1, n_threads=threads)
     best = None
@@ -109,8 +138,37 @@ def cpu_baseline(ps, nodes, cam, depth, args, sample_spp=2, repeats=1):
             best = (dt, rays, c)
     dt, rays, c = best
     return {"value": rays / dt / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "port",
-            "sample": f"{args.size}x{args.size} pixels x {kw['s1']} of {args.spp} spp ({c['paths']} paths, {rays} rays, {dt:.2f} s, "
+            "sample": f"{args.width}x{args.height} pixels x {kw['s1']} of {args.spp} spp ({c['paths']} paths, {rays} rays, {dt:.2f} s, "
                       f"OpenMP {threads} threads, oracle/lt_oracle.c)"}, dt, rays
+
+
+def time_to_rmse(R, cam, depth, args, size=256, target=0.01, chunk=32, ref_factor=16):
+    """BASELINE metric, second half: wall-time until the image's RMSE against a reference image with
+    16x the spp of the config (same scene, same integrator) drops below `target`; 256x256 film."""
+    import torch
+    n = size * size * 3
+    kw = dict(width=size, height=size, max_depth=WORKLOAD["max_depth"], camera=cam, f_distance=depth, semantics=WORKLOAD["semantics"],
+              traversal=args.traversal, real=args.real, scheduler=args.scheduler)
+    ref_spp = WORKLOAD["spp"] * ref_factor
+    film = torch.zeros(n, dtype=torch.float64, device="cuda")
+    ref = torch.empty_like(film)
+    R.render(spp=ref_spp, seed=999, film=film, **kw)
+    R.finalize(film, ref_spp, out=ref)
+    film.zero_()
+    img = torch.empty_like(film)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    done, rmse, spp_max = 0, float("inf"), WORKLOAD["spp"] * 4
+    while done < spp_max:                      # progressive passes share one job (spp_max) so counters stay disjoint
+        R.render(spp=spp_max, s0=done, s1=done + chunk, seed=7, film=film, **kw)
+        done += chunk
+        R.finalize(film, done, out=img)
+        rmse = float(torch.sqrt(torch.mean((img - ref) ** 2)))
+        if rmse <= target:
+            break
+    torch.cuda.synchronize()
+    return {"target_rmse": target, "seconds": time.perf_counter() - t0, "spp": done, "rmse": rmse, "film": [size, size],
+            "reference_spp": ref_spp, "reached": rmse <= target}
 
 
 def run_reference(args, rank):
@@ -135,11 +193,14 @@ def run_reference(args, rank):
 
 
 def config_dict(args, n):
-    return {"workload": f"C2: LTS example scene (Cornell box + glass cone, 28 triangles, 2000 light samples), {args.size}x{args.size}, "
-                        f"{args.spp} spp per GPU, max depth {WORKLOAD['max_depth']}, {WORKLOAD['semantics']} semantics, "
-                        f"{args.traversal} traversal, Philox4x32-10",
-            "film": [args.size, args.size], "spp_per_gpu": args.spp, "spp_total": args.spp * n, "max_depth": WORKLOAD["max_depth"],
-            "semantics": WORKLOAD["semantics"], "traversal": args.traversal, "rng": "philox", "parallelism": f"photon-sharded x{n}",
+    strong = WORKLOAD["scaling"] == "strong"
+    per_gpu = args.spp // n if strong else args.spp
+    return {"workload": f"{args.config.upper()}: {SCENE_DESC[WORKLOAD['scene']]}, {args.width}x{args.height}, "
+                        f"{per_gpu} spp per GPU, max depth {WORKLOAD['max_depth']}, {WORKLOAD['semantics']} semantics, "
+                        f"{args.traversal} traversal, {args.scheduler} scheduler, Philox4x32-10",
+            "film": [args.width, args.height], "spp_per_gpu": per_gpu, "spp_total": args.spp if strong else args.spp * n,
+            "max_depth": WORKLOAD["max_depth"], "semantics": WORKLOAD["semantics"], "traversal": args.traversal,
+            "scheduler": args.scheduler, "rng": "philox", "parallelism": f"photon-sharded x{n}",
             "l2": "flushed between timed steps (256 MiB write)"}
 
 
@@ -164,14 +225,14 @@ def main():
     R = host.Renderer(ps, nodes, device=local, build_lbvh=(args.traversal == "lbvh"))
     stream = torch.cuda.current_stream()
     R.set_stream(stream.cuda_stream)
-    W = H = args.size
-    spp_total = args.spp * world
+    W, H = args.width, args.height
+    spp_total = args.spp if WORKLOAD["scaling"] == "strong" else args.spp * world
     s0, s1 = parallel.sample_range(rank, world, spp_total)
     film = torch.zeros(H * W * 3, dtype=torch.float64, device="cuda")
     image = torch.empty_like(film)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     kw = dict(width=W, height=H, spp=spp_total, s0=s0, s1=s1, max_depth=WORKLOAD["max_depth"], camera=cam, f_distance=depth,
-              semantics=WORKLOAD["semantics"], traversal=args.traversal, real=args.real)
+              semantics=WORKLOAD["semantics"], traversal=args.traversal, real=args.real, scheduler=args.scheduler)
 
     def step(i, timed):
         """one pass: clear film, walk, (reduce), finalize.  Returns (event ms, counters)."""
@@ -222,7 +283,9 @@ def main():
     e2e_steps = max(1, min(args.steps, 2))
     sc = api.Scene(camera=cam, lights=lights, width=W, height=H, max_depth=WORKLOAD["max_depth"], f_distance=depth,
                    number_of_samples=1, allocate=False)
-    h2d = sum(v.nbytes for v in ps.to_npz_dict().values()) + sum(getattr(nodes, k).nbytes for k in ("bmin", "bmax", "prim_off", "second", "n_prims", "axis"))
+    h2d = sum(v.nbytes for v in ps.to_npz_dict().values())
+    if nodes is not None:
+        h2d += sum(getattr(nodes, k).nbytes for k in ("bmin", "bmax", "prim_off", "second", "n_prims", "axis"))
     d2h = H * W * 3 * 8
     torch.cuda.synchronize()
     if world > 1:
@@ -232,7 +295,7 @@ def main():
     for i in range(e2e_steps):
         img, info = lt.render_scene(sc, ps, nodes, spp=spp_total, rng="philox", seed=500 + i, semantics=WORKLOAD["semantics"],
                                     traversal=args.traversal, real=args.real, world=(True if world > 1 else None), device=local,
-                                    return_info=True)
+                                    return_info=True, scheduler=args.scheduler)
         e_rays += info["rays_ext"] + info["rays_shadow"]
     torch.cuda.synchronize()
     et = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
@@ -246,7 +309,7 @@ def main():
         peak_tf = R.measure_fp32_peak()
         achieved_tf = flops / (kernel_ns * 1e-9) / 1e12
         out = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-               "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": WORKLOAD["scaling"], "vs_baseline": None,
                "dtype": args.real, "data": "synthetic", "config": config_dict(args, world),
                "mpaths_per_s": paths_all / (ms_max * 1e-3) / 1e6, "rays_per_path": rays_all / max(paths_all, 1),
                "clocks": clocks,
@@ -262,8 +325,10 @@ def main():
                             "box_tests_per_ray": last["box_tests"] / max(last["rays_ext"] + last["rays_shadow"], 1),
                             "tri_tests_per_ray": last["tri_tests"] / max(last["rays_ext"] + last["rays_shadow"], 1),
                             "lane_utilisation": last["lane_steps"] / max(last["lane_slots"], 1)}}
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and WORKLOAD["scene"] != "mesh":
             out["cpu_baseline"], _, _ = cpu_baseline(ps, nodes, cam, depth, args, sample_spp=8)
+        if world == 1 and not args.no_rmse and args.config == "c2":
+            out["time_to_rmse"] = time_to_rmse(R, cam, depth, args)
         print(json.dumps(out))
     R.close()
     if world > 1:

@@ -527,13 +527,14 @@ int lt_render_image(lt_scene* s, const lt_render_params* p, const double* rand0,
     LT_CUDA_OK(cudaMemsetAsync(ctx->film, 0, n * sizeof(double), ctx->stream));
     int rc = lt_render(s, p, rand0, rand1, light_idx, ctx->film, samples_out, c);
     if (rc) return rc;
-    OutBuf<double> out;
-    if ((rc = out.init(image_out, n, false, ctx->stream))) return rc;
     const int ns = p->s1 - p->s0;
     int grid = (int)std::min<int64_t>(((int64_t)n + 255) / 256, (int64_t)ctx->prop.multiProcessorCount * 8);
-    finalize_div_kernel<<<std::max(grid, 1), 256, 0, ctx->stream>>>(ctx->film, (int64_t)n, (double)std::max(ns, 1), out.dev);
+    const bool dev_out = is_device_ptr(image_out);
+    // finalize in place (elementwise) unless the caller gave a device buffer; then ONE copy of the image
+    double* dst = dev_out ? image_out : ctx->film;
+    finalize_div_kernel<<<std::max(grid, 1), 256, 0, ctx->stream>>>(ctx->film, (int64_t)n, (double)std::max(ns, 1), dst);
     LT_CUDA_OK(cudaGetLastError());
-    if ((rc = out.finish(ctx->stream))) return rc;
+    if (!dev_out) LT_CUDA_OK(cudaMemcpyAsync(image_out, ctx->film, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     LT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
     if (c) c->launches += 1;
     return LT_OK;

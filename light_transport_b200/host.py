@@ -9,6 +9,7 @@ a missing library or GPU raises.
 """
 from __future__ import annotations
 
+import atexit
 import ctypes as C
 import os
 
@@ -109,15 +110,38 @@ def _ptr(a, typ):
     return C.cast(C.c_void_p(int(a)), typ)
 
 
+_ctx_cache: dict[int, C.c_void_p] = {}
+
+
+def _get_ctx(device: int) -> C.c_void_p:
+    """One lt_ctx per device and process: stream, film/arena scratch and the CUDA context set-up are paid
+    once, not per render_scene call (creating them per call cost 0.1-1.3 s of cudaMalloc/cudaFree jitter)."""
+    ctx = _ctx_cache.get(device)
+    if ctx is None:
+        ctx = C.c_void_p()
+        _check(lib().lt_init(C.c_int(device), C.byref(ctx)))
+        _ctx_cache[device] = ctx
+    return ctx
+
+
+@atexit.register
+def _destroy_contexts():
+    for ctx in _ctx_cache.values():
+        try:
+            lib().lt_destroy(ctx)
+        except Exception:
+            pass
+    _ctx_cache.clear()
+
+
 class Renderer:
-    """A device context plus one uploaded scene (the 'H2D once' half of the boundary)."""
+    """One uploaded scene on a device (the 'H2D once' half of the boundary); shares the per-device context."""
 
     def __init__(self, packed: _pack.PackedScene, nodes: compat_bvh.CompatNodes | None = None, device: int = 0,
                  build_lbvh: bool = False):
         L = lib()
-        self._ctx = C.c_void_p()
+        self._ctx = _get_ctx(device)
         self._scene = C.c_void_p()
-        _check(L.lt_init(C.c_int(device), C.byref(self._ctx)))
         f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
         i = lambda a: np.ascontiguousarray(a, dtype=np.int32)
         self._keep = dict(tri_v0=f(packed.tri_v0), tri_v1=f(packed.tri_v1), tri_v2=f(packed.tri_v2), tri_n=f(packed.tri_n),
@@ -252,11 +276,9 @@ class Renderer:
 
     def close(self):
         if getattr(self, "_scene", None) and self._scene:
+            self.set_stream(None)
             lib().lt_scene_destroy(self._scene)
             self._scene = C.c_void_p()
-        if getattr(self, "_ctx", None) and self._ctx:
-            lib().lt_destroy(self._ctx)
-            self._ctx = C.c_void_p()
 
     def __del__(self):
         try:

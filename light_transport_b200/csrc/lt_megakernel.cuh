@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(LT_BLOCK, sizeof(R) == 4 ? LT_MIN_BLOCKS_F32 :
                 else if (TRAV == LT_TRAV_NEAREST)
                     nearest_query<R>(tris, P.S.n_tris, ln.o, ln.d, eps, ln.tlimit, anyhit, ln.skip, prim, t, st);
                 else
-                    lbvh_query<R>(P.S.lbvh, tris, P.S.n_tris, ln.o, ln.d, eps, ln.tlimit, anyhit, ln.skip, prim, t, st);
+                    lbvh_query<R>(am, P.S.lbvh, tris, P.S.n_tris, ln.o, ln.d, eps, ln.tlimit, anyhit, ln.skip, prim, t, st);
                 int stt;
                 R adv_rand0 = (R)0;
                 if (ln.qtype == 1) {
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(LT_BLOCK) intersect_kernel(const IntersectPara
             else if (TRAV == LT_TRAV_NEAREST)
                 nearest_query<R>(P.S.tris, P.S.n_tris, o, d, (R)P.eps, Lim<R>::inf(), false, -1, prim, t, st);
             else
-                lbvh_query<R>(P.S.lbvh, P.S.tris, P.S.n_tris, o, d, (R)P.eps, Lim<R>::inf(), false, -1, prim, t, st);
+                lbvh_query<R>(am, P.S.lbvh, P.S.tris, P.S.n_tris, o, d, (R)P.eps, Lim<R>::inf(), false, -1, prim, t, st);
             P.prim[r] = prim;
             P.t[r] = prim >= 0 ? (double)t : (double)Lim<double>::inf();
         }

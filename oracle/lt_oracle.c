@@ -350,6 +350,163 @@ static void trace_path_reference(walk_t *w, ray_t *ray, int bounce, double *ligh
     w->depth_frames--;
 }
 
+static void add_counters(lto_counters *a, const lto_counters *b);
+
+/* ---------------- R/src/path_tracing.py:23-159 again, now with every side output
+ * and the calculate_grad gate (rank 2).  `rlp` is the frame's record_log_pdf array (returned value),
+ * dl/il the frame's direct/indirect lists [3][D] (may be NULL below the root: the caller drops them). */
+typedef struct {
+    double *scene_rlp;      /* scene.record_log_pdf[i,j,s,:]  (written when !grad) */
+    int8_t *bounce_record;  /* scene.bounce_record[i,j,s,:]   (written when !grad, read when grad) */
+    const double *r0, *r1;  /* rand sets of THIS replay (may differ from the walk's base rows) */
+    int grad;
+} rec_t;
+
+static void trace_path_reference_rec(walk_t *w, const rec_t *rc, ray_t *ray, int bounce, double *light, double *rlp,
+                                     double *dl, double *il) {
+    const lto_scene *S = w->S;
+    const lto_params *P = w->P;
+    const int D = P->max_depth;
+    double T[3] = {1, 1, 1};
+    light[0] = light[1] = light[2] = 0;
+    for (int b = 0; b < D; ++b) rlp[b] = 0;
+    if (dl) for (int k = 0; k < 3 * D; ++k) { dl[k] = 0; il[k] = 0; }
+    for (;;) {
+        /* :33-34 read rand_set[bounce] before any test (index D is read but unused there) */
+        if (rc->grad && bounce < D && rc->bounce_record[bounce] == 0) break;       /* :37-39 */
+        if (bounce >= D) break;
+        double rand_0 = rc->r0[bounce], rand_1 = rc->r1[bounce];
+        int prim; double t;
+        w->c.rays_ext++;
+        if (!closest_hit(w, ray, &prim, &t)) {
+            if (!rc->grad) for (int b = bounce; b < D; ++b) rc->bounce_record[b] = 0;   /* :50-52 */
+            break;
+        }
+        double p[3] = {ray->o[0] + t * ray->d[0], ray->o[1] + t * ray->d[1], ray->o[2] + t * ray->d[2]};
+        int m = S->tri_mat[prim];
+        double n[3] = {S->tri_n[3 * prim], S->tri_n[3 * prim + 1], S->tri_n[3 * prim + 2]};
+        if (S->tri_light[prim] && bounce == 0)
+            for (int c = 0; c < 3; ++c) light[c] += S->mat_emission[m] * T[c];
+        int inside = 0;
+        if (dot3(n, ray->d) > 0) { n[0] = -n[0]; n[1] = -n[1]; n[2] = -n[2]; inside = 1; }
+        if (S->mat_flags[m] & 1) {
+            double so[3] = {p[0] + P->eps * n[0], p[1] + P->eps * n[1], p[2] + P->eps * n[2]};
+            double direct[3], dir[3], tp[3];
+            cast_one_shadow_ray(w, prim, so, n, direct);
+            double pdf = cosine_weighted_hemisphere_sampling(n, ray->d, rand_0, rand_1, dir);
+            if (pdf == 0) {
+                if (!rc->grad) for (int b = bounce + 1; b < D; ++b) rc->bounce_record[b] = 0;  /* :77-79 */
+                break;
+            }
+            for (int c = 0; c < 3; ++c) { ray->o[c] = p[c] + P->eps * dir[c]; ray->d[c] = dir[c]; }
+            double cos_theta = dot3(dir, n);
+            for (int c = 0; c < 3; ++c) T[c] *= (S->mat_kd[3 * m + c] * INV_PI) * cos_theta / pdf;
+            double child_rlp[D > 0 ? D : 1];
+            trace_path_reference_rec(w, rc, ray, bounce + 1, tp, child_rlp, 0, 0);
+            for (int b = 0; b < D; ++b) rlp[b] = child_rlp[b];          /* :93 the callee's array REPLACES ours */
+            rlp[bounce] = log(pdf);                                      /* :94 */
+            if (!rc->grad) rc->scene_rlp[bounce] = log(pdf);             /* :95-96 */
+            if (dl) for (int c = 0; c < 3; ++c) { dl[c * D + bounce] = direct[c]; il[c * D + bounce] = T[c] * tp[c]; }
+            for (int c = 0; c < 3; ++c) light[c] += direct[c] + T[c] * tp[c];
+        } else if (!specular_bounce(S, m, inside, p, n, rand_0, P->eps, ray)) {
+            break;
+        }
+        if (bounce > P->rr_start) {
+            double r_r = 1 - T[1] > P->rr_floor ? 1 - T[1] : P->rr_floor;
+            if (rand_0 < r_r) {
+                if (!rc->grad) for (int b = bounce + 1; b < D; ++b) rc->bounce_record[b] = 0;  /* :151-153 */
+                break;
+            }
+            for (int c = 0; c < 3; ++c) T[c] /= 1 - r_r;
+        }
+        bounce += 1;
+    }
+}
+
+/* R/src/path_tracing.py:19-21 (Q16: this is sigma(-x)) */
+static inline double sigmoid_ref(double x) { return 1 / (1 + exp(x)); }
+
+/* render_scene_samples' per-sample body (R/src/path_tracing.py:270-303) for replayed random numbers:
+ * the base walk with its side outputs, then calculate_gradients (:203-249) when minus/plus are given. */
+int lto_render_records(const lto_scene *S, const lto_params *P, const double *rand0, const double *rand1,
+                       const double *logit0, const double *logit1, const int32_t *light_idx, double *samples_out,
+                       double *record_log_pdf, double *scene_record_log_pdf, int8_t *bounce_record, double *direct_list,
+                       double *indirect_list, double *rlp_minus, double *rlp_plus, lto_counters *cnt) {
+    const int W = P->width, H = P->height, D = P->max_depth, spp = P->spp;
+    if (!rand0 || !rand1 || P->s0 != 0 || P->s1 != spp || D <= 0) return -2;
+    const double aspect = (double)W / (double)H, top = 1 / aspect, bottom = -1 / aspect;
+    const double step_y = H > 1 ? (bottom - top) / (double)(H - 1) : 0;
+    const double step_x = W > 1 ? (1.0 - (-1.0)) / (double)(W - 1) : 0;
+    lto_counters total;
+    memset(&total, 0, sizeof total);
+    int err = 0;
+#pragma omp parallel
+    {
+        walk_t w;
+        memset(&w, 0, sizeof w);
+        w.S = S; w.P = P;
+        double *r0s = (double *)malloc(sizeof(double) * 2 * (size_t)D), *r1s = r0s + D;
+#pragma omp for schedule(dynamic, 16)
+        for (int64_t pix = 0; pix < (int64_t)W * H; ++pix) {
+            int i = (int)(pix / W), j = (int)(pix % W);
+            double y = (H > 1 && i == H - 1) ? bottom : top + i * step_y;
+            double x = (W > 1 && j == W - 1) ? 1.0 : -1.0 + j * step_x;
+            for (int s = 0; s < spp; ++s) {
+                uint64_t path = (uint64_t)pix * (uint64_t)spp + (uint64_t)s;
+                const double *b0 = rand0 + path * (uint64_t)D, *b1 = rand1 + path * (uint64_t)D;
+                w.path_id = path;
+                w.r0 = b0; w.r1 = b1;
+                w.lidx = light_idx ? light_idx + path * (uint64_t)P->n_light_idx : 0;
+                w.nee_count = 0;
+                ray_t cam_ray, ray;
+                double end[3] = {x + b0[0] / W, y + b0[0] / H, P->f_distance};
+                for (int c = 0; c < 3; ++c) { cam_ray.o[c] = P->camera[c]; cam_ray.d[c] = end[c] - P->camera[c]; }
+                normalize3(cam_ray.d);
+                rec_t rc;
+                rc.scene_rlp = scene_record_log_pdf + path * (uint64_t)D;
+                rc.bounce_record = bounce_record + path * (uint64_t)D;
+                for (int b = 0; b < D; ++b) { rc.scene_rlp[b] = 0; rc.bounce_record[b] = 1; }   /* R/src/scene.py:72-73 */
+                rc.r0 = b0; rc.r1 = b1; rc.grad = 0;
+                double L[3];
+                ray = cam_ray;
+                trace_path_reference_rec(&w, &rc, &ray, 0, L, record_log_pdf + path * (uint64_t)D,
+                                         direct_list ? direct_list + path * 3 * (uint64_t)D : 0,
+                                         indirect_list ? indirect_list + path * 3 * (uint64_t)D : 0);
+                w.c.paths++;
+                if (samples_out) for (int c = 0; c < 3; ++c) samples_out[path * 3 + c] = L[c];
+                if (rlp_minus && rlp_plus) {                      /* calculate_gradients, :203-249 */
+                    const double *l0 = logit0 + path * (uint64_t)D, *l1 = logit1 + path * (uint64_t)D;
+                    rc.grad = 1;
+                    for (int which = 0; which < 2; ++which)
+                        for (int ri = 0; ri < D; ++ri)
+                            for (int sign = 0; sign < 2; ++sign) {
+                                for (int b = 0; b < D; ++b) { r0s[b] = sigmoid_ref(l0[b]); r1s[b] = sigmoid_ref(l1[b]); }
+                                const double sstep = 0.01;
+                                double *tgt = which == 0 ? r0s : r1s;
+                                const double *lg = which == 0 ? l0 : l1;
+                                double pert = lg[ri];
+                                if (sign == 0) pert -= sstep; else pert += sstep;    /* logits[rand_i] -= / += _s */
+                                tgt[ri] = sigmoid_ref(pert);
+                                rc.r0 = r0s; rc.r1 = r1s;
+                                ray = cam_ray;
+                                double Lg[3];
+                                double *out = (sign == 0 ? rlp_minus : rlp_plus) + (path * 2 * (uint64_t)D + (uint64_t)(which * D + ri)) * (uint64_t)D;
+                                trace_path_reference_rec(&w, &rc, &ray, 0, Lg, out, 0, 0);
+                            }
+                }
+            }
+        }
+        free(r0s);
+#pragma omp critical
+        {
+            add_counters(&total, &w.c);
+            if (w.error) err = -1;
+        }
+    }
+    if (cnt) *cnt = total;
+    return err;
+}
+
 /* ---------------- R/src/path_tracing_fix1.py:17-136 trace_path (iterative reformulation) */
 static void trace_path_iterative(walk_t *w, ray_t *ray, int bounce, double *light) {
     const lto_scene *S = w->S;

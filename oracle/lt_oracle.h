@@ -59,6 +59,16 @@ int lto_intersect(const lto_scene *S, int traversal, const double *o, const doub
 int lto_render(const lto_scene *S, const lto_params *P, const double *rand0, const double *rand1,
                const int32_t *light_idx, double *film_sum, double *samples_out, lto_counters *c);
 
+/* render_scene_samples' per-sample outputs for replayed random numbers:
+ * samples [H][W][spp][3]; record_log_pdf (the array trace_path RETURNS), scene_record_log_pdf and
+ * bounce_record (the arrays it writes into Scene) [H][W][spp][D]; direct/indirect lists of the root frame
+ * [H][W][spp][3][D]; and, when rlp_minus/rlp_plus are given, calculate_gradients' replays
+ * [H][W][spp][2D][D] driven by logit0/logit1 = log(u/(1-u)).  Whole sample range only. */
+int lto_render_records(const lto_scene *S, const lto_params *P, const double *rand0, const double *rand1,
+                       const double *logit0, const double *logit1, const int32_t *light_idx, double *samples_out,
+                       double *record_log_pdf, double *scene_record_log_pdf, int8_t *bounce_record, double *direct_list,
+                       double *indirect_list, double *rlp_minus, double *rlp_plus, lto_counters *cnt);
+
 /* Philox4x32-10 known-answer access for the tests */
 void lto_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 

@@ -131,3 +131,42 @@ def render(scene: OracleScene, *, width, height, spp, max_depth, camera, f_dista
     if rc:
         raise IndexError("setitem out of range (Q9b)")
     return film, samples, cnt.as_dict()
+
+
+def render_records(scene: OracleScene, *, width, height, spp, max_depth, camera, f_distance, rand0, rand1, light_idx=None,
+                   traversal="compat", gradients=False, n_threads=0):
+    """render_scene_samples' per-sample outputs (lto_render_records): dict with samples, record_log_pdf,
+    scene_record_log_pdf, bounce_record, direct_list, indirect_list and (gradients=True) rlp_minus/rlp_plus/record_s."""
+    p = LtoParams()
+    p.width, p.height, p.spp, p.s0, p.s1, p.max_depth = width, height, spp, 0, spp, max_depth
+    p.semantics, p.traversal, p.rr_start = 0, 0 if traversal == "compat" else 1, 3
+    p.rr_floor, p.eps, p.f_distance, p.n_threads = 0.05, 0.000001, float(f_distance), n_threads
+    for k in range(3):
+        p.camera[k] = float(camera[k])
+    rand0 = np.ascontiguousarray(rand0, dtype=np.float64)
+    rand1 = np.ascontiguousarray(rand1, dtype=np.float64)
+    assert rand0.shape == (height, width, spp, max_depth)
+    l0 = np.log(rand0 / (1 - rand0))          # R/src/scene.py:70-71
+    l1 = np.log(rand1 / (1 - rand1))
+    if light_idx is not None:
+        light_idx = np.ascontiguousarray(light_idx, dtype=np.int32)
+        p.n_light_idx = light_idx.shape[3]
+    D = max_depth
+    out = dict(samples=np.zeros((height, width, spp, 3)), record_log_pdf=np.zeros((height, width, spp, D)),
+               scene_record_log_pdf=np.zeros((height, width, spp, D)), bounce_record=np.ones((height, width, spp, D), np.int8),
+               direct_list=np.zeros((height, width, spp, 3, D)), indirect_list=np.zeros((height, width, spp, 3, D)))
+    if gradients:
+        out["rlp_minus"] = np.zeros((height, width, spp, 2 * D, D))
+        out["rlp_plus"] = np.zeros((height, width, spp, 2 * D, D))
+        out["record_s"] = np.full((height, width, spp, 2 * D), 0.01)
+    cnt = LtoCounters()
+    L = lib()
+    L.lto_render_records.restype = C.c_int
+    rc = L.lto_render_records(C.byref(scene.c), C.byref(p), _p(rand0, PD), _p(rand1, PD), _p(l0, PD), _p(l1, PD), _p(light_idx, PI32),
+                              _p(out["samples"], PD), _p(out["record_log_pdf"], PD), _p(out["scene_record_log_pdf"], PD),
+                              out["bounce_record"].ctypes.data_as(C.POINTER(C.c_int8)), _p(out["direct_list"], PD),
+                              _p(out["indirect_list"], PD), _p(out.get("rlp_minus"), PD), _p(out.get("rlp_plus"), PD), C.byref(cnt))
+    if rc:
+        raise RuntimeError(f"lto_render_records failed ({rc})")
+    out["counters"] = cnt.as_dict()
+    return out

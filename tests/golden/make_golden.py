@@ -175,6 +175,69 @@ def drive_fix1(scene, prims, bvh, seed_base, out):
                 out[i, j, s, :] = fix_trace(scene, prims, bvh, ray, 0, [i, j, s])
 
 
+ref_grads = r_pt.calculate_gradients
+
+
+@numba.njit
+def drive_records(scene, prims, bvh, seed_base, out, out_rlp, out_dl, out_il, out_minus, out_plus, out_s):
+    # restates the per-sample body of render_scene_samples, R/src/path_tracing.py:270-303
+    H, W, S = scene.height, scene.width, scene.number_of_samples
+    top_bottom = np.linspace(scene.top, scene.bottom, H)
+    left_right = np.linspace(scene.left, scene.right, W)
+    for i in range(H):
+        y = top_bottom[i]
+        for j in range(W):
+            x = left_right[j]
+            for s in range(S):
+                r0 = scene.rand_0[i, j, s]
+                r1 = scene.rand_1[i, j, s]
+                end = np.array([x, y, scene.f_distance, 1], dtype=np.float64)
+                end[0] += r0[0] / W
+                end[1] += r0[0] / H
+                origin = np.array([scene.camera[0], scene.camera[1], scene.camera[2], 1], dtype=np.float64)
+                direction = normalize(end - origin)
+                ray = Ray(origin, direction)
+                np.random.seed(seed_base + (i * W + j) * S + s)
+                L, rlp, lists = ref_trace(scene, prims, bvh, ray, 0, r0, r1, (i, j, s), False)
+                out[i, j, s, :] = L
+                out_rlp[i, j, s, :] = rlp
+                out_dl[i, j, s, :, :] = lists[0]
+                out_il[i, j, s, :, :] = lists[1]
+                m, p, ss = ref_grads(scene, prims, bvh, origin, direction, scene.rand_0_logit[i, j, s], scene.rand_1_logit[i, j, s], (i, j, s))
+                out_minus[i, j, s, :, :] = m
+                out_plus[i, j, s, :, :] = p
+                out_s[i, j, s, :] = ss
+
+
+def golden_records(name, objects, lin, lights, camera, fdist, W, H, spp, D, rand_seed, seed_base):
+    sc = r_scene.Scene(camera=camera, lights=lights, width=W, height=H, max_depth=D, f_distance=fdist, number_of_samples=spp)
+    np.random.seed(rand_seed)
+    rand_0 = np.random.rand(H, W, spp, D)
+    rand_1 = np.random.rand(H, W, spp, D)
+    sc.rand_0 = rand_0.copy()
+    sc.rand_1 = rand_1.copy()
+    sc.rand_0_logit = np.log(rand_0 / (1 - rand_0))          # R/src/scene.py:70-71
+    sc.rand_1_logit = np.log(rand_1 / (1 - rand_1))
+    out = np.zeros((H, W, spp, 3)); rlp = np.zeros((H, W, spp, D))
+    dl = np.zeros((H, W, spp, 3, D)); il = np.zeros((H, W, spp, 3, D))
+    minus = np.zeros((H, W, spp, 2 * D, D)); plus = np.zeros((H, W, spp, 2 * D, D)); ss = np.zeros((H, W, spp, 2 * D))
+    t0 = time.time()
+    drive_records(sc, objects, lin, seed_base, out, rlp, dl, il, minus, plus, ss)
+    nL = len(lights)
+    lidx = np.zeros((H * W * spp, K_LIGHT), np.int16)
+    tmp = np.zeros(K_LIGHT, np.int64)
+    for p in range(H * W * spp):
+        draw_light_idx(seed_base + p, nL, tmp)
+        lidx[p] = tmp
+    print(f"{name}: {H*W*spp} samples with records + {4*D} gradient replays each in {time.time()-t0:.1f}s; "
+          f"bounce_record mean {sc.bounce_record.mean():.3f}")
+    np.savez_compressed(os.path.join(OUT, name), radiance=out, record_log_pdf=rlp, direct_list=dl, indirect_list=il,
+                        rlp_minus=minus, rlp_plus=plus, record_s=ss, scene_record_log_pdf=np.asarray(sc.record_log_pdf),
+                        bounce_record=np.asarray(sc.bounce_record), light_idx=lidx.reshape(H, W, spp, K_LIGHT),
+                        W=W, H=H, spp=spp, D=D, rand_seed=rand_seed, seed_base=seed_base, camera=camera[:3], f_distance=fdist,
+                        semantics="reference", image=np.clip(out.mean(axis=2), 0, 1))
+
+
 def make_rays(rng, packed, camera, fdist, n_cam=64, n_int=6000, n_light=6000):
     ys = np.linspace(1, -1, n_cam)
     xs = np.linspace(-1, 1, n_cam)
@@ -245,6 +308,13 @@ def golden_paths(name, objects, lin, lights, camera, fdist, W, H, spp, D, rand_s
 
 
 def main():
+    only = sys.argv[1] if len(sys.argv) > 1 else None
+    if only == "records":
+        objects, lights, camera, depth = scenes.lts_scene(ref_ns, new_list=numba.typed.List)
+        lin = ref_bvh(objects)
+        golden_records("records_lts_d4.npz", objects, lin, lights, camera, depth, 24, 24, 2, 4, 5, 700000)
+        golden_records("records_lts_d8.npz", objects, lin, lights, camera, depth, 16, 12, 2, 8, 6, 800000)
+        return
     # ---- verify the light-index replay recipe (Q12) ----
     a = check_choice(123, 2000, 16)
     b = np.zeros(16, np.int64)
@@ -266,6 +336,9 @@ def main():
     golden_paths("paths_lts_ref_d8.npz", objects, lin, lights, camera, depth, 48, 48, 4, 8, 1, 1000, "reference")
     golden_paths("paths_lts_ref_d16.npz", objects, lin, lights, camera, depth, 32, 24, 4, 16, 2, 500000, "reference")
     golden_paths("paths_lts_iter_d8.npz", objects, lin, lights, camera, depth, 48, 48, 4, 8, 3, 900000, "iterative")
+    if only in (None, "records"):
+        golden_records("records_lts_d4.npz", objects, lin, lights, camera, depth, 24, 24, 2, 4, 5, 700000)
+        golden_records("records_lts_d8.npz", objects, lin, lights, camera, depth, 16, 12, 2, 8, 6, 800000)
 
     # ---- mirror box (C4a) ----
     mobj, mlights, mcam, mf = scenes.mirror_box(ref_ns, new_list=numba.typed.List)

@@ -100,3 +100,23 @@ def test_oracle_properties(oracle):
     assert not z.any() and cz["paths"] == 0
     z, _, _ = oracle.render(S, **{**kw, "max_depth": 0})
     assert not z.any()
+
+
+@pytest.mark.parametrize("name", ["records_lts_d4.npz", "records_lts_d8.npz"])
+def test_records_and_gradients_bit_exact(oracle, name):
+    """per-sample side outputs of trace_path (returned record_log_pdf, the arrays it
+    writes into Scene, the root frame's direct/indirect lists) and calculate_gradients' 4*D replays
+    (R/src/path_tracing.py:203-249), against the unmodified reference."""
+    ps, nodes, _, _ = load_scene("lts_scene.npz")
+    g = np.load(os.path.join(GOLDEN, name))
+    W, H, spp, D = int(g["W"]), int(g["H"]), int(g["spp"]), int(g["D"])
+    np.random.seed(int(g["rand_seed"]))
+    r0, r1 = np.random.rand(H, W, spp, D), np.random.rand(H, W, spp, D)
+    out = oracle.render_records(oracle.OracleScene(ps, nodes), width=W, height=H, spp=spp, max_depth=D, camera=g["camera"],
+                                f_distance=float(g["f_distance"]), rand0=r0, rand1=r1, light_idx=g["light_idx"].astype(np.int32),
+                                gradients=True)
+    for k, gk in (("samples", "radiance"), ("record_log_pdf", "record_log_pdf"), ("scene_record_log_pdf", "scene_record_log_pdf"),
+                  ("bounce_record", "bounce_record"), ("direct_list", "direct_list"), ("indirect_list", "indirect_list"),
+                  ("rlp_minus", "rlp_minus"), ("rlp_plus", "rlp_plus"), ("record_s", "record_s")):
+        assert np.array_equal(out[k], g[gk]), k
+    assert (g["rlp_minus"] != g["rlp_plus"]).any()        # the replays do differ: the fixture exercises them

@@ -137,6 +137,20 @@ int lt_render(lt_scene *, const lt_render_params *, const double *rand0, const d
 int lt_render_image(lt_scene *, const lt_render_params *, const double *rand0, const double *rand1,
                     const int32_t *light_idx, double *image_out, double *samples_out, lt_counters *c);
 
+/* The per-sample outputs of render_scene_samples (R/src/path_tracing.py:251-303) for replayed random
+ * numbers, REFERENCE semantics, whole sample range, max_depth <= 32:
+ *   samples_out            [H][W][spp][3]     per-path radiance                                  (:297)
+ *   record_log_pdf         [H][W][spp][D]     the array trace_path returns                        (:288,300)
+ *   scene_record_log_pdf   [H][W][spp][D]     Scene.record_log_pdf side effect                    (:95-96)
+ *   bounce_record          [H][W][spp][D] i8  Scene.bounce_record side effect                     (:50-52,77-79,151-153)
+ *   direct_list, indirect_list [H][W][spp][3][D]  the root frame's lists, optional               (:99-100)
+ *   rlp_minus, rlp_plus    [H][W][spp][2D][D] calculate_gradients' replays (:203-249), optional; need
+ *                          logit0/logit1 [H][W][spp][D] = log(u/(1-u)) (Scene.rand_0_logit, scene.py:70-71). */
+int lt_render_records(lt_scene *, const lt_render_params *, const double *rand0, const double *rand1,
+                      const double *logit0, const double *logit1, const int32_t *light_idx, double *samples_out,
+                      double *record_log_pdf, double *scene_record_log_pdf, int8_t *bounce_record, double *direct_list,
+                      double *indirect_list, double *rlp_minus, double *rlp_plus, lt_counters *c);
+
 /* image = clip(film_sum / spp_total, 0, 1)   (R/src/path_tracing.py:304-305) */
 int lt_film_finalize(lt_ctx *, const double *film_sum, int64_t n_values, int64_t spp_total, double *image_out);
 

@@ -8,12 +8,12 @@ fallback — calls raise if the library or a GPU is missing.
 from . import api, scenes, compat_bvh  # noqa: F401
 from ._pack import PackedScene, pack_scene, from_arrays  # noqa: F401
 
-__all__ = ["render_scene", "intersect", "Renderer", "api", "scenes", "compat_bvh", "PackedScene",
+__all__ = ["render_scene", "render_scene_full", "intersect", "Renderer", "api", "scenes", "compat_bvh", "PackedScene",
            "pack_scene", "from_arrays"]
 
 
 def __getattr__(name):
-    if name in ("render_scene", "intersect", "Renderer", "lib"):
+    if name in ("render_scene", "render_scene_full", "intersect", "Renderer", "lib"):
         from . import host
         return getattr(host, name)
     raise AttributeError(name)

@@ -8,6 +8,7 @@
 
 #include "lt_megakernel.cuh"
 #include "lt_wavefront.cuh"
+#include "lt_record.cuh"
 #include "lt_host.h"
 
 namespace lt {
@@ -339,6 +340,82 @@ static int do_render(lt_scene* s, const lt_render_params* p, const double* rand0
     return LT_OK;
 }
 
+template <typename R>
+static int do_records(lt_scene* s, const lt_render_params* p, const double* rand0, const double* rand1, const double* logit0,
+                      const double* logit1, const int32_t* light_idx, double* samples_out, double* record_log_pdf,
+                      double* scene_rlp, int8_t* bounce_record, double* direct_list, double* indirect_list, double* rlp_minus,
+                      double* rlp_plus, lt_counters* c) {
+    lt_ctx* ctx = s->ctx;
+    cudaStream_t st = ctx->stream;
+    const int W = p->width, H = p->height, D = p->max_depth, spp = p->spp;
+    const size_t paths = (size_t)W * H * spp;
+    const bool grads = rlp_minus && rlp_plus;
+    InBuf<double> b0, b1, bl0, bl1;
+    InBuf<int32_t> bl;
+    OutBuf<double> o_s, o_rlp, o_srlp, o_dl, o_il, o_m, o_p;
+    OutBuf<int8_t> o_br;
+    int rc;
+    if ((rc = b0.init(rand0, paths * D, st)) || (rc = b1.init(rand1, paths * D, st)) ||
+        (rc = bl.init(light_idx, paths * (size_t)p->n_light_idx, st)) || (rc = o_s.init(samples_out, paths * 3, false, st)) ||
+        (rc = o_rlp.init(record_log_pdf, paths * D, false, st)) || (rc = o_srlp.init(scene_rlp, paths * D, false, st)) ||
+        (rc = o_br.init(bounce_record, paths * D, false, st)) || (rc = o_dl.init(direct_list, paths * 3 * D, false, st)) ||
+        (rc = o_il.init(indirect_list, paths * 3 * D, false, st)))
+        return rc;
+    if (grads && ((rc = bl0.init(logit0, paths * D, st)) || (rc = bl1.init(logit1, paths * D, st)) ||
+                  (rc = o_m.init(rlp_minus, paths * 2 * D * D, false, st)) || (rc = o_p.init(rlp_plus, paths * 2 * D * D, false, st))))
+        return rc;
+    LT_CUDA_OK(cudaMemsetAsync(ctx->d_counters, 0, sizeof(lt_counters), st));
+    WalkParams<R> P;
+    memset(&P, 0, sizeof P);
+    fill_view<R>(s, P.S);
+    P.width = W; P.height = H; P.spp = spp; P.s0 = 0; P.ns = spp; P.max_depth = D;
+    P.rr_start = p->rr_start; P.n_light_idx = p->n_light_idx; P.semantics = LT_SEM_REFERENCE; P.traversal = p->traversal;
+    P.rr_floor = p->rr_floor; P.eps = p->eps;
+    for (int k = 0; k < 3; ++k) P.cam[k] = p->camera[k];
+    P.f_distance = p->f_distance;
+    const double aspect = (double)W / (double)H;
+    P.top = 1 / aspect; P.bottom = -1 / aspect;
+    P.step_y = H > 1 ? (P.bottom - P.top) / (double)(H - 1) : 0.0;
+    P.step_x = W > 1 ? (1.0 - (-1.0)) / (double)(W - 1) : 0.0;
+    P.seed = p->seed;
+    P.rand0 = b0.dev; P.rand1 = b1.dev; P.light_idx = bl.dev;
+    P.samples = o_s.dev;
+    P.counters = reinterpret_cast<unsigned long long*>(ctx->d_counters);
+    RecParams RP;
+    memset(&RP, 0, sizeof RP);
+    RP.rlp_a = o_rlp.dev; RP.scene_rlp = o_srlp.dev; RP.bounce_record = reinterpret_cast<signed char*>(o_br.dev);
+    RP.direct = (o_dl.dev && o_il.dev) ? o_dl.dev : nullptr; RP.indirect = RP.direct ? o_il.dev : nullptr;
+    RP.grad = 0; RP.mult = 1;
+    P.total_paths = (int64_t)paths;
+    auto grid_for = [&](int64_t items) { return (int)std::max<int64_t>(1, std::min<int64_t>((items + LT_BLOCK - 1) / LT_BLOCK, (int64_t)ctx->prop.multiProcessorCount * 8)); };
+    LT_CUDA_OK(cudaEventRecord(ctx->ev0, st));
+    if ((rc = launch_record<R>(P, RP, grid_for(P.total_paths), st))) return rc;
+    int launches = 1;
+    if (grads) {       // calculate_gradients: 4*D gated replays per sample, only their returned arrays are kept
+        RP.grad = 1; RP.mult = 4 * D;
+        RP.rlp_a = o_m.dev; RP.rlp_b = o_p.dev; RP.logit0 = bl0.dev; RP.logit1 = bl1.dev;
+        RP.direct = RP.indirect = nullptr;
+        P.samples = nullptr; P.light_idx = nullptr;      // light picks do not influence record_log_pdf
+        P.total_paths = (int64_t)paths * RP.mult;
+        if ((rc = launch_record<R>(P, RP, grid_for(P.total_paths), st))) return rc;
+        launches = 2;
+    }
+    LT_CUDA_OK(cudaEventRecord(ctx->ev1, st));
+    if ((rc = o_s.finish(st)) || (rc = o_rlp.finish(st)) || (rc = o_srlp.finish(st)) || (rc = o_br.finish(st)) || (rc = o_dl.finish(st)) ||
+        (rc = o_il.finish(st)) || (rc = o_m.finish(st)) || (rc = o_p.finish(st)))
+        return rc;
+    LT_CUDA_OK(cudaStreamSynchronize(st));
+    lt_counters hc;
+    LT_CUDA_OK(cudaMemcpy(&hc, ctx->d_counters, sizeof hc, cudaMemcpyDeviceToHost));
+    float ms = 0;
+    LT_CUDA_OK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    hc.kernel_ns = (uint64_t)(ms * 1e6);
+    hc.launches = launches;
+    if (c) *c = hc;
+    if (hc.frame_overflow) { set_error("record kernel: frame stack overflow"); return LT_E_OVERFLOW; }
+    return LT_OK;
+}
+
 __global__ void finalize_kernel(const double* film, int64_t n, double inv_spp, double* image) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         double v = film[i] * inv_spp;   // color / spp; np.clip(color, 0, 1)
@@ -538,6 +615,38 @@ int lt_render_image(lt_scene* s, const lt_render_params* p, const double* rand0,
     LT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
     if (c) c->launches += 1;
     return LT_OK;
+}
+
+int lt_render_records(lt_scene* s, const lt_render_params* p, const double* rand0, const double* rand1, const double* logit0,
+                      const double* logit1, const int32_t* light_idx, double* samples_out, double* record_log_pdf,
+                      double* scene_record_log_pdf, int8_t* bounce_record, double* direct_list, double* indirect_list,
+                      double* rlp_minus, double* rlp_plus, lt_counters* c) {
+    if (!s || !p || !rand0 || !rand1 || !record_log_pdf || !scene_record_log_pdf || !bounce_record) {
+        set_error("lt_render_records: rand0/rand1 and the three [H][W][spp][D] outputs are required");
+        return LT_E_INVALID;
+    }
+    if (p->width <= 0 || p->height <= 0 || p->spp <= 0 || p->max_depth <= 0 || p->max_depth > LT_REC_FRAMES) {
+        set_error("lt_render_records: need 1 <= max_depth <= %d", LT_REC_FRAMES);
+        return LT_E_INVALID;
+    }
+    if ((rlp_minus == nullptr) != (rlp_plus == nullptr) || (rlp_minus && (!logit0 || !logit1))) {
+        set_error("lt_render_records: rlp_minus/rlp_plus go together and need logit0/logit1");
+        return LT_E_INVALID;
+    }
+    if ((direct_list == nullptr) != (indirect_list == nullptr)) { set_error("direct_list and indirect_list go together"); return LT_E_INVALID; }
+    if (light_idx && p->n_light_idx <= 0) { set_error("light_idx given but n_light_idx == 0"); return LT_E_INVALID; }
+    if (s->n_lights <= 0) { set_error("scene has no Light"); return LT_E_INVALID; }
+    LT_CUDA_OK(cudaSetDevice(s->ctx->device));
+    int rc = check_traversal(s, p->traversal);
+    if (rc) return rc;
+    if (p->real == LT_REAL_F64)
+        return do_records<double>(s, p, rand0, rand1, logit0, logit1, light_idx, samples_out, record_log_pdf, scene_record_log_pdf,
+                                  bounce_record, direct_list, indirect_list, rlp_minus, rlp_plus, c);
+    if (p->real == LT_REAL_F32)
+        return do_records<float>(s, p, rand0, rand1, logit0, logit1, light_idx, samples_out, record_log_pdf, scene_record_log_pdf,
+                                 bounce_record, direct_list, indirect_list, rlp_minus, rlp_plus, c);
+    set_error("unknown real %d", p->real);
+    return LT_E_INVALID;
 }
 
 int lt_film_finalize(lt_ctx* ctx, const double* film_sum, int64_t n, int64_t spp_total, double* image_out) {

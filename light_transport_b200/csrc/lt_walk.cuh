@@ -64,6 +64,7 @@ struct Lane {
     // pending across the shadow query
     V3<R> contrib, new_o, new_d, tfac;
     R rand0_pending;
+    R pdf_pending;                // pdf of the pending hemisphere sample (record kernel: log(pdf), R/src/path_tracing.py:94)
 };
 
 // random numbers of (path, bounce): replayed Scene.rand_0/rand_1 rows or Philox stream 0
@@ -210,17 +211,15 @@ LT_DEVINL bool advance(const WalkParams<R>& P, Lane<R>& ln, const Frame<R>* fram
 // branches (miss, specular, shadow resolve) run it together instead of through five inlined copies.
 enum { ST_QUERY = 0, ST_ADVANCE = 1, ST_ADVANCE_ENDED = 2 };
 
-// Shading after an EXTENSION query.
+// Shading after an EXTENSION query, given the bounce's two random numbers.
 template <typename R, int SEM>
-LT_DEVINL int shade_extension(const WalkParams<R>& P, Lane<R>& ln, int prim, R t, const TriRec<R>* tris, const MatRec<R>* mats,
-                              uint32_t& lidx_overflow, R& adv_rand0) {
+LT_DEVINL int shade_extension_with(const WalkParams<R>& P, Lane<R>& ln, int prim, R t, const TriRec<R>* tris, const MatRec<R>* mats,
+                                   uint32_t& lidx_overflow, R& adv_rand0, R rand_0, R rand_1) {
     const R eps = (R)P.eps;
     const R inv_pi = (R)(1 / 3.141592653589793);
     if (sizeof(R) == 4 && prim >= 0) ln.skip = prim;   // every continuation ray below starts on `prim`;
                                                        // on a miss the (unchanged) ray keeps its own skip
     if (prim < 0) return ST_ADVANCE_ENDED;                             // miss: frame ends (:48-53)
-    R rand_0, rand_1;
-    get_rand<R>(P, ln.path_id, ln.bounce, rand_0, rand_1);
     const TriRec<R>& tr = tris[prim];
     const MatRec<R>& m = mats[tr.mat];
     V3<R> p = mk<R>(ln.o.x + t * ln.d.x, ln.o.y + t * ln.d.y, ln.o.z + t * ln.d.z);    // utils.py:65
@@ -250,6 +249,7 @@ LT_DEVINL int shade_extension(const WalkParams<R>& P, Lane<R>& ln, int prim, R t
         R pdf = cosine_sample<R>(n, ln.d, rand_0, rand_1, dir);
         ln.pdf_zero = (pdf == 0) ? 1 : 0;
         ln.rand0_pending = rand_0;
+        ln.pdf_pending = pdf;
         R ct = dot(dir, n);
         ln.tfac = mk<R>((m.kd[0] * inv_pi) * ct / pdf, (m.kd[1] * inv_pi) * ct / pdf, (m.kd[2] * inv_pi) * ct / pdf);
         ln.new_o = mk<R>(p.x + eps * dir.x, p.y + eps * dir.y, p.z + eps * dir.z);
@@ -295,6 +295,15 @@ LT_DEVINL int shade_extension(const WalkParams<R>& P, Lane<R>& ln, int prim, R t
     }
     adv_rand0 = rand_0;
     return ok ? ST_ADVANCE : ST_ADVANCE_ENDED;
+}
+
+// Shading after an EXTENSION query; draws rand(path, bounce) only when something was hit.
+template <typename R, int SEM>
+LT_DEVINL int shade_extension(const WalkParams<R>& P, Lane<R>& ln, int prim, R t, const TriRec<R>* tris, const MatRec<R>* mats,
+                              uint32_t& lidx_overflow, R& adv_rand0) {
+    R rand_0 = (R)0, rand_1 = (R)0;
+    if (prim >= 0) get_rand<R>(P, ln.path_id, ln.bounce, rand_0, rand_1);
+    return shade_extension_with<R, SEM>(P, ln, prim, t, tris, mats, lidx_overflow, adv_rand0, rand_0, rand_1);
 }
 
 // After the SHADOW query.  occluded = a hit was found in (eps, r - eps).

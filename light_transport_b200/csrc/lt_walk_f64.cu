@@ -7,4 +7,5 @@ template int walk_kernel_attrs<double>(int, int, int*, int*, int*, size_t);
 template int launch_wavefront<double>(const WalkParams<double>&, unsigned long long*, int, size_t, cudaStream_t);
 template int wavefront_kernel_attrs<double>(int, int, int*, int*, size_t);
 template size_t wavefront_smem_bytes<double>(size_t);
+template int launch_record<double>(const WalkParams<double>&, const RecParams&, int, cudaStream_t);
 }

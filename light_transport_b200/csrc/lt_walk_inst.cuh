@@ -5,6 +5,7 @@
 #pragma once
 #include "lt_megakernel.cuh"
 #include "lt_wavefront.cuh"
+#include "lt_record.cuh"
 
 namespace lt {
 
@@ -103,6 +104,18 @@ int wavefront_kernel_attrs(int trav, int sem, int* regs, int* max_blocks, size_t
 #undef LT_WF_A
     set_error("unknown wavefront kernel variant");
     return LT_E_INVALID;
+}
+
+template <typename R>
+int launch_record(const WalkParams<R>& P, const RecParams& RP, int grid, cudaStream_t stream) {
+    switch (P.traversal) {
+        case LT_TRAV_COMPAT: record_kernel<R, LT_TRAV_COMPAT><<<grid, LT_BLOCK, 0, stream>>>(P, RP); break;
+        case LT_TRAV_NEAREST: record_kernel<R, LT_TRAV_NEAREST><<<grid, LT_BLOCK, 0, stream>>>(P, RP); break;
+        case LT_TRAV_LBVH: record_kernel<R, LT_TRAV_LBVH><<<grid, LT_BLOCK, 0, stream>>>(P, RP); break;
+        default: set_error("unknown traversal %d", P.traversal); return LT_E_INVALID;
+    }
+    LT_CUDA_OK(cudaGetLastError());
+    return LT_OK;
 }
 
 template <typename R>

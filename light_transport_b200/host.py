@@ -86,7 +86,7 @@ def lib():
         L.lt_last_error.restype = C.c_char_p
         L.lt_version.restype = C.c_char_p
         for name in ("lt_init", "lt_set_stream", "lt_device_info", "lt_scene_create", "lt_scene_set_compat_bvh", "lt_bvh_build",
-                     "lt_intersect", "lt_render", "lt_render_image", "lt_film_finalize", "lt_measure_fp32_peak"):
+                     "lt_intersect", "lt_render", "lt_render_image", "lt_render_records", "lt_film_finalize", "lt_measure_fp32_peak"):
             getattr(L, name).restype = C.c_int
         L.lt_destroy.restype = None
         L.lt_scene_destroy.restype = None
@@ -246,6 +246,52 @@ class Renderer:
                                _ptr(film_buf, PD), _ptr(samples, PD), C.byref(cnt)))
         return film_buf, samples, cnt.as_dict()
 
+    def render_records(self, *, width, height, spp, max_depth, camera, f_distance, rand0, rand1, light_idx=None,
+                       traversal="compat", real="f64", gradients=False, lists=True, seed=0):
+        """The per-sample outputs of the reference's ``render_scene_samples`` (R/src/path_tracing.py:251-303) for
+        replayed random numbers: dict with ``samples``, ``record_log_pdf`` (the array ``trace_path`` returns),
+        ``scene_record_log_pdf`` / ``bounce_record`` (what it writes into ``Scene``), ``direct_list`` /
+        ``indirect_list`` (root frame) and, with ``gradients=True``, ``rlp_minus`` / ``rlp_plus`` / ``record_s`` of
+        ``calculate_gradients`` (:203-249).  REFERENCE semantics, ``max_depth <= 32``."""
+        p = LtRenderParams()
+        p.width, p.height, p.spp, p.s0, p.s1, p.max_depth = width, height, spp, 0, spp, max_depth
+        p.semantics, p.traversal, p.real, p.scheduler = 0, TRAVERSAL[traversal], REAL[real], 0
+        p.rr_start, p.rr_floor, p.eps, p.f_distance, p.seed = 3, 0.05, _pack_eps(), float(f_distance), int(seed)
+        cam = np.asarray(camera, dtype=np.float64)
+        for k in range(3):
+            p.camera[k] = float(cam[k])
+        rand0 = np.ascontiguousarray(rand0, dtype=np.float64)
+        rand1 = np.ascontiguousarray(rand1, dtype=np.float64)
+        if rand0.shape != (height, width, spp, max_depth) or rand1.shape != rand0.shape:
+            raise ValueError("rand_0/rand_1 must be [H,W,spp,max_depth]")
+        if light_idx is not None:
+            light_idx = np.ascontiguousarray(light_idx, dtype=np.int32)
+            if light_idx.shape[:3] != (height, width, spp):
+                raise ValueError("light_idx must be [H,W,spp,K]")
+            p.n_light_idx = light_idx.shape[3]
+        D = max_depth
+        out = dict(samples=np.zeros((height, width, spp, 3)), record_log_pdf=np.zeros((height, width, spp, D)),
+                   scene_record_log_pdf=np.zeros((height, width, spp, D)), bounce_record=np.ones((height, width, spp, D), np.int8))
+        if lists:
+            out["direct_list"] = np.zeros((height, width, spp, 3, D))
+            out["indirect_list"] = np.zeros((height, width, spp, 3, D))
+        l0 = l1 = None
+        if gradients:
+            with np.errstate(divide="ignore"):
+                l0 = np.log(rand0 / (1 - rand0))              # Scene.rand_0_logit, R/src/scene.py:70-71
+                l1 = np.log(rand1 / (1 - rand1))
+            out["rlp_minus"] = np.zeros((height, width, spp, 2 * D, D))
+            out["rlp_plus"] = np.zeros((height, width, spp, 2 * D, D))
+            out["record_s"] = np.full((height, width, spp, 2 * D), 0.01)      # _s of :210,230
+        cnt = LtCounters()
+        _check(lib().lt_render_records(self._scene, C.byref(p), _ptr(rand0, PD), _ptr(rand1, PD), _ptr(l0, PD), _ptr(l1, PD),
+                                       _ptr(light_idx, PI32), _ptr(out["samples"], PD), _ptr(out["record_log_pdf"], PD),
+                                       _ptr(out["scene_record_log_pdf"], PD), _ptr(out["bounce_record"], C.POINTER(C.c_int8)),
+                                       _ptr(out.get("direct_list"), PD), _ptr(out.get("indirect_list"), PD),
+                                       _ptr(out.get("rlp_minus"), PD), _ptr(out.get("rlp_plus"), PD), C.byref(cnt)))
+        out["counters"] = cnt.as_dict()
+        return out
+
     def finalize(self, film_sum, spp_total, out=None):
         """``image = clip(film_sum / spp, 0, 1)`` (R/src/path_tracing.py:304-305) on the device."""
         if isinstance(film_sum, np.ndarray):
@@ -390,3 +436,37 @@ def render_scene(scene, primitives, bvh=None, *, spp=None, rng=None, seed=0, sem
     if return_info:
         out += (info,)
     return out[0] if len(out) == 1 else out
+
+
+def render_scene_full(scene, primitives, bvh=None, *, light_idx=None, traversal="compat", real="f64", device=0):
+    """The reference's CURRENT ``path_tracing.render_scene`` (R/src/path_tracing.py:371-387), whose return value
+    feeds the control-variate cells of ``R/examples/LTS.ipynb``: the 10-tuple
+
+        image_ver0, image_ver1, image_ver2, samples, record_log_pdf, record_log_pdf_minus_set,
+        record_log_pdf_plus_set, record_s_set, data_more_samples, two_light_list
+
+    and the side effects on ``scene.image`` / ``scene.bounce_record`` / ``scene.record_log_pdf``.  Consumes
+    ``scene.rand_0/rand_1`` (replay).  ``data_more_samples`` is ``None``: that block (:310-364) draws from numba's
+    private generator inside njit and indexes fixed pixels of a 150x150 film — notebook-specific."""
+    H, W, D, S = int(scene.height), int(scene.width), int(scene.max_depth), int(scene.number_of_samples)
+    if getattr(scene, "rand_0", None) is None:
+        raise ValueError("render_scene_full replays scene.rand_0/rand_1")
+    packed = primitives if isinstance(primitives, _pack.PackedScene) else _pack.pack_scene(primitives, scene.lights)
+    nodes = _nodes_from_bvh(bvh, packed) if traversal == "compat" else None
+    r = Renderer(packed, nodes, device=device, build_lbvh=(traversal == "lbvh"))
+    try:
+        o = r.render_records(width=W, height=H, spp=S, max_depth=D, camera=scene.camera, f_distance=scene.f_distance,
+                             rand0=np.asarray(scene.rand_0), rand1=np.asarray(scene.rand_1), light_idx=light_idx,
+                             traversal=traversal, real=real, gradients=True)
+    finally:
+        r.close()
+    image_ver0 = np.array(scene.image, dtype=np.float64, copy=True)        # :373 copies scene.image BEFORE rendering
+    image_ver2 = image_ver0.copy()
+    image = np.clip(o["samples"].sum(axis=2) / S, 0, 1)                   # :304-305 and :378-384 (same numbers)
+    for name, val in (("image", image), ("bounce_record", o["bounce_record"]), ("record_log_pdf", o["scene_record_log_pdf"])):
+        try:
+            getattr(scene, name)[...] = val
+        except Exception:
+            setattr(scene, name, val)
+    return (image_ver0, image, image_ver2, o["samples"], o["record_log_pdf"], o["rlp_minus"], o["rlp_plus"], o["record_s"], None,
+            (o["direct_list"], o["indirect_list"]))

@@ -7,9 +7,10 @@ fallback — calls raise if the library or a GPU is missing.
 """
 from . import api, scenes, compat_bvh  # noqa: F401
 from ._pack import PackedScene, pack_scene, from_arrays  # noqa: F401
+from .mesh_io import load_obj  # noqa: F401
 
 __all__ = ["render_scene", "render_scene_full", "intersect", "Renderer", "api", "scenes", "compat_bvh", "PackedScene",
-           "pack_scene", "from_arrays"]
+           "pack_scene", "from_arrays", "load_obj"]
 
 
 def __getattr__(name):

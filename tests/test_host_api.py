@@ -112,3 +112,19 @@ def test_sample_range_partition():
             assert all(rs[i][1] == rs[i + 1][0] for i in range(R - 1))
             sizes = [b - a for a, b in rs]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_load_obj(tmp_path):
+    import light_transport_b200 as lt
+    obj = tmp_path / "cube.obj"
+    obj.write_text("# unit cube, quads + a degenerate face\n"
+                   "v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nv 0 0 1\nv 1 0 1\nv 1 1 1\nv 0 1 1\nvn 0 0 1\n"
+                   "f 1 2 3 4\nf 5/1/1 6/2/1 7/3/1 8/4/1\nf 1 2 6 5\nf 2 3 7 6\nf 3 4 8 7\nf -5 -8 -4 -1\nf 1 1 2\n")
+    v = lt.load_obj(str(obj), scale=2.0, translate=(0, -5, 0))
+    assert v.shape == (12, 3, 3) and v.min() == -5 and v.max() == 2
+    base, _, _, _ = load_scene("lts_scene.npz")
+    ps = lt.from_arrays(v, base=base, kd=(0.3, 0.4, 0.5))
+    assert ps.n_tris == 28 + 12 and np.allclose(ps.mat_kd[-1], (0.3, 0.4, 0.5))
+    with pytest.raises(ValueError):
+        (tmp_path / "empty.obj").write_text("v 0 0 0\n")
+        lt.load_obj(str(tmp_path / "empty.obj"))

@@ -307,6 +307,14 @@ def main():
 
     if rank == 0:
         peak_tf = R.measure_fp32_peak()
+        traffic = None
+        try:      # dram bytes of one launch of this kernel from the committed ncu capture of the same command
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            key = f"{args.config}:{args.traversal}:{args.scheduler}:{args.real}"
+            if key in tj and args.size is None and args.spp == CONFIGS[args.config]["spp"]:
+                traffic = tj[key]["bytes"]
+        except Exception:
+            traffic = None
         achieved_tf = flops / (kernel_ns * 1e-9) / 1e12
         out = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": WORKLOAD["scaling"], "vs_baseline": None,
@@ -317,7 +325,7 @@ def main():
                        "api": "light_transport_b200.render_scene(scene, primitives, bvh, spp=, rng='philox')", "steps": e2e_steps},
                "gpu_launches": int(args.steps * 2),
                "roofline": {"bound": "fp32", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
-                            "traffic": None, "kernel": "lt::walk_megakernel",
+                            "traffic": traffic, "traffic_unit": "bytes per launch (dram read+write, ncu, profiles/r01_traffic.json)", "kernel": "lt::walk_megakernel",
                             "peak_source": "FP32 FMA micro-benchmark run in this process (lt_measure_fp32_peak); MEASURED_PEAKS.json has "
                                            "no FP32 figure (nominal 148 SM x 128 x 2 x 1.965 GHz = 74.4)",
                             "flops_model": "21*box_tests + 48*tri_tests + 150*ext_rays + 40*shadow_rays (SURVEY.md 8d)",

@@ -184,12 +184,12 @@ def run_reference(args, rank):
         tot_r += rays
     v = tot_r / tot_t / 1e6
     cb["value"] = v
-    print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": "Mrays/s", "n_gpus": args.gpus,
+    emit({"impl": "reference", "metric": METRIC, "value": v, "unit": "Mrays/s", "n_gpus": args.gpus,
                       "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_t / max(args.steps, 1) * 1e3,
                       "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                       "config": config_dict(args, 1), "cpu_baseline": cb,
                       "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                      "gpu_launches": 0}))
+                      "gpu_launches": 0})
 
 
 def config_dict(args, n):
@@ -204,8 +204,22 @@ def config_dict(args, n):
             "l2": "flushed between timed steps (256 MiB write)"}
 
 
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """the ONE JSON line of the contract, on the process's real stdout"""
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(obj) + "\n").encode())
+
+
 def main():
+    global _REAL_STDOUT
     args = parse()
+    # libraries (NCCL's version banner, torchrun notices) must not share stdout with the JSON line:
+    # keep the real stdout aside and point fd 1 at stderr for everything else
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -337,7 +351,7 @@ def main():
             out["cpu_baseline"], _, _ = cpu_baseline(ps, nodes, cam, depth, args, sample_spp=8)
         if world == 1 and not args.no_rmse and args.config == "c2":
             out["time_to_rmse"] = time_to_rmse(R, cam, depth, args)
-        print(json.dumps(out))
+        emit(out)
     R.close()
     if world > 1:
         dist.destroy_process_group()

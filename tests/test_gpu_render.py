@@ -254,3 +254,28 @@ def test_wavefront_equals_megakernel(R_lts, trav, semantics, real):
         a = R_lts.render(scheduler="wavefront", **{**kw, **extra})
         b = R_lts.render(scheduler="megakernel", **{**kw, **extra})
         assert same(a[1], b[1]) and a[2]["paths"] == b[2]["paths"]
+
+
+def test_full_size_properties(R_lts):
+    """BASELINE's C2 film (1024x1024) at a bounded sample count: the size-independent properties hold at full
+    film size — sample-range additivity (the multi-GPU decomposition), determinism, counters add up, the image
+    is a clipped mean, both schedulers agree statistically."""
+    ps, nodes, cam, f = load_scene("lts_scene.npz")
+    W = H = 1024
+    kw = dict(width=W, height=H, spp=1024, max_depth=16, camera=cam, f_distance=f, seed=5, traversal="compat", real="f32")
+    full, _, c_full = R_lts.render(s0=0, s1=8, **kw)
+    acc = np.zeros_like(full)
+    rays = 0
+    for a, b in ((0, 3), (3, 4), (4, 8)):
+        part, _, c = R_lts.render(s0=a, s1=b, **kw)
+        acc += part
+        rays += c["rays_ext"] + c["rays_shadow"]
+    assert np.allclose(acc, full, rtol=1e-12, atol=1e-9)
+    assert rays == c_full["rays_ext"] + c_full["rays_shadow"] and c_full["paths"] == W * H * 8
+    again, _, c2 = R_lts.render(s0=0, s1=8, **kw)
+    assert np.allclose(again, full, rtol=1e-12, atol=1e-9) and c2["rays_ext"] == c_full["rays_ext"]
+    img = R_lts.finalize(full, 8)
+    assert img.min() >= 0 and img.max() <= 1 and np.allclose(img, np.clip(full / 8, 0, 1))
+    wf, _, c_wf = R_lts.render(s0=0, s1=8, scheduler="wavefront", **kw)
+    assert c_wf["paths"] == c_full["paths"] and abs(wf.mean() - full.mean()) < 2e-3 * full.mean()
+    assert 7.0 < (c_full["rays_ext"] + c_full["rays_shadow"]) / c_full["paths"] < 7.7       # SURVEY: ~8 rays per path

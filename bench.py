@@ -270,12 +270,13 @@ def main():
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    ms, rays, paths, kernel_ns, flops, last = 0.0, 0, 0, 0, 0.0, None
+    ms, rays, paths, kernel_ns, flops, last, memo = 0.0, 0, 0, 0, 0.0, None, 0
     for i in range(args.steps):
         t, c = step(100 + i, True)
         ms += t
         rays += c["rays_ext"] + c["rays_shadow"]
         paths += c["paths"]
+        memo += c["rays_memo"]
         kernel_ns += c["kernel_ns"]
         flops += flops_per_launch(c)
         last = c
@@ -334,6 +335,10 @@ def main():
                "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": WORKLOAD["scaling"], "vs_baseline": None,
                "dtype": args.real, "data": "synthetic", "config": config_dict(args, world),
                "mpaths_per_s": paths_all / (ms_max * 1e-3) / 1e6, "rays_per_path": rays_all / max(paths_all, 1),
+               "ray_accounting": "a ray = one intersect_bvh call of the reference's control flow (R/src/utils.py:59, "
+                                 "R/src/light_samples.py:48), the same count the CPU arm reports; rays_memo_fraction of them are "
+                                 "re-traces of a ray object that has just missed (Q1) and are answered without a traversal",
+               "rays_memo_fraction": memo / max(rays, 1),
                "clocks": clocks,
                "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                        "api": "light_transport_b200.render_scene(scene, primitives, bvh, spp=, rng='philox')", "steps": e2e_steps},

@@ -95,6 +95,10 @@ typedef struct {
 typedef struct {
     uint64_t paths, rays_ext, rays_shadow, box_tests, tri_tests, max_frames, light_idx_overflow,
         frame_overflow, lane_steps, lane_slots, kernel_ns, launches;
+    /* rays_ext counts every closest-hit query the reference makes for these paths (R/src/utils.py:59).
+     * rays_memo of them were answered from a memo instead of a traversal: after a callee's ray misses,
+     * trace_path's caller re-traces the SAME ray object (Q1) and must miss again. */
+    uint64_t rays_memo;
 } lt_counters;
 
 typedef struct {

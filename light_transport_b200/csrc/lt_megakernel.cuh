@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(LT_BLOCK, sizeof(R) == 4 ? LT_MIN_BLOCKS_F32 :
     ln.qtype = 0;
     Stats st;
     uint32_t n_ext = 0, n_shadow = 0, n_paths = 0, lidx_overflow = 0, frame_overflow = 0, max_frames = 0;
-    uint32_t lane_steps = 0, warp_iters = 0;
+    uint32_t lane_steps = 0, warp_iters = 0, n_memo = 0;
     double acc[3] = {0, 0, 0};
     int64_t acc_pix = -1;
 
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(LT_BLOCK, sizeof(R) == 4 ? LT_MIN_BLOCKS_F32 :
                 }
                 bool alive = true;
                 if (stt != ST_QUERY) {      // roulette / bounce++ / frame pops: one shared copy for every branch
-                    alive = advance<R, SEM, LT_LOCAL_FRAMES>(P, ln, frames, gtid, stt == ST_ADVANCE_ENDED, adv_rand0);
+                    alive = advance<R, SEM, LT_LOCAL_FRAMES>(P, ln, frames, gtid, stt == ST_ADVANCE_ENDED, adv_rand0, n_memo);
                     ln.qtype = 1;
                     ln.tlimit = Lim<R>::inf();
                 }
@@ -168,11 +168,11 @@ __global__ void __launch_bounds__(LT_BLOCK, sizeof(R) == 4 ? LT_MIN_BLOCKS_F32 :
     }
     // ---- counters: warp-reduced, one atomic per warp and field
     if (P.counters) {
-        unsigned long long v[10] = {n_paths, n_ext, n_shadow, st.box_tests, st.tri_tests, 0, lidx_overflow, frame_overflow,
-                                    lane_steps, (unsigned long long)warp_iters};
+        unsigned long long v[13] = {n_paths, (unsigned long long)n_ext + n_memo, n_shadow, st.box_tests, st.tri_tests, 0, lidx_overflow,
+                                    frame_overflow, lane_steps, (unsigned long long)warp_iters, 0, 0, n_memo};
 #pragma unroll
-        for (int k = 0; k < 10; ++k) {
-            if (k == 5) continue;
+        for (int k = 0; k < 13; ++k) {
+            if (k == 5 || k == 10 || k == 11) continue;
             unsigned long long x = v[k];
             if (k == 9) { x = lane == 0 ? x * 32ull : 0ull; }
             for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(full, x, o);

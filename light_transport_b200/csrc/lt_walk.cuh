@@ -60,6 +60,7 @@ struct Lane {
     uint64_t path_id;             // (pixel * spp + s): Philox counter / replay row
     int32_t bounce, nframes, nee;
     int32_t pdf_zero;
+    int32_t memo_miss;            // the current extension ray is known to miss (it already did): Q1 re-traces need no traversal
     V3<R> T, W, L;
     // pending across the shadow query
     V3<R> contrib, new_o, new_d, tfac;
@@ -182,8 +183,11 @@ template <typename R, int LF> LT_DEVINL void frame_load(const WalkParams<R>& P, 
 // (:41), and — whenever a frame ends — resumption of its parent at the roulette (Q1).
 // `ended` = the current frame has already ended (miss / pdf==0 / malformed material).
 // Returns true when the lane has a new extension ray to trace, false when the whole path is over.
+// A frame that resumes after its callee's ray MISSED re-traces that very ray object (Q1) and must miss
+// too: that query is answered from the memo (ln.memo_miss) — counted in n_memo, no traversal — and the
+// frame ends like the reference's does (:48-53), which unwinds the whole stack without another iteration.
 template <typename R, int SEM, int LF>
-LT_DEVINL bool advance(const WalkParams<R>& P, Lane<R>& ln, const Frame<R>* frames, int64_t gtid, bool ended, R rand_0) {
+LT_DEVINL bool advance(const WalkParams<R>& P, Lane<R>& ln, const Frame<R>* frames, int64_t gtid, bool ended, R rand_0, uint32_t& n_memo) {
     for (;;) {
         if (!ended) {
             bool die = false;
@@ -195,7 +199,10 @@ LT_DEVINL bool advance(const WalkParams<R>& P, Lane<R>& ln, const Frame<R>* fram
             }
             if (!die) {
                 ln.bounce += 1;
-                if (ln.bounce < P.max_depth) return true;
+                if (ln.bounce < P.max_depth) {
+                    if (!ln.memo_miss) return true;
+                    n_memo++;                                  // the reference's intersect_bvh call, answered: miss
+                }
             }
         }
         // this frame is over
@@ -219,7 +226,9 @@ LT_DEVINL int shade_extension_with(const WalkParams<R>& P, Lane<R>& ln, int prim
     const R inv_pi = (R)(1 / 3.141592653589793);
     if (sizeof(R) == 4 && prim >= 0) ln.skip = prim;   // every continuation ray below starts on `prim`;
                                                        // on a miss the (unchanged) ray keeps its own skip
-    if (prim < 0) return ST_ADVANCE_ENDED;                             // miss: frame ends (:48-53)
+    if (prim < 0) { ln.memo_miss = 1; return ST_ADVANCE_ENDED; }       // miss: frame ends (:48-53)
+    ln.memo_miss = 0;
+    ln.pdf_zero = 0;
     const TriRec<R>& tr = tris[prim];
     const MatRec<R>& m = mats[tr.mat];
     V3<R> p = mk<R>(ln.o.x + t * ln.d.x, ln.o.y + t * ln.d.y, ln.o.z + t * ln.d.z);    // utils.py:65
@@ -247,7 +256,10 @@ LT_DEVINL int shade_extension_with(const WalkParams<R>& P, Lane<R>& ln, int prim
         // thing left between here and the recursion point
         V3<R> dir;
         R pdf = cosine_sample<R>(n, ln.d, rand_0, rand_1, dir);
-        ln.pdf_zero = (pdf == 0) ? 1 : 0;
+        // pdf == 0 (u0 == 0 exactly, or a direction with zero z): the reference breaks BEFORE touching the ray
+        // (:76-80) and drops the direct light it has just computed — nothing to trace, the frame ends on the
+        // incoming ray (the light pick above was still consumed, as in cast_one_shadow_ray)
+        if (pdf == 0) { ln.pdf_zero = 1; adv_rand0 = rand_0; return ST_ADVANCE_ENDED; }
         ln.rand0_pending = rand_0;
         ln.pdf_pending = pdf;
         R ct = dot(dir, n);
@@ -358,6 +370,7 @@ LT_DEVINL void start_path(const WalkParams<R>& P, Lane<R>& ln, int64_t pix, int 
     ln.d = normalize(end - cam);
     ln.tlimit = Lim<R>::inf();
     ln.skip = -1;
+    ln.memo_miss = 0;
     ln.qtype = P.max_depth > 0 ? 1 : 0;
 }
 

@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(WfCfg<R>::NT, WfCfg<R>::MINB) walk_wavefront(c
 
     Stats st;
     uint32_t n_ext = 0, n_shadow = 0, n_paths = 0, lidx_overflow = 0, frame_overflow = 0, max_frames = 0;
-    uint32_t lane_steps = 0, warp_iters = 0;
+    uint32_t lane_steps = 0, warp_iters = 0, n_memo = 0;
 
     for (int round = 0;; ++round) {
         const int par = round & 1;
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(WfCfg<R>::NT, WfCfg<R>::MINB) walk_wavefront(c
                 stt = shade_extension<R, SEM>(P, ln, ln.hit_prim, ln.hit_t, tris, mats, lidx_overflow, adv_rand0);
             bool alive = true;
             if (stt != ST_QUERY) {
-                alive = advance<R, SEM, 0>(P, ln, nullptr, acol, stt == ST_ADVANCE_ENDED, adv_rand0);
+                alive = advance<R, SEM, 0>(P, ln, nullptr, acol, stt == ST_ADVANCE_ENDED, adv_rand0, n_memo);
                 ln.qtype = alive ? 1 : 0;
                 ln.tlimit = Lim<R>::inf();
             }
@@ -247,11 +247,11 @@ __global__ void __launch_bounds__(WfCfg<R>::NT, WfCfg<R>::MINB) walk_wavefront(c
     }
     // ---- counters
     if (P.counters) {
-        unsigned long long v[10] = {n_paths, n_ext, n_shadow, st.box_tests, st.tri_tests, 0, lidx_overflow, frame_overflow,
-                                    lane_steps, (unsigned long long)warp_iters};
+        unsigned long long v[13] = {n_paths, (unsigned long long)n_ext + n_memo, n_shadow, st.box_tests, st.tri_tests, 0, lidx_overflow,
+                                    frame_overflow, lane_steps, (unsigned long long)warp_iters, 0, 0, n_memo};
 #pragma unroll
-        for (int k = 0; k < 10; ++k) {
-            if (k == 5) continue;
+        for (int k = 0; k < 13; ++k) {
+            if (k == 5 || k == 10 || k == 11) continue;
             unsigned long long x = v[k];
             if (k == 9) { x = lane == 0 ? x * 32ull : 0ull; }
             for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(full, x, o);

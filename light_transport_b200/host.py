@@ -54,7 +54,7 @@ class LtRenderParams(C.Structure):
 class LtCounters(C.Structure):
     _fields_ = [(k, C.c_uint64) for k in ("paths", "rays_ext", "rays_shadow", "box_tests", "tri_tests", "max_frames",
                                           "light_idx_overflow", "frame_overflow", "lane_steps", "lane_slots",
-                                          "kernel_ns", "launches")]
+                                          "kernel_ns", "launches", "rays_memo")]
 
     def as_dict(self):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}

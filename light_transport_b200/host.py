@@ -24,6 +24,8 @@ TRAVERSAL = {"compat": 0, "nearest": 1, "lbvh": 2}
 SEMANTICS = {"reference": 0, "iterative": 1}
 REAL = {"f32": 0, "f64": 1}
 SCHEDULER = {"megakernel": 0, "wavefront": 1}
+# measured: the megakernel wins in float32, the wavefront scheduler in float64
+AUTO_SCHEDULER = {"f32": "megakernel", "f64": "wavefront"}
 
 PD = C.POINTER(C.c_double)
 PI32 = C.POINTER(C.c_int32)
@@ -209,6 +211,8 @@ class Renderer:
         p = LtRenderParams()
         s1 = spp if s1 is None else s1
         p.width, p.height, p.spp, p.s0, p.s1, p.max_depth = width, height, spp, s0, s1, max_depth
+        if scheduler == "auto":
+            scheduler = AUTO_SCHEDULER[real]
         p.semantics, p.traversal, p.real, p.scheduler = SEMANTICS[semantics], TRAVERSAL[traversal], REAL[real], SCHEDULER[scheduler]
         p.rr_start = (3 if semantics == "reference" else 5) if rr_start is None else rr_start   # path_tracing.py:148 / fix1:126
         p.rr_floor, p.eps, p.f_distance, p.seed = 0.05, _pack_eps(), float(f_distance), int(seed)
@@ -359,7 +363,7 @@ def intersect(primitives, bvh, o, d, *, lights=(), traversal="compat", real="f64
 
 def render_scene(scene, primitives, bvh=None, *, spp=None, rng=None, seed=0, semantics="reference", traversal="compat",
                  light_idx=None, real=None, return_samples=False, world=None, device=None, return_info=False,
-                 scheduler="megakernel"):
+                 scheduler="auto"):
     """Drop-in for ``render_scene(scene, primitives, bvh)``.
 
     ``scene``/``primitives``/``bvh`` are the reference's objects (or the ``api`` mirrors / a

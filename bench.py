@@ -34,6 +34,8 @@ CONFIGS = {
     "c2": dict(scene="lts", width=1024, height=1024, spp=1024, max_depth=16, semantics="reference", traversal="compat", scaling="weak"),
     "c3": dict(scene="mesh", width=1920, height=1080, spp=256, max_depth=8, semantics="iterative", traversal="lbvh", scaling="weak"),
     "c4": dict(scene="mirror", width=512, height=512, spp=64, max_depth=256, semantics="reference", traversal="compat", scaling="weak"),
+    "c4b": dict(scene="medium", width=0, height=0, spp=0, max_depth=256, semantics="implicit", traversal="none", scaling="weak",
+                albedo=0.99, g=0.8, radius=20.0, photons=50_000_000),
     "c5": dict(scene="lts", width=4096, height=4096, spp=4096, max_depth=8, semantics="reference", traversal="lbvh", scaling="strong"),
 }
 WORKLOAD = dict(CONFIGS["c2"])
@@ -171,6 +173,58 @@ def time_to_rmse(R, cam, depth, args, size=256, target=0.01, chunk=32, ref_facto
             "reference_spp": ref_spp, "reached": rmse <= target}
 
 
+def run_medium(args, rank, world, local):
+    """C4b: homogeneous scattering medium, albedo 0.99, max depth 256; a ray = one flight segment."""
+    import torch
+    import torch.distributed as dist
+    from light_transport_b200 import medium
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    n = WORKLOAD["photons"]
+    kw = dict(albedo=WORKLOAD["albedo"], g=WORKLOAD["g"], radius=WORKLOAD["radius"], max_depth=WORKLOAD["max_depth"], mode=WORKLOAD["semantics"],
+              n_rbins=32, real=args.real, device=local)
+    for i in range(args.warmup):
+        medium.walk(n // 10, seed=i, first_photon=rank * n, **kw)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    seg, ms, wall0 = 0, 0.0, time.perf_counter()
+    hist = np.zeros(WORKLOAD["max_depth"] + 1, np.uint64)
+    for i in range(args.steps):
+        r = medium.walk(n, seed=100 + i, first_photon=rank * n, **kw)       # disjoint photon ranges per rank
+        seg += r["n_segments"]; ms += r["kernel_ms"]; hist += r["hist"]
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - wall0
+    tm = torch.tensor([ms, wall], dtype=torch.float64, device="cuda")
+    ts = torch.tensor([float(seg)], dtype=torch.float64, device="cuda")
+    th = torch.from_numpy(hist.astype(np.float64)).cuda()
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ts)
+        dist.all_reduce(th)                                                  # the tally reduce of a pass
+    if rank == 0:
+        out = {"metric": METRIC, "value": float(ts[0]) / (float(tm[0]) * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": float(tm[0]) / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": args.real, "data": "synthetic",
+               "config": {"workload": f"C4b: homogeneous sphere R={WORKLOAD['radius']} mfp, albedo {WORKLOAD['albedo']}, HG g={WORKLOAD['g']}, max depth "
+                                      f"{WORKLOAD['max_depth']}, implicit capture + roulette, {n} photons per GPU per step; a ray = one flight segment",
+                          "photons_per_gpu": n, "parallelism": f"photon-sharded x{world}"},
+               "e2e": {"value": float(ts[0]) / float(tm[1]) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 80, "d2h_bytes_per_step": int(hist.nbytes + 32 * 8 + 72),
+                       "api": "light_transport_b200.medium.walk(...)"},
+               "gpu_launches": args.steps, "mean_collisions": float((th.cpu().numpy() * np.arange(len(hist))).sum() / max(float(th.sum()), 1))}
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import oracle as O
+            t0 = time.perf_counter()
+            o = O.medium_walk(n // 100, seed=1, **{k: v for k, v in kw.items() if k not in ("real", "device")})
+            dt = time.perf_counter() - t0
+            out["cpu_baseline"] = {"value": o["n_segments"] / dt / 1e6, "unit": "Mrays/s", "cores": os.cpu_count(), "kind": "port",
+                                   "sample": f"{n // 100} photons, {o['n_segments']} segments, {dt:.2f} s (oracle/lt_oracle.c lto_medium_walk)"}
+        emit(out)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -225,6 +279,9 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank)
+        return
+    if WORKLOAD["scene"] == "medium":
+        run_medium(args, rank, world, local)
         return
 
     import torch

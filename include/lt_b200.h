@@ -158,6 +158,26 @@ int lt_render_records(lt_scene *, const lt_render_params *, const double *rand0,
 /* image = clip(film_sum / spp_total, 0, 1)   (R/src/path_tracing.py:304-305) */
 int lt_film_finalize(lt_ctx *, const double *film_sum, int64_t n_values, int64_t spp_total, double *image_out);
 
+/* ---- C4b: many-bounce photon walk in a homogeneous scattering medium (BASELINE.json config 4).  The
+ * reference only has the Henyey-Greenstein evaluation (R/src/medium_samples.py:14-16, lt_henyey_greenstein);
+ * the walk itself is beyond the reference and is pinned by the oracle + analytic expectations. */
+typedef struct {
+    double albedo, g, radius;      /* single-scattering albedo, HG asymmetry, sphere radius in mean free paths (<= 0: infinite) */
+    int32_t max_depth, mode;       /* max collisions; 0 analog absorption, 1 implicit capture + roulette */
+    int32_t rr_start, n_rbins;     /* roulette when collision index > rr_start; radial bins of the absorbed-weight tally */
+    double rr_floor;
+    uint64_t seed, first_photon;   /* Philox key; global index of the first photon (ranks take disjoint ranges) */
+    int32_t real, reserved;
+} lt_medium_params;
+typedef struct {
+    double escaped, absorbed, truncated, rr_killed, rr_gained, sum_mu;
+    uint64_t n_collisions, n_segments, n_scatters;
+} lt_medium_totals;
+/* hist[max_depth+1]: photons by collision count; rbins[n_rbins]: absorbed weight by radial shell (host pointers) */
+int lt_medium_walk(lt_ctx *, const lt_medium_params *, uint64_t n_photons, uint64_t *hist, double *rbins,
+                   lt_medium_totals *totals, float *kernel_ms);
+double lt_henyey_greenstein(double cos_theta, double g);
+
 /* measured FP32 FMA throughput of this device (TFLOP/s), for the roofline denominator */
 int lt_measure_fp32_peak(lt_ctx *, double *tflops);
 

@@ -648,3 +648,115 @@ int lto_render(const lto_scene *S, const lto_params *P, const double *rand0, con
     if (cnt) *cnt = total;
     return err;
 }
+
+
+/* ================================================================================================
+ * C4b — photon random walk in a homogeneous medium (sigma_t = 1): free flight, collision, absorption
+ * (analog or implicit capture + the reference's roulette rule R/src/path_tracing.py:148-155 applied to
+ * the photon weight), Henyey-Greenstein scattering.  Philox4x32-10: key = seed, counter =
+ * (photon lo, photon hi, collision index, stream 2 | 3).
+ * ================================================================================================ */
+/* R/src/medium_samples.py:14-16 */
+double lto_henyey_greenstein(double cosTheta, double g) {
+    const double inv_4_pi = 0.25 * INV_PI;
+    double denom = 1 + g * g + 2 * g * cosTheta;
+    return inv_4_pi * (1 - g * g) / (denom * sqrt(denom));
+}
+
+static void medium_rand4(const lto_medium_params *P, uint64_t photon, uint32_t k, double u[4]) {
+    uint32_t key[2] = {(uint32_t)P->seed, (uint32_t)(P->seed >> 32)}, o[4];
+    uint32_t c2[4] = {(uint32_t)photon, (uint32_t)(photon >> 32), k, 2u};
+    lto_philox4x32_10(c2, key, o);
+    u[0] = u53(o[0], o[1]); u[1] = u53(o[2], o[3]);
+    uint32_t c3[4] = {(uint32_t)photon, (uint32_t)(photon >> 32), k, 3u};
+    lto_philox4x32_10(c3, key, o);
+    u[2] = u53(o[0], o[1]); u[3] = u53(o[2], o[3]);
+}
+
+int lto_medium_walk(const lto_medium_params *P, uint64_t n_photons, uint64_t *hist, double *rbins, lto_medium_totals *tot,
+                    int n_threads) {
+    const int D = P->max_depth, NB = P->n_rbins;
+    const double a = P->albedo, g = P->g, Rs = P->radius;
+    lto_medium_totals T;
+    memset(&T, 0, sizeof T);
+#ifdef _OPENMP
+    if (n_threads > 0) omp_set_num_threads(n_threads);
+#endif
+#pragma omp parallel
+    {
+        lto_medium_totals t;
+        memset(&t, 0, sizeof t);
+        uint64_t *h = (uint64_t *)calloc((size_t)D + 1, sizeof(uint64_t));
+        double *rb = (double *)calloc((size_t)(NB > 0 ? NB : 1), sizeof(double));
+#pragma omp for schedule(dynamic, 256)
+        for (int64_t i = 0; i < (int64_t)n_photons; ++i) {
+            const uint64_t id = P->first_photon + (uint64_t)i;
+            double x[3] = {0, 0, 0}, d[3], w = 1.0, u[4];
+            medium_rand4(P, id, 0xffffffffu, u);                /* isotropic point source at the centre */
+            {
+                double mu = 1 - 2 * u[0], sn = sqrt(1 - mu * mu > 0 ? 1 - mu * mu : 0), ph = 2 * 3.14159265358979323846 * u[1];
+                d[0] = sn * cos(ph); d[1] = sn * sin(ph); d[2] = mu;
+            }
+            int k = 0;                                          /* collisions so far */
+            for (;;) {
+                medium_rand4(P, id, (uint32_t)k, u);
+                double s = -log(1.0 - u[0]);                    /* free path, sigma_t = 1 */
+                t.n_segments++;
+                for (int c = 0; c < 3; ++c) x[c] += s * d[c];
+                double r2 = x[0] * x[0] + x[1] * x[1] + x[2] * x[2];
+                if (Rs > 0 && r2 >= Rs * Rs) { t.escaped += w; break; }
+                k++;
+                t.n_collisions++;
+                int shell = NB > 0 ? (Rs > 0 ? (int)(sqrt(r2) / Rs * NB) : 0) : -1;
+                if (shell >= NB) shell = NB - 1;
+                if (P->mode == 0) {                             /* analog: absorbed with probability 1 - albedo */
+                    if (u[1] >= a) { t.absorbed += w; if (shell >= 0) rb[shell] += w; break; }
+                } else {                                        /* implicit capture, then roulette on the weight */
+                    double dep = w * (1 - a);
+                    t.absorbed += dep;
+                    if (shell >= 0) rb[shell] += dep;
+                    w *= a;
+                    if (k - 1 > P->rr_start) {
+                        double q = 1 - w > P->rr_floor ? 1 - w : P->rr_floor;
+                        if (u[1] < q) { t.rr_killed += w; break; }
+                        t.rr_gained += w / (1 - q) - w;
+                        w /= 1 - q;
+                    }
+                }
+                if (k >= D) { t.truncated += w; break; }
+                /* Henyey-Greenstein scattering about the flight direction */
+                double mu;
+                if (fabs(g) < 1e-3) mu = 1 - 2 * u[2];
+                else { double sq = (1 - g * g) / (1 - g + 2 * g * u[2]); mu = (1 + g * g - sq * sq) / (2 * g); }
+                if (mu > 1) mu = 1;
+                if (mu < -1) mu = -1;
+                t.sum_mu += mu;
+                t.n_scatters++;
+                double sn = sqrt(1 - mu * mu), ph = 2 * 3.14159265358979323846 * u[3], cp = cos(ph), sp = sin(ph);
+                double nd[3];
+                if (fabs(d[2]) > 0.99999) {
+                    nd[0] = sn * cp; nd[1] = sn * sp; nd[2] = d[2] > 0 ? mu : -mu;
+                } else {
+                    double den = sqrt(1 - d[2] * d[2]);
+                    nd[0] = sn * (d[0] * d[2] * cp - d[1] * sp) / den + d[0] * mu;
+                    nd[1] = sn * (d[1] * d[2] * cp + d[0] * sp) / den + d[1] * mu;
+                    nd[2] = -sn * cp * den + d[2] * mu;
+                }
+                double nn = sqrt(nd[0] * nd[0] + nd[1] * nd[1] + nd[2] * nd[2]);
+                for (int c = 0; c < 3; ++c) d[c] = nd[c] / nn;
+            }
+            h[k < D ? k : D]++;
+        }
+#pragma omp critical
+        {
+            T.escaped += t.escaped; T.absorbed += t.absorbed; T.truncated += t.truncated; T.rr_killed += t.rr_killed;
+            T.rr_gained += t.rr_gained; T.sum_mu += t.sum_mu; T.n_collisions += t.n_collisions; T.n_segments += t.n_segments; T.n_scatters += t.n_scatters;
+            for (int k = 0; k <= D; ++k) hist[k] += h[k];
+            for (int b = 0; b < NB; ++b) rbins[b] += rb[b];
+        }
+        free(h);
+        free(rb);
+    }
+    if (tot) *tot = T;
+    return 0;
+}

@@ -69,6 +69,24 @@ int lto_render_records(const lto_scene *S, const lto_params *P, const double *ra
                        double *record_log_pdf, double *scene_record_log_pdf, int8_t *bounce_record, double *direct_list,
                        double *indirect_list, double *rlp_minus, double *rlp_plus, lto_counters *cnt);
 
+/* ---- C4b: many-bounce walk in a homogeneous scattering medium (beyond the reference: it only has the
+ * Henyey-Greenstein evaluation R/src/medium_samples.py:14-16).  Same record as lt_medium_params. */
+typedef struct {
+    double albedo, g, radius;      /* single-scattering albedo, HG asymmetry, sphere radius in mean free paths (<=0: infinite) */
+    int32_t max_depth, mode;       /* max collisions; mode 0 analog absorption, 1 implicit capture + roulette */
+    int32_t rr_start, n_rbins;     /* roulette when collision index > rr_start; radial bins of the absorbed-weight tally */
+    double rr_floor;
+    uint64_t seed, first_photon;
+} lto_medium_params;
+typedef struct {
+    double escaped, absorbed, truncated, rr_killed, rr_gained, sum_mu;   /* weights; sum of sampled scattering cosines */
+    uint64_t n_collisions, n_segments, n_scatters;
+} lto_medium_totals;
+/* hist[k], k=0..max_depth: photons that made exactly k collisions; rbins[n_rbins]: absorbed weight by shell */
+int lto_medium_walk(const lto_medium_params *P, uint64_t n_photons, uint64_t *hist, double *rbins, lto_medium_totals *tot,
+                    int n_threads);
+double lto_henyey_greenstein(double cos_theta, double g);
+
 /* Philox4x32-10 known-answer access for the tests */
 void lto_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 

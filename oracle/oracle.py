@@ -170,3 +170,36 @@ def render_records(scene: OracleScene, *, width, height, spp, max_depth, camera,
         raise RuntimeError(f"lto_render_records failed ({rc})")
     out["counters"] = cnt.as_dict()
     return out
+
+
+class LtoMediumParams(C.Structure):
+    _fields_ = [("albedo", C.c_double), ("g", C.c_double), ("radius", C.c_double), ("max_depth", C.c_int32), ("mode", C.c_int32),
+                ("rr_start", C.c_int32), ("n_rbins", C.c_int32), ("rr_floor", C.c_double), ("seed", C.c_uint64), ("first_photon", C.c_uint64)]
+
+
+class LtoMediumTotals(C.Structure):
+    _fields_ = [(k, C.c_double) for k in ("escaped", "absorbed", "truncated", "rr_killed", "rr_gained", "sum_mu")] + \
+               [(k, C.c_uint64) for k in ("n_collisions", "n_segments", "n_scatters")]
+
+
+def medium_walk(n_photons, *, albedo=0.99, g=0.0, radius=0.0, max_depth=256, mode="implicit", rr_start=3, rr_floor=0.05, n_rbins=32,
+                seed=0, first_photon=0, n_threads=0):
+    """CPU restatement of lt_medium_walk (float64, same Philox streams)."""
+    p = LtoMediumParams(float(albedo), float(g), float(radius), int(max_depth), 0 if mode == "analog" else 1, int(rr_start), int(n_rbins),
+                        float(rr_floor), int(seed), int(first_photon))
+    hist = np.zeros(max_depth + 1, np.uint64)
+    rbins = np.zeros(max(n_rbins, 1), np.float64)
+    tot = LtoMediumTotals()
+    L = lib()
+    L.lto_medium_walk.restype = C.c_int
+    L.lto_medium_walk(C.byref(p), C.c_uint64(int(n_photons)), hist.ctypes.data_as(C.c_void_p), rbins.ctypes.data_as(C.c_void_p),
+                      C.byref(tot), C.c_int(n_threads))
+    out = {k: getattr(tot, k) for k, _ in LtoMediumTotals._fields_}
+    out.update(hist=hist, rbins=rbins[:n_rbins], n_photons=int(n_photons))
+    return out
+
+
+def henyey_greenstein(cos_theta, g):
+    L = lib()
+    L.lto_henyey_greenstein.restype = C.c_double
+    return L.lto_henyey_greenstein(C.c_double(cos_theta), C.c_double(g))

@@ -305,6 +305,7 @@ static int do_render(lt_scene* s, const lt_render_params* p, const double* rand0
         if (granules < nwarps) grid = (int)std::max<int64_t>(1, (granules * 32 + block - 1) / block);
     }
     P.paths_per_warp = (int32_t)ppw;
+    P.lbvh_chunk = ((p->flags >> 8) & 0xff) ? ((p->flags >> 8) & 0xff) : 24;
     // suspended-frame storage for REFERENCE walks: a frame at stack depth k has bounce >= k and can still
     // recurse at bounce D-1, so up to D suspended frames; the megakernel keeps the first LT_LOCAL_FRAMES locally
     P.arena = nullptr; P.arena_frames = 0; P.arena_threads = (int64_t)grid * block;

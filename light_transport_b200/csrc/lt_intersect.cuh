@@ -224,48 +224,73 @@ LT_DEVINL bool slab_t(R lx, R ly, R lz, R hx, R hy, R hz, V3<R> o, V3<R> inv, R 
 // minority only grows).  The classic per-lane while-while loop ran with 5.5 of 32 lanes active on the
 // 1 M-triangle scene (ncu, round 1) because lanes drifted between the two phases.
 // Near child first, far child on the stack (local memory, LT_LBVH_STACK deep, checked at build time).
+// Traversal state of one lane; the stack lives in the caller's local memory so that a traversal can be
+// suspended and resumed (the megakernel runs it in bounded chunks, see lt_megakernel.cuh).
 template <typename R>
-LT_DEVINL void lbvh_query(unsigned amask, const LbvhNode* __restrict__ nodes, const TriRec<R>* __restrict__ tris, int n_tris,
-                          V3<R> o, V3<R> d, R eps, R tlimit, bool anyhit, int skip, int& prim, R& best, Stats& st) {
-    prim = -1;
-    best = tlimit;
-    V3<R> inv = mk<R>((R)1 / d.x, (R)1 / d.y, (R)1 / d.z);
-    int stack[LT_LBVH_STACK];
-    int sp = 0;
-    int cur = n_tris > 1 ? 0 : ~0;       // interior node index >= 0, leaf ~prim < 0, LT_LBVH_DONE
+struct LbvhState {
+    int cur, sp, prim;       // interior node index >= 0, leaf ~prim < 0, LT_LBVH_DONE; stack pointer; best primitive
+    R best;
+};
+
+template <typename R>
+LT_DEVINL void lbvh_begin(LbvhState<R>& s, int n_tris, R tlimit, bool live) {
+    s.prim = -1;
+    s.best = tlimit;
+    s.sp = 0;
+    s.cur = live ? (n_tris > 1 ? 0 : ~0) : LT_LBVH_DONE;
+}
+
+// Runs at most `max_steps` warp-voted steps (every lane of `amask` must call it, finished or idle lanes
+// with cur == LT_LBVH_DONE).  Returns when all lanes are done or the budget is used up.
+template <typename R>
+LT_DEVINL void lbvh_run(unsigned amask, LbvhState<R>& s, int* stack, const LbvhNode* __restrict__ nodes,
+                        const TriRec<R>* __restrict__ tris, V3<R> o, V3<R> d, V3<R> inv, R eps, bool anyhit, int skip, Stats& st,
+                        int max_steps) {
     // (dropping stale stack entries at pop time — entry distance kept beside the node — was measured:
     //  fewer node visits but 6-9 % slower overall on both the 28- and the 1 M-triangle scene.)
-    for (;;) {
-        const bool at_node = cur >= 0, at_leaf = (cur < 0) & (cur != LT_LBVH_DONE);
+    for (int step = 0; step < max_steps; ++step) {
+        const bool at_node = s.cur >= 0, at_leaf = (s.cur < 0) & (s.cur != LT_LBVH_DONE);
         const unsigned nm = __ballot_sync(amask, at_node), lm = __ballot_sync(amask, at_leaf);
         if (!(nm | lm)) break;
         if (__popc(nm) >= __popc(lm)) {
             if (at_node) {
-                const float4* p = reinterpret_cast<const float4*>(nodes + cur);
+                const float4* p = reinterpret_cast<const float4*>(nodes + s.cur);
                 float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
                 int4 r = __ldg(reinterpret_cast<const int4*>(p + 3));
                 R t0n, t1n;
                 st.box_tests += 2;
-                bool h0 = slab_t<R>((R)a.x, (R)a.y, (R)a.z, (R)a.w, (R)b.x, (R)b.y, o, inv, best, t0n);
-                bool h1 = slab_t<R>((R)b.z, (R)b.w, (R)c.x, (R)c.y, (R)c.z, (R)c.w, o, inv, best, t1n);
+                bool h0 = slab_t<R>((R)a.x, (R)a.y, (R)a.z, (R)a.w, (R)b.x, (R)b.y, o, inv, s.best, t0n);
+                bool h1 = slab_t<R>((R)b.z, (R)b.w, (R)c.x, (R)c.y, (R)c.z, (R)c.w, o, inv, s.best, t1n);
                 bool swap = t1n < t0n;
                 int nearc = swap ? r.y : r.x, farc = swap ? r.x : r.y;
-                if (h0 & h1) { stack[sp++] = farc; cur = nearc; }
-                else if (h0 | h1) cur = h0 ? r.x : r.y;
-                else cur = sp > 0 ? stack[--sp] : LT_LBVH_DONE;
+                if (h0 & h1) { stack[s.sp++] = farc; s.cur = nearc; }
+                else if (h0 | h1) s.cur = h0 ? r.x : r.y;
+                else s.cur = s.sp > 0 ? stack[--s.sp] : LT_LBVH_DONE;
             }
         } else if (at_leaf) {
-            int k = ~cur;
+            int k = ~s.cur;
             R t;
             st.tri_tests++;
             bool h = tri_intersect(tris[k], o, d, t);
-            if (h & (k != skip) & (eps < t) & ((t < best) | ((t == best) & (k < prim)))) {
-                best = t;
-                prim = k;
+            if (h & (k != skip) & (eps < t) & ((t < s.best) | ((t == s.best) & (k < s.prim)))) {
+                s.best = t;
+                s.prim = k;
             }
-            cur = (sp > 0 && !(anyhit && prim >= 0)) ? stack[--sp] : LT_LBVH_DONE;
+            s.cur = (s.sp > 0 && !(anyhit && s.prim >= 0)) ? stack[--s.sp] : LT_LBVH_DONE;
         }
     }
+}
+
+template <typename R>
+LT_DEVINL void lbvh_query(unsigned amask, const LbvhNode* __restrict__ nodes, const TriRec<R>* __restrict__ tris, int n_tris,
+                          V3<R> o, V3<R> d, R eps, R tlimit, bool anyhit, int skip, int& prim, R& best, Stats& st) {
+    int stack[LT_LBVH_STACK];
+    LbvhState<R> s;
+    lbvh_begin<R>(s, n_tris, tlimit, true);
+    V3<R> inv = mk<R>((R)1 / d.x, (R)1 / d.y, (R)1 / d.z);
+    lbvh_run<R>(amask, s, stack, nodes, tris, o, d, inv, eps, anyhit, skip, st, 0x7fffffff);
+    prim = s.prim;
+    best = s.best;
 }
 
 }  // namespace lt

@@ -96,53 +96,81 @@ static void fill_view(const lt_scene* s, SceneView<R>& v) {
     v.n_cnodes = s->n_cnodes; v.n_cleaves = s->n_cleaves; v.n_lbvh_nodes = s->n_lbvh_nodes;
 }
 
+template <typename R> static int build_compat_arrays(lt_scene* s);
+
+// Triangle records are formed ON THE DEVICE from the raw float64 arrays (uploaded once, also the LBVH
+// builder's input): a 1 M-triangle mesh never goes through a host loop.  ab/ac are float64 differences
+// rounded to R afterwards, exactly as R/src/intersects.py:64-65 forms them per call.
 template <typename R>
-static int build_scene_arrays(lt_scene* s, const lt_scene_desc* d) {
-    std::vector<TriRec<R>> tris(d->n_tris);
-    for (int i = 0; i < d->n_tris; ++i) {
-        TriRec<R>& t = tris[i];
-        memset(&t, 0, sizeof t);
-        for (int c = 0; c < 3; ++c) {
-            double a = d->tri_v0[3 * i + c], b = d->tri_v1[3 * i + c], cc = d->tri_v2[3 * i + c];
-            t.v0[c] = (R)a;
-            t.ab[c] = (R)(b - a);     // R/src/intersects.py:64-65, formed in float64 like the reference
-            t.ac[c] = (R)(cc - a);
-            t.n[c] = (R)d->tri_n[3 * i + c];
-        }
-        t.mat = d->tri_mat[i];
-        t.is_light = d->tri_light ? d->tri_light[i] : 0;
+__global__ void build_tris_kernel(const double* __restrict__ v0, const double* __restrict__ v1, const double* __restrict__ v2,
+                                  const double* __restrict__ nn, const int32_t* __restrict__ mat, const uint8_t* __restrict__ light, int n,
+                                  TriRec<R>* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    TriRec<R> t;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        double a = v0[3 * i + c], b = v1[3 * i + c], cc = v2[3 * i + c];
+        t.v0[c] = (R)a;
+        t.ab[c] = (R)__dsub_rn(b, a);
+        t.ac[c] = (R)__dsub_rn(cc, a);
+        t.n[c] = (R)nn[3 * i + c];
     }
-    std::vector<MatRec<R>> mats(d->n_mats);
-    for (int i = 0; i < d->n_mats; ++i) {
+    t.mat = mat[i];
+    t.is_light = light ? light[i] : 0;
+    t.pad[0] = t.pad[1] = 0;
+    out[i] = t;
+}
+
+template <typename T>
+static int upload_raw(T** dst, const T* src, size_t n, cudaStream_t st) {
+    LT_CUDA_OK(cudaMalloc(dst, std::max<size_t>(n, 1) * sizeof(T)));
+    if (n) LT_CUDA_OK(cudaMemcpyAsync(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice, st));
+    return LT_OK;
+}
+
+// build the R-typed device arrays of a scene on first use (float32 at creation, float64 when a float64 call needs it)
+template <typename R>
+static int ensure_arrays(lt_scene* s) {
+    SceneArrays<R>& a = s->arrays<R>();
+    if (a.tris) return LT_OK;
+    cudaStream_t st = s->ctx->stream;
+    const int n = s->n_tris;
+    LT_CUDA_OK(cudaMalloc(&a.tris, (size_t)n * sizeof(TriRec<R>)));
+    build_tris_kernel<R><<<(n + 255) / 256, 256, 0, st>>>(s->d_v0, s->d_v1, s->d_v2, s->d_n, s->d_mat, s->d_light, n, a.tris);
+    LT_CUDA_OK(cudaGetLastError());
+    std::vector<MatRec<R>> mats(s->n_mats);
+    for (int i = 0; i < s->n_mats; ++i) {
         MatRec<R>& m = mats[i];
         memset(&m, 0, sizeof m);
-        for (int c = 0; c < 3; ++c) m.kd[c] = (R)d->mat_kd[3 * i + c];
-        m.emission = (R)d->mat_emission[i];
-        m.ior = (R)d->mat_ior[i];
-        m.transmission = (R)d->mat_transmission[i];
-        m.flags = d->mat_flags[i];
+        for (int c = 0; c < 3; ++c) m.kd[c] = (R)s->h_mat_kd[3 * i + c];
+        m.emission = (R)s->h_mat_emission[i];
+        m.ior = (R)s->h_mat_ior[i];
+        m.transmission = (R)s->h_mat_transmission[i];
+        m.flags = s->h_mat_flags[i];
     }
-    std::vector<LightRec<R>> lights(d->n_lights);
-    for (int i = 0; i < d->n_lights; ++i) {
+    std::vector<LightRec<R>> lights(s->n_lights);
+    for (int i = 0; i < s->n_lights; ++i) {
         LightRec<R>& l = lights[i];
         memset(&l, 0, sizeof l);
         for (int c = 0; c < 3; ++c) {
-            l.pos[c] = (R)d->light_pos[3 * i + c];
-            l.n[c] = (R)d->light_n[3 * i + c];
-            l.lekd[c] = (R)d->light_lekd[3 * i + c];
+            l.pos[c] = (R)s->h_light_pos[3 * i + c];
+            l.n[c] = (R)s->h_light_n[3 * i + c];
+            l.lekd[c] = (R)s->h_light_lekd[3 * i + c];
         }
-        l.area = (R)d->light_area[i];
+        l.area = (R)s->h_light_area[i];
     }
-    SceneArrays<R>& a = s->arrays<R>();
     int rc;
-    if ((rc = upload(&a.tris, tris))) return rc;
     if ((rc = upload(&a.mats, mats))) return rc;
     if ((rc = upload(&a.lights, lights))) return rc;
+    if (s->h_nodes.n_nodes > 0 && (rc = build_compat_arrays<R>(s))) return rc;
+    LT_CUDA_OK(cudaStreamSynchronize(st));
     return LT_OK;
 }
 
 template <typename R>
-static int build_compat_arrays(lt_scene* s, const lt_node_desc* d) {
+static int build_compat_arrays(lt_scene* s) {
+    const HostNodes* d = &s->h_nodes;
     std::vector<CompatNode<R>> nodes(d->n_nodes);
     std::vector<CompatLeaf<R>> leaves;
     std::vector<int> leafpos(d->n_nodes, -1);
@@ -204,6 +232,7 @@ static int check_traversal(const lt_scene* s, int trav) {
 template <typename R>
 static int do_intersect(lt_scene* s, int traversal, const double* o, const double* d, int64_t n, int32_t* prim_out, double* t_out,
                         lt_counters* c) {
+    { int rc0 = ensure_arrays<R>(s); if (rc0) return rc0; }
     lt_ctx* ctx = s->ctx;
     cudaStream_t st = ctx->stream;
     InBuf<double> bo, bd;
@@ -235,6 +264,7 @@ static int do_intersect(lt_scene* s, int traversal, const double* o, const doubl
 template <typename R>
 static int do_render(lt_scene* s, const lt_render_params* p, const double* rand0, const double* rand1, const int32_t* light_idx,
                      double* film_sum, double* samples_out, lt_counters* c) {
+    { int rc0 = ensure_arrays<R>(s); if (rc0) return rc0; }
     lt_ctx* ctx = s->ctx;
     cudaStream_t st = ctx->stream;
     const int W = p->width, H = p->height, D = p->max_depth;
@@ -346,6 +376,7 @@ static int do_records(lt_scene* s, const lt_render_params* p, const double* rand
                       const double* logit1, const int32_t* light_idx, double* samples_out, double* record_log_pdf,
                       double* scene_rlp, int8_t* bounce_record, double* direct_list, double* indirect_list, double* rlp_minus,
                       double* rlp_plus, lt_counters* c) {
+    { int rc0 = ensure_arrays<R>(s); if (rc0) return rc0; }
     lt_ctx* ctx = s->ctx;
     cudaStream_t st = ctx->stream;
     const int W = p->width, H = p->height, D = p->max_depth, spp = p->spp;
@@ -515,11 +546,23 @@ int lt_scene_create(lt_ctx* ctx, const lt_scene_desc* d, lt_scene** out) {
     lt_scene* s = new lt_scene();
     s->ctx = ctx;
     s->n_tris = d->n_tris; s->n_mats = d->n_mats; s->n_lights = d->n_lights;
-    s->h_v0.assign(d->tri_v0, d->tri_v0 + 3 * (size_t)d->n_tris);
-    s->h_v1.assign(d->tri_v1, d->tri_v1 + 3 * (size_t)d->n_tris);
-    s->h_v2.assign(d->tri_v2, d->tri_v2 + 3 * (size_t)d->n_tris);
+    const size_t n3 = 3 * (size_t)d->n_tris;
+    cudaStream_t st = ctx->stream;
     int rc;
-    if ((rc = build_scene_arrays<float>(s, d)) || (rc = build_scene_arrays<double>(s, d))) { lt_scene_destroy(s); return rc; }
+    if ((rc = upload_raw(&s->d_v0, d->tri_v0, n3, st)) || (rc = upload_raw(&s->d_v1, d->tri_v1, n3, st)) ||
+        (rc = upload_raw(&s->d_v2, d->tri_v2, n3, st)) || (rc = upload_raw(&s->d_n, d->tri_n, n3, st)) ||
+        (rc = upload_raw(&s->d_mat, d->tri_mat, (size_t)d->n_tris, st))) { lt_scene_destroy(s); return rc; }
+    if (d->tri_light && (rc = upload_raw(&s->d_light, d->tri_light, (size_t)d->n_tris, st))) { lt_scene_destroy(s); return rc; }
+    s->h_mat_kd.assign(d->mat_kd, d->mat_kd + 3 * (size_t)d->n_mats);
+    s->h_mat_emission.assign(d->mat_emission, d->mat_emission + d->n_mats);
+    s->h_mat_ior.assign(d->mat_ior, d->mat_ior + d->n_mats);
+    s->h_mat_transmission.assign(d->mat_transmission, d->mat_transmission + d->n_mats);
+    s->h_mat_flags.assign(d->mat_flags, d->mat_flags + d->n_mats);
+    s->h_light_pos.assign(d->light_pos, d->light_pos + 3 * (size_t)d->n_lights);
+    s->h_light_n.assign(d->light_n, d->light_n + 3 * (size_t)d->n_lights);
+    s->h_light_lekd.assign(d->light_lekd, d->light_lekd + 3 * (size_t)d->n_lights);
+    s->h_light_area.assign(d->light_area, d->light_area + d->n_lights);
+    if ((rc = ensure_arrays<float>(s))) { lt_scene_destroy(s); return rc; }     // float64 records are built on first float64 use
     *out = s;
     return LT_OK;
 }
@@ -530,6 +573,12 @@ void lt_scene_destroy(lt_scene* s) {
     s->f32.release();
     s->f64.release();
     if (s->lbvh_nodes) cudaFree(s->lbvh_nodes);
+    if (s->d_v0) cudaFree(s->d_v0);
+    if (s->d_v1) cudaFree(s->d_v1);
+    if (s->d_v2) cudaFree(s->d_v2);
+    if (s->d_n) cudaFree(s->d_n);
+    if (s->d_mat) cudaFree(s->d_mat);
+    if (s->d_light) cudaFree(s->d_light);
     delete s;
 }
 
@@ -551,8 +600,14 @@ int lt_scene_set_compat_bvh(lt_scene* s, const lt_node_desc* d) {
         }
     }
     LT_CUDA_OK(cudaSetDevice(s->ctx->device));
+    HostNodes& h = s->h_nodes;
+    h.n_nodes = d->n_nodes;
+    h.bmin.assign(d->bmin, d->bmin + 3 * (size_t)d->n_nodes); h.bmax.assign(d->bmax, d->bmax + 3 * (size_t)d->n_nodes);
+    h.prim_off.assign(d->prim_off, d->prim_off + d->n_nodes); h.second.assign(d->second, d->second + d->n_nodes);
+    h.n_prims.assign(d->n_prims, d->n_prims + d->n_nodes); h.axis.assign(d->axis, d->axis + d->n_nodes);
     int rc;
-    if ((rc = build_compat_arrays<float>(s, d)) || (rc = build_compat_arrays<double>(s, d))) return rc;
+    if ((rc = build_compat_arrays<float>(s))) return rc;
+    if (s->f64.tris && (rc = build_compat_arrays<double>(s))) return rc;
     return LT_OK;
 }
 

@@ -25,6 +25,12 @@ struct SceneArrays {
 
 }  // namespace lt
 
+struct HostNodes {
+    int n_nodes = 0;
+    std::vector<double> bmin, bmax;
+    std::vector<int32_t> prim_off, second, n_prims, axis;
+};
+
 struct lt_ctx {
     int device = 0;
     cudaDeviceProp prop;
@@ -47,7 +53,14 @@ struct lt_scene {
     lt::SceneArrays<float> f32;
     lt::SceneArrays<double> f64;
     lt::LbvhNode* lbvh_nodes = nullptr;
-    std::vector<double> h_v0, h_v1, h_v2;   // host copy of the vertices (LBVH build input)
+    // raw float64 scene arrays on the device (uploaded once): input of the record builders and of the LBVH build
+    double *d_v0 = nullptr, *d_v1 = nullptr, *d_v2 = nullptr, *d_n = nullptr;
+    int32_t* d_mat = nullptr;
+    uint8_t* d_light = nullptr;
+    // small host copies for the lazily built float64 records
+    std::vector<double> h_mat_kd, h_mat_emission, h_mat_ior, h_mat_transmission, h_light_pos, h_light_n, h_light_lekd, h_light_area;
+    std::vector<int32_t> h_mat_flags;
+    HostNodes h_nodes;
     template <typename R> lt::SceneArrays<R>& arrays();
     template <typename R> const lt::SceneArrays<R>& arrays() const;
 };

@@ -311,28 +311,23 @@ extern "C" int lt_bvh_build(lt_scene* s, int flags, lt_bvh_stats* out) {
     }
     const int blocks = (n + LB_THREADS - 1) / LB_THREADS;
     const int tiles = (n + RS_TILE - 1) / RS_TILE;
-    Tmp<double> v0, v1, v2;
     Tmp<Box> prim_boxes, node_boxes;
     Tmp<float> block_cb, cb;
     Tmp<uint64_t> keys_a, keys_b;
     Tmp<uint32_t> vals_a, vals_b, hist;
     Tmp<int> left, right, par_i, par_l, arrive, maxd;
-    LT_CUDA_OK(v0.alloc(3 * (size_t)n)); LT_CUDA_OK(v1.alloc(3 * (size_t)n)); LT_CUDA_OK(v2.alloc(3 * (size_t)n));
     LT_CUDA_OK(prim_boxes.alloc(n)); LT_CUDA_OK(node_boxes.alloc(n));
     LT_CUDA_OK(block_cb.alloc(6 * (size_t)blocks)); LT_CUDA_OK(cb.alloc(6));
     LT_CUDA_OK(keys_a.alloc(n)); LT_CUDA_OK(keys_b.alloc(n)); LT_CUDA_OK(vals_a.alloc(n)); LT_CUDA_OK(vals_b.alloc(n));
     LT_CUDA_OK(hist.alloc(256 * (size_t)tiles));
     LT_CUDA_OK(left.alloc(n)); LT_CUDA_OK(right.alloc(n)); LT_CUDA_OK(par_i.alloc(n)); LT_CUDA_OK(par_l.alloc(n));
     LT_CUDA_OK(arrive.alloc(n)); LT_CUDA_OK(maxd.alloc(1));
-    LT_CUDA_OK(cudaMemcpyAsync(v0.p, s->h_v0.data(), 3 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
-    LT_CUDA_OK(cudaMemcpyAsync(v1.p, s->h_v1.data(), 3 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
-    LT_CUDA_OK(cudaMemcpyAsync(v2.p, s->h_v2.data(), 3 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
     LT_CUDA_OK(cudaMemsetAsync(arrive.p, 0, (size_t)n * sizeof(int), st));
     LT_CUDA_OK(cudaMemsetAsync(maxd.p, 0, sizeof(int), st));
     cudaEvent_t e0, e1, e2, e3;
     cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventCreate(&e3);
     cudaEventRecord(e0, st);
-    prim_boxes_kernel<<<blocks, LB_THREADS, 0, st>>>(v0.p, v1.p, v2.p, n, prim_boxes.p, block_cb.p);
+    prim_boxes_kernel<<<blocks, LB_THREADS, 0, st>>>(s->d_v0, s->d_v1, s->d_v2, n, prim_boxes.p, block_cb.p);
     reduce_cb_kernel<<<1, LB_THREADS, 0, st>>>(block_cb.p, blocks, cb.p);
     morton_kernel<<<blocks, LB_THREADS, 0, st>>>(prim_boxes.p, n, cb.p, keys_a.p, vals_a.p);
     cudaEventRecord(e1, st);

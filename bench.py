@@ -328,8 +328,11 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     ms, rays, paths, kernel_ns, flops, last, memo = 0.0, 0, 0, 0, 0.0, None, 0
+    counters_sum = {"box_tests": 0, "tri_tests": 0, "rays_ext": 0, "rays_shadow": 0}
     for i in range(args.steps):
         t, c = step(100 + i, True)
+        for k in counters_sum:
+            counters_sum[k] += c[k]
         ms += t
         rays += c["rays_ext"] + c["rays_shadow"]
         paths += c["paths"]
@@ -409,6 +412,28 @@ def main():
                             "box_tests_per_ray": last["box_tests"] / max(last["rays_ext"] + last["rays_shadow"], 1),
                             "tri_tests_per_ray": last["tri_tests"] / max(last["rays_ext"] + last["rays_shadow"], 1),
                             "lane_utilisation": last["lane_steps"] / max(last["lane_slots"], 1)}}
+        if args.traversal == "lbvh" and WORKLOAD["scene"] == "mesh":
+            # a large mesh is bound by node/triangle bytes, not flops.  B_ray = 64 B per visited
+            # binary node (both child boxes + links; box_tests counts 2 per visit) + 48 B per tested triangle +
+            # 48 B ray in / hit out.  Served mostly from L2 (the tree is L2-resident), so this is an upper bound
+            # on what HBM had to deliver; the denominator is still the measured HBM copy bandwidth.
+            peaks = {}
+            try:
+                peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            except Exception:
+                pass
+            hbm = float(peaks.get("hbm_gbs", 6556.5))
+            bytes_all = (32.0 * counters_sum["box_tests"] + 48.0 * counters_sum["tri_tests"]
+                         + 48.0 * (counters_sum["rays_ext"] + counters_sum["rays_shadow"]))
+            gbs = bytes_all / (kernel_ns * 1e-9) / 1e9
+            rf = out["roofline"]
+            rf["fp32"] = {"achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
+                          "flops_model": rf.pop("flops_model"), "peak_source": rf.pop("peak_source")}
+            rf.update({"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
+                       "bytes_model": "64 B x visited nodes (= box_tests/2) + 48 B x tri_tests + 48 B x rays (SURVEY.md 8d); "
+                                      "algorithmic bytes, mostly served by the 126 MB L2",
+                       "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6556.5 GB/s (B200_PROFILING.md)",
+                       "bytes_per_ray": bytes_all / max(counters_sum["rays_ext"] + counters_sum["rays_shadow"], 1)})
         if world == 1 and not args.no_cpu_baseline and WORKLOAD["scene"] != "mesh":
             out["cpu_baseline"], _, _ = cpu_baseline(ps, nodes, cam, depth, args, sample_spp=8)
         if world == 1 and not args.no_rmse and args.config == "c2":

@@ -83,6 +83,67 @@ LT_DEVINL bool slab(const float* bmin, const float* bmax, V3<float> o, V3<float>
     return !(t0 > t1);
 }
 
+// ---- float32 leaf bounds, two leaves per step ---------------------------------------------------------
+// The hit mask over the COMPAT leaves is a third of the whole walk's instructions, so the float32 path
+// evaluates it from a table laid out for it (built per CTA in shared memory by build_slab_pairs):
+//   * per axis the NEAR plane is bmin when the direction component is positive and bmax when it is
+//     negative, so the per-axis min/max of the two slab distances becomes an ADDRESS choice made once
+//     per ray: each (pair, axis) holds {near_a, near_b, far_a, far_b} for both signs, 16 bytes apart.
+//     Rounding is monotone, so the selected value is bit-identical to fminf/fmaxf of the two products
+//     (they differ only when a distance is NaN: origin exactly on a box plane and a zero direction).
+//   * the subtract and the multiply run on two leaves at a time (add.f32x2 / mul.f32x2, sm_100),
+//     each half rounded exactly like the scalar instruction.
+// 13.5 instructions per leaf instead of 27.5.
+#define LT_SLAB_PAIR_FLOATS 24
+LT_DEVINL int slab_pairs_bytes(int n_leaves) { return ((n_leaves + 1) >> 1) * LT_SLAB_PAIR_FLOATS * 4; }
+
+LT_DEVINL void build_slab_pairs(float* tab, const CompatLeaf<float>* leaves, int n_leaves) {
+    const int n_pairs = (n_leaves + 1) >> 1;
+    for (int i = threadIdx.x; i < n_pairs * 3; i += blockDim.x) {
+        const int p = i / 3, k = i - 3 * p;
+        const CompatLeaf<float>& a = leaves[2 * p];
+        const CompatLeaf<float>& b = leaves[min(2 * p + 1, n_leaves - 1)];     // odd count: the last leaf twice, bit masked off
+        float* t = tab + LT_SLAB_PAIR_FLOATS * p + 8 * k;
+        t[0] = a.bmin[k]; t[1] = b.bmin[k]; t[2] = a.bmax[k]; t[3] = b.bmax[k];     // direction component >= 0
+        t[4] = a.bmax[k]; t[5] = b.bmax[k]; t[6] = a.bmin[k]; t[7] = b.bmin[k];     // direction component < 0
+    }
+}
+
+LT_DEVINL uint64_t slab_pairs_mask(const float* tab, int n_leaves, V3<float> o, V3<float> inv) {
+    const float widen = 1.0f + 2.0f * ((3.0f * 5.9604644775390625e-08f) / (1.0f - 3.0f * 5.9604644775390625e-08f));
+    const float4* tx = reinterpret_cast<const float4*>(tab) + (__float_as_uint(inv.x) >> 31);
+    const float4* ty = reinterpret_cast<const float4*>(tab) + 2 + (__float_as_uint(inv.y) >> 31);
+    const float4* tz = reinterpret_cast<const float4*>(tab) + 4 + (__float_as_uint(inv.z) >> 31);
+    const float2 nox = make_float2(-o.x, -o.x), noy = make_float2(-o.y, -o.y), noz = make_float2(-o.z, -o.z);
+    const float2 ivx = make_float2(inv.x, inv.x), ivy = make_float2(inv.y, inv.y), ivz = make_float2(inv.z, inv.z);
+    const float2 w2 = make_float2(widen, widen);
+    const int n_pairs = (n_leaves + 1) >> 1;
+    uint64_t hm = 0;
+    for (int p0 = 0; p0 < n_pairs; p0 += 16) {          // 32 leaves per 32-bit word
+        const int pe = min(n_pairs - p0, 16);
+        uint32_t m = 0, bit = 1u;
+#pragma unroll 4
+        for (int q = 0; q < pe; ++q) {
+            const int p = p0 + q;
+            const float4 X = tx[6 * p], Y = ty[6 * p], Z = tz[6 * p];
+            const float2 nx = __fmul2_rn(__fadd2_rn(make_float2(X.x, X.y), nox), ivx);
+            const float2 fx = __fmul2_rn(__fadd2_rn(make_float2(X.z, X.w), nox), ivx);
+            const float2 ny = __fmul2_rn(__fadd2_rn(make_float2(Y.x, Y.y), noy), ivy);
+            const float2 fy = __fmul2_rn(__fadd2_rn(make_float2(Y.z, Y.w), noy), ivy);
+            const float2 nz = __fmul2_rn(__fadd2_rn(make_float2(Z.x, Z.y), noz), ivz);
+            const float2 fz = __fmul2_rn(__fadd2_rn(make_float2(Z.z, Z.w), noz), ivz);
+            const float t0a = fmaxf(fmaxf(nx.x, ny.x), fmaxf(nz.x, 0.0f));
+            const float t0b = fmaxf(fmaxf(nx.y, ny.y), fmaxf(nz.y, 0.0f));
+            const float2 t1 = __fmul2_rn(make_float2(fminf(fminf(fx.x, fy.x), fz.x), fminf(fminf(fx.y, fy.y), fz.y)), w2);
+            if (!(t0a > t1.x)) m |= bit;
+            if (!(t0b > t1.y)) m |= bit << 1;
+            bit <<= 2;
+        }
+        hm |= (uint64_t)m << (2 * p0);
+    }
+    return n_leaves >= 64 ? hm : hm & ((1ull << n_leaves) - 1ull);
+}
+
 // ---- COMPAT --------------------------------------------------------------------------------------
 // intersect_bvh keeps a `visited` list over NODES, starts at the root and (a) follows near children
 // while interior bounds are hit, then (b) repeatedly jumps to the LAST unvisited index (its scan has
@@ -101,7 +162,7 @@ LT_DEVINL bool slab(const float* bmin, const float* bmax, V3<float> o, V3<float>
 // mask; then every lane repeatedly takes its lowest hit-and-unvisited position.  Loops are
 // warp-uniform (`amask` = the lanes running this query together) so the lanes stay in lock step.
 template <typename R>
-LT_DEVINL void compat_query(unsigned amask, const CompatNode<R>* nodes, const CompatLeaf<R>* leaves, int n_leaves,
+LT_DEVINL void compat_query(unsigned amask, const CompatNode<R>* nodes, const CompatLeaf<R>* leaves, int n_leaves, const float* slabtab,
                             const TriRec<R>* tris, V3<R> o, V3<R> d, R eps, R tlimit, bool anyhit, int skip, int& prim, R& best,
                             Stats& st) {
     V3<R> inv = mk<R>((R)1 / d.x, (R)1 / d.y, (R)1 / d.z);
@@ -131,7 +192,9 @@ LT_DEVINL void compat_query(unsigned amask, const CompatNode<R>* nodes, const Co
     // phase (b) part 1: bounds of all leaves (a root that ends the walk needs none)
     uint64_t hm = 0;
     if (!done) {
-        if (n_leaves <= 32) {                       // the usual case: 32-bit mask arithmetic
+        if (sizeof(R) == 4 && slabtab) {            // float32: paired, sign-selected table (see slab_pairs_mask)
+            hm = slab_pairs_mask(slabtab, n_leaves, mk<float>((float)o.x, (float)o.y, (float)o.z), mk<float>((float)inv.x, (float)inv.y, (float)inv.z));
+        } else if (n_leaves <= 32) {                // 32-bit mask arithmetic
             uint32_t m = 0;
 #pragma unroll 4
             for (int li = 0; li < n_leaves; ++li) {

@@ -27,18 +27,19 @@ LT_DEVINL const T* stage_array(char*& cursor, const T* src, int n) {
     return dst;
 }
 
-LT_DEVINL void flush_film(double* film, int64_t pix, double acc[3]) {
+LT_DEVINL void flush_film(double* film, int32_t pix, double acc[3]) {
     if (pix >= 0 && (acc[0] != 0.0 || acc[1] != 0.0 || acc[2] != 0.0)) {
-        atomicAdd(film + pix * 3 + 0, acc[0]);
-        atomicAdd(film + pix * 3 + 1, acc[1]);
-        atomicAdd(film + pix * 3 + 2, acc[2]);
+        double* f = film + (size_t)pix * 3;
+        atomicAdd(f + 0, acc[0]);
+        atomicAdd(f + 1, acc[1]);
+        atomicAdd(f + 2, acc[2]);
     }
     acc[0] = acc[1] = acc[2] = 0.0;
 }
 
 // granule-end flush: lanes holding the same pixel are summed by the lowest such lane (shuffles),
 // which then issues the atomics — one triple per distinct pixel per warp.
-LT_DEVINL void flush_film_warp(double* film, int64_t pix, double acc[3]) {
+LT_DEVINL void flush_film_warp(double* film, int32_t pix, double acc[3]) {
     const unsigned full = 0xffffffffu;
     int lane = threadIdx.x & 31;
     unsigned same = __match_any_sync(full, pix);
@@ -66,6 +67,7 @@ __global__ void __launch_bounds__(LT_BLOCK, sizeof(R) == 4 ? LT_MIN_BLOCKS_F32 :
     const MatRec<R>* mats = P.S.mats;
     const CompatNode<R>* cnodes = P.S.cnodes;
     const CompatLeaf<R>* cleaves = P.S.cleaves;
+    const float* slabtab = nullptr;
     if (TRAV != LT_TRAV_LBVH) {
         char* cur = smem;
         tris = stage_array(cur, P.S.tris, P.S.n_tris);
@@ -75,6 +77,11 @@ __global__ void __launch_bounds__(LT_BLOCK, sizeof(R) == 4 ? LT_MIN_BLOCKS_F32 :
             cleaves = stage_array(cur, P.S.cleaves, P.S.n_cleaves);
         }
         __syncthreads();
+        if (TRAV == LT_TRAV_COMPAT && sizeof(R) == 4) {     // float32: leaf bounds re-laid for slab_pairs_mask
+            build_slab_pairs(reinterpret_cast<float*>(cur), reinterpret_cast<const CompatLeaf<float>*>(cleaves), P.S.n_cleaves);
+            slabtab = reinterpret_cast<const float*>(cur);
+            __syncthreads();
+        }
     }
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -98,35 +105,42 @@ __global__ void __launch_bounds__(LT_BLOCK, sizeof(R) == 4 ? LT_MIN_BLOCKS_F32 :
     V3<R> tinv = mk<R>((R)0, (R)0, (R)0);
     bool tracing = false;
     Stats st;
-    uint32_t n_ext = 0, n_shadow = 0, n_paths = 0, lidx_overflow = 0, frame_overflow = 0, max_frames = 0;
-    uint32_t lane_steps = 0, warp_iters = 0, n_memo = 0;
+    // Counters live in SHARED memory, one row per warp, bumped by lane 0 with result-less atomics (fire and
+    // forget) from warp-uniform values (ballot/popc, warp reductions at the converged ends of an iteration).
+    // As eleven per-lane registers they did not fit the 80-register budget, were spilled, and every `n++` became
+    // a local-memory load + store whose latency was 12 % of all stall samples.
+    enum { C_EXT = 0, C_SHADOW, C_STEPS, C_ITERS, C_MEMO, C_LIDX, C_FOVF, C_MAXF, C_PATHS, C_N };
+    __shared__ unsigned int sh_cnt[LT_BLOCK / 32][C_N];
+    unsigned int* const cnt = sh_cnt[threadIdx.x >> 5];
+    if (lane < C_N) cnt[lane] = 0;
+    __syncwarp();
     double acc[3] = {0, 0, 0};
-    int64_t acc_pix = -1;
+    int32_t acc_pix = -1;
 
     for (int64_t g = gwarp; g * ppw < P.total_paths; g += nwarps) {
-        int64_t next = g * ppw;
-        const int64_t end = min(P.total_paths, next + ppw);
-        // (pixel, sample) of the granule's first index: one 64-bit division per granule, 32-bit ones per path
-        const int64_t g_pix = next / P.ns;
-        const uint32_t g_s = (uint32_t)(next - g_pix * P.ns);
-        const int64_t g_first = next;
+        // the granule: indices [g*ppw, g*ppw + g_n); (pixel, sample) of its first index from one 64-bit division,
+        // 32-bit ones per path
+        const int64_t g_first = g * ppw;
+        const int32_t g_n = (int32_t)min((int64_t)ppw, P.total_paths - g_first);
+        const int32_t g_pix = (int32_t)(g_first / P.ns);
+        const uint32_t g_s = (uint32_t)(g_first - (int64_t)g_pix * P.ns);
+        int32_t next = 0;
+        if (lane == 0) atomicAdd(cnt + C_PATHS, (unsigned)g_n);            // every started path is tallied exactly once
         for (;;) {
             // ---- regeneration: idle lanes take the next indices of the granule
             bool need = ln.qtype == 0;
             unsigned m = __ballot_sync(full, need);
             if (m) {
-                int rank = __popc(m & ((1u << lane) - 1u));
-                int64_t mine = next + rank;
+                int32_t mine = next + __popc(m & ((1u << lane) - 1u));
                 next += __popc(m);
-                if (need && mine < end) {
-                    uint32_t off = (uint32_t)(mine - g_first) + g_s;
+                if (need && mine < g_n) {
+                    uint32_t off = (uint32_t)mine + g_s;
                     uint32_t dp = off / (uint32_t)P.ns;
-                    int64_t pix = P.pixel0 + g_pix + dp;
+                    int32_t pix = P.pixel0 + g_pix + (int32_t)dp;
                     int s_rel = (int)(off - dp * (uint32_t)P.ns);
                     if (pix != acc_pix) { flush_film(P.film, acc_pix, acc); acc_pix = pix; }
                     start_path<R>(P, ln, pix, s_rel);
                     if (ln.qtype == 0) {   // max_depth == 0
-                        n_paths++;
                         if (P.samples) { double* o = P.samples + ((size_t)pix * P.ns + s_rel) * 3; o[0] = o[1] = o[2] = 0; }
                     }
                 }
@@ -134,7 +148,7 @@ __global__ void __launch_bounds__(LT_BLOCK, sizeof(R) == 4 ? LT_MIN_BLOCKS_F32 :
             bool active = ln.qtype != 0;
             unsigned am = __ballot_sync(full, active);
             if (!am) break;
-            warp_iters++;
+            uint32_t it_memo = 0, it_lidx = 0, it_fovf = 0, it_maxf = 0;    // this iteration's per-lane events, reduced below
             if (TRAV == LT_TRAV_LBVH) {
                 if (active && !tracing) {
                     lbvh_begin<R>(ts, P.S.n_tris, ln.tlimit, true);
@@ -142,39 +156,43 @@ __global__ void __launch_bounds__(LT_BLOCK, sizeof(R) == 4 ? LT_MIN_BLOCKS_F32 :
                     tracing = true;
                 }
                 lbvh_run<R>(full, ts, tstack, P.S.lbvh, tris, ln.o, ln.d, tinv, eps, ln.qtype == 2, ln.skip, st, P.lbvh_chunk);
-                if (active) lane_steps++;
                 active = tracing && ts.cur == LT_LBVH_DONE;       // only lanes whose query just completed go on to shade
                 if (active) tracing = false;
             }
+            {
+                const unsigned em = __ballot_sync(full, active && ln.qtype == 1), sm = __ballot_sync(full, active && ln.qtype == 2);
+                if (lane == 0) {
+                    atomicAdd(cnt + C_ITERS, 1u);
+                    atomicAdd(cnt + C_STEPS, (unsigned)__popc(am));
+                    if (em) atomicAdd(cnt + C_EXT, (unsigned)__popc(em));
+                    if (sm) atomicAdd(cnt + C_SHADOW, (unsigned)__popc(sm));
+                }
+            }
             if (active) {
-                if (TRAV != LT_TRAV_LBVH) lane_steps++;
                 // ---- the one ray query of this iteration
                 int prim = ts.prim;
                 R t = ts.best;
                 const bool anyhit = ln.qtype == 2;
                 if (TRAV == LT_TRAV_COMPAT)
-                    compat_query<R>(am, cnodes, cleaves, P.S.n_cleaves, tris, ln.o, ln.d, eps, ln.tlimit, anyhit, ln.skip, prim, t, st);
+                    compat_query<R>(am, cnodes, cleaves, P.S.n_cleaves, slabtab, tris, ln.o, ln.d, eps, ln.tlimit, anyhit, ln.skip, prim, t, st);
                 else if (TRAV == LT_TRAV_NEAREST)
                     nearest_query<R>(tris, P.S.n_tris, ln.o, ln.d, eps, ln.tlimit, anyhit, ln.skip, prim, t, st);
                 (void)anyhit;
                 int stt;
                 R adv_rand0 = (R)0;
                 if (ln.qtype == 1) {
-                    n_ext++;
-                    stt = shade_extension<R, SEM>(P, ln, prim, t, tris, mats, lidx_overflow, adv_rand0);
+                    stt = shade_extension<R, SEM>(P, ln, prim, t, tris, mats, it_lidx, adv_rand0);
                 } else {
-                    n_shadow++;
-                    stt = shade_shadow<R, SEM, LT_LOCAL_FRAMES>(P, ln, frames, gtid, prim >= 0, frame_overflow, max_frames, adv_rand0);
+                    stt = shade_shadow<R, SEM, LT_LOCAL_FRAMES>(P, ln, frames, gtid, prim >= 0, it_fovf, it_maxf, adv_rand0);
                 }
                 bool alive = true;
                 if (stt != ST_QUERY) {      // roulette / bounce++ / frame pops: one shared copy for every branch
-                    alive = advance<R, SEM, LT_LOCAL_FRAMES>(P, ln, frames, gtid, stt == ST_ADVANCE_ENDED, adv_rand0, n_memo);
+                    alive = advance<R, SEM, LT_LOCAL_FRAMES>(P, ln, frames, gtid, stt == ST_ADVANCE_ENDED, adv_rand0, it_memo);
                     ln.qtype = 1;
                     ln.tlimit = Lim<R>::inf();
                 }
                 if (!alive) {
                     // ---- tally (R/src/path_tracing.py:297-298)
-                    n_paths++;
                     acc[0] += (double)ln.L.x; acc[1] += (double)ln.L.y; acc[2] += (double)ln.L.z;
                     if (P.samples) {
                         double* o = P.samples + ((size_t)ln.pix * P.ns + ln.s_rel) * 3;
@@ -183,28 +201,35 @@ __global__ void __launch_bounds__(LT_BLOCK, sizeof(R) == 4 ? LT_MIN_BLOCKS_F32 :
                     ln.qtype = 0;
                 }
             }
+            // ---- converged again: fold this iteration's per-lane events into the warp's counters
+            if (SEM == LT_SEM_REFERENCE) {
+                const unsigned memo = __reduce_add_sync(full, it_memo), maxf = __reduce_max_sync(full, it_maxf);
+                if (lane == 0) {
+                    if (memo) atomicAdd(cnt + C_MEMO, memo);
+                    if (maxf) atomicMax(cnt + C_MAXF, maxf);
+                }
+            }
+            if (__any_sync(full, (it_lidx | it_fovf) != 0)) {
+                const unsigned a = __reduce_add_sync(full, it_lidx), b = __reduce_add_sync(full, it_fovf);
+                if (lane == 0) { atomicAdd(cnt + C_LIDX, a); atomicAdd(cnt + C_FOVF, b); }
+            }
         }
         flush_film_warp(P.film, acc_pix, acc);
         acc_pix = -1;
     }
-    // ---- counters: warp-reduced, one atomic per warp and field
+    // ---- counters: one global atomic per warp and field (box/triangle tests are the only per-lane ones left)
     if (P.counters) {
-        unsigned long long v[13] = {n_paths, (unsigned long long)n_ext + n_memo, n_shadow, st.box_tests, st.tri_tests, 0, lidx_overflow,
-                                    frame_overflow, lane_steps, (unsigned long long)warp_iters, 0, 0, n_memo};
+        unsigned long long bt = st.box_tests, tt = st.tri_tests;
+        for (int o = 16; o > 0; o >>= 1) { bt += __shfl_xor_sync(full, bt, o); tt += __shfl_xor_sync(full, tt, o); }
+        __syncwarp();
+        if (lane == 0) {
+            const unsigned long long memo = cnt[C_MEMO];
+            const unsigned long long v[13] = {cnt[C_PATHS], cnt[C_EXT] + memo, cnt[C_SHADOW], bt, tt, 0, cnt[C_LIDX], cnt[C_FOVF],
+                                              cnt[C_STEPS], (unsigned long long)cnt[C_ITERS] * 32ull, 0, 0, memo};
 #pragma unroll
-        for (int k = 0; k < 13; ++k) {
-            if (k == 5 || k == 10 || k == 11) continue;
-            unsigned long long x = v[k];
-            if (k == 9) { x = lane == 0 ? x * 32ull : 0ull; }
-            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(full, x, o);
-            if (lane == 0 && x) atomicAdd(P.counters + k, x);
-        }
-        if (SEM == LT_SEM_REFERENCE) {
-            uint32_t mf = max(max_frames, 1u);
-            for (int o = 16; o > 0; o >>= 1) mf = max(mf, __shfl_xor_sync(full, mf, o));
-            if (lane == 0) atomicMax(P.counters + 5, (unsigned long long)mf);
-        } else if (lane == 0 && threadIdx.x == 0 && blockIdx.x == 0) {
-            atomicMax(P.counters + 5, 1ull);
+            for (int k = 0; k < 13; ++k)
+                if (k != 5 && k != 10 && k != 11 && v[k]) atomicAdd(P.counters + k, v[k]);
+            atomicMax(P.counters + 5, SEM == LT_SEM_REFERENCE ? (unsigned long long)max(cnt[C_MAXF], 1u) : 1ull);
         }
     }
 }
@@ -226,6 +251,13 @@ struct IntersectParams {
 template <typename R, int TRAV>
 __global__ void __launch_bounds__(LT_BLOCK) intersect_kernel(const IntersectParams<R> P) {
     Stats st;
+    extern __shared__ __align__(16) char smem[];
+    const float* slabtab = nullptr;
+    if (TRAV == LT_TRAV_COMPAT && sizeof(R) == 4) {     // dynamic shared memory = slab_pairs_bytes(n_cleaves)
+        build_slab_pairs(reinterpret_cast<float*>(smem), reinterpret_cast<const CompatLeaf<float>*>(P.S.cleaves), P.S.n_cleaves);
+        slabtab = reinterpret_cast<const float*>(smem);
+        __syncthreads();
+    }
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -240,7 +272,7 @@ __global__ void __launch_bounds__(LT_BLOCK) intersect_kernel(const IntersectPara
             int prim;
             R t;
             if (TRAV == LT_TRAV_COMPAT)
-                compat_query<R>(am, P.S.cnodes, P.S.cleaves, P.S.n_cleaves, P.S.tris, o, d, (R)P.eps, Lim<R>::inf(), false, -1, prim, t, st);
+                compat_query<R>(am, P.S.cnodes, P.S.cleaves, P.S.n_cleaves, slabtab, P.S.tris, o, d, (R)P.eps, Lim<R>::inf(), false, -1, prim, t, st);
             else if (TRAV == LT_TRAV_NEAREST)
                 nearest_query<R>(P.S.tris, P.S.n_tris, o, d, (R)P.eps, Lim<R>::inf(), false, -1, prim, t, st);
             else

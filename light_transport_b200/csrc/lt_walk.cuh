@@ -69,6 +69,13 @@ struct Lane {
     R pdf_pending;                // pdf of the pending hemisphere sample (record kernel: log(pdf), R/src/path_tracing.py:94)
 };
 
+// (pixel * spp + s): Philox counter / replay row.  Derived at each use (one 64-bit multiply-add) instead of being
+// carried in two registers through the whole walk.
+template <typename R>
+LT_DEVINL uint64_t path_id_of(const WalkParams<R>& P, const Lane<R>& ln) {
+    return (uint64_t)(uint32_t)ln.pix * (uint64_t)(uint32_t)P.spp + (uint64_t)(uint32_t)(P.s0 + ln.s_rel);
+}
+
 // random numbers of (path, bounce): replayed Scene.rand_0/rand_1 rows or Philox stream 0
 template <typename R>
 LT_DEVINL void get_rand(const WalkParams<R>& P, uint64_t path_id, int bounce, R& r0, R& r1) {
@@ -93,13 +100,14 @@ LT_DEVINL R get_rand0(const WalkParams<R>& P, uint64_t path_id, int bounce) {
 template <typename R>
 LT_DEVINL int pick_light(const WalkParams<R>& P, Lane<R>& ln, uint32_t& overflow) {
     uint32_t k = (uint32_t)ln.nee++;
+    const uint64_t path_id = path_id_of(P, ln);
     if (P.light_idx) {
         if ((int)k >= P.n_light_idx) { overflow++; return 0; }
-        return __ldg(P.light_idx + (size_t)ln.path_id * (size_t)P.n_light_idx + k);
+        return __ldg(P.light_idx + (size_t)path_id * (size_t)P.n_light_idx + k);
     }
     if (P.S.n_lights == 1) return 0;
     uint32_t w[4];
-    philox4x32_10((uint32_t)ln.path_id, (uint32_t)(ln.path_id >> 32), k, 1u, (uint32_t)P.seed, (uint32_t)(P.seed >> 32), w);
+    philox4x32_10((uint32_t)path_id, (uint32_t)(path_id >> 32), k, 1u, (uint32_t)P.seed, (uint32_t)(P.seed >> 32), w);
     return (int)__umulhi(w[0], (uint32_t)P.S.n_lights);
 }
 
@@ -315,7 +323,7 @@ template <typename R, int SEM>
 LT_DEVINL int shade_extension(const WalkParams<R>& P, Lane<R>& ln, int prim, R t, const TriRec<R>* tris, const MatRec<R>* mats,
                               uint32_t& lidx_overflow, R& adv_rand0) {
     R rand_0 = (R)0, rand_1 = (R)0;
-    if (prim >= 0) get_rand<R>(P, ln.path_id, ln.bounce, rand_0, rand_1);
+    if (prim >= 0) get_rand<R>(P, path_id_of(P, ln), ln.bounce, rand_0, rand_1);
     return shade_extension_with<R, SEM>(P, ln, prim, t, tris, mats, lidx_overflow, adv_rand0, rand_0, rand_1);
 }
 

@@ -53,11 +53,17 @@ LT_DEVINL void flush_film_warp(double* film, int32_t pix, double acc[3]) {
     acc[0] = acc[1] = acc[2] = 0.0;
 }
 
+// float32: 5 CTAs x 4 warps per SM = 96 registers, no spills.  Measured on C2 (Grays/s): 4: 14.7, 5: 15.5, 6 (80
+// registers, 72 B of spills): 15.0, 7: 14.4, 8: 13.9 — the walk is bound by dependent-instruction latency and
+// divergence, not by the number of resident warps.
 #ifndef LT_MIN_BLOCKS_F32
-#define LT_MIN_BLOCKS_F32 6
+#define LT_MIN_BLOCKS_F32 5
 #endif
 #ifndef LT_MIN_BLOCKS_F64
 #define LT_MIN_BLOCKS_F64 3
+#endif
+#ifndef LT_PHASED
+#define LT_PHASED 16          // lanes waiting for a shadow query that trigger a shadow phase; 0 = no phase alignment
 #endif
 
 template <typename R, int TRAV, int SEM>
@@ -148,6 +154,19 @@ __global__ void __launch_bounds__(LT_BLOCK, sizeof(R) == 4 ? LT_MIN_BLOCKS_F32 :
             bool active = ln.qtype != 0;
             unsigned am = __ballot_sync(full, active);
             if (!am) break;
+            int want = ln.qtype;
+            if (TRAV != LT_TRAV_LBVH && LT_PHASED > 0) {
+                // Phase alignment: an iteration serves EITHER extension OR shadow queries, so the lanes that shade
+                // afterwards run one branch family together (the traversal is the cheap, converged part of an
+                // iteration; the shading branches are the expensive, divergent one).  Lanes holding the other kind of
+                // query sit the iteration out.  A shadow phase runs once LT_PHASED lanes wait for one (or nobody has
+                // an extension ray).  Measured on C2: off 15.5, strict alternation 16.2, threshold 8/12/16/20/24/28:
+                // 16.2/16.3/16.4/16.4/16.2/16.2 Grays/s, with 83 % instead of 99 % of the traversal lanes busy.
+                const unsigned em0 = __ballot_sync(full, ln.qtype == 1), sm0 = __ballot_sync(full, ln.qtype == 2);
+                want = (__popc(sm0) >= LT_PHASED || !em0) ? 2 : 1;
+                active = ln.qtype == want;
+                am = __ballot_sync(full, active);
+            }
             uint32_t it_memo = 0, it_lidx = 0, it_fovf = 0, it_maxf = 0;    // this iteration's per-lane events, reduced below
             if (TRAV == LT_TRAV_LBVH) {
                 if (active && !tracing) {
@@ -180,7 +199,7 @@ __global__ void __launch_bounds__(LT_BLOCK, sizeof(R) == 4 ? LT_MIN_BLOCKS_F32 :
                 (void)anyhit;
                 int stt;
                 R adv_rand0 = (R)0;
-                if (ln.qtype == 1) {
+                if (want == 1) {            // warp-uniform when phases are aligned
                     stt = shade_extension<R, SEM>(P, ln, prim, t, tris, mats, it_lidx, adv_rand0);
                 } else {
                     stt = shade_shadow<R, SEM, LT_LOCAL_FRAMES>(P, ln, frames, gtid, prim >= 0, it_fovf, it_maxf, adv_rand0);

@@ -36,7 +36,8 @@ CONFIGS = {
     "c4": dict(scene="mirror", width=512, height=512, spp=64, max_depth=256, semantics="reference", traversal="compat", scaling="weak"),
     "c4b": dict(scene="medium", width=0, height=0, spp=0, max_depth=256, semantics="implicit", traversal="none", scaling="weak",
                 albedo=0.99, g=0.8, radius=20.0, photons=50_000_000),
-    "c5": dict(scene="lts", width=4096, height=4096, spp=4096, max_depth=8, semantics="reference", traversal="lbvh", scaling="strong"),
+    # NEAREST semantics (true closest hit).  On a 28-triangle scene the all-primitive scan (15.0 Grays/s) beats the LBVH (11.3)
+    "c5": dict(scene="lts", width=4096, height=4096, spp=4096, max_depth=8, semantics="reference", traversal="nearest", scaling="strong"),
 }
 WORKLOAD = dict(CONFIGS["c2"])
 METRIC = "Mrays/s (path segments/s)"

@@ -133,9 +133,12 @@ __global__ void __launch_bounds__(LT_BLOCK, sizeof(R) == 4 ? LT_MIN_BLOCKS_F32 :
         int32_t next = 0;
         if (lane == 0) atomicAdd(cnt + C_PATHS, (unsigned)g_n);            // every started path is tallied exactly once
         for (;;) {
-            // ---- regeneration: idle lanes take the next indices of the granule
+            // ---- regeneration: idle lanes take the next indices of the granule (not ahead of a shadow phase, which
+            // they could not join: they are refilled together before the next extension phase)
+            const bool phased = TRAV != LT_TRAV_LBVH && LT_PHASED > 0;
+            const bool shadow_phase = phased && __popc(__ballot_sync(full, ln.qtype == 2)) >= LT_PHASED;
             bool need = ln.qtype == 0;
-            unsigned m = __ballot_sync(full, need);
+            unsigned m = shadow_phase ? 0u : __ballot_sync(full, need);
             if (m) {
                 int32_t mine = next + __popc(m & ((1u << lane) - 1u));
                 next += __popc(m);
@@ -155,15 +158,14 @@ __global__ void __launch_bounds__(LT_BLOCK, sizeof(R) == 4 ? LT_MIN_BLOCKS_F32 :
             unsigned am = __ballot_sync(full, active);
             if (!am) break;
             int want = ln.qtype;
-            if (TRAV != LT_TRAV_LBVH && LT_PHASED > 0) {
+            if (phased) {
                 // Phase alignment: an iteration serves EITHER extension OR shadow queries, so the lanes that shade
                 // afterwards run one branch family together (the traversal is the cheap, converged part of an
                 // iteration; the shading branches are the expensive, divergent one).  Lanes holding the other kind of
                 // query sit the iteration out.  A shadow phase runs once LT_PHASED lanes wait for one (or nobody has
                 // an extension ray).  Measured on C2: off 15.5, strict alternation 16.2, threshold 8/12/16/20/24/28:
                 // 16.2/16.3/16.4/16.4/16.2/16.2 Grays/s, with 83 % instead of 99 % of the traversal lanes busy.
-                const unsigned em0 = __ballot_sync(full, ln.qtype == 1), sm0 = __ballot_sync(full, ln.qtype == 2);
-                want = (__popc(sm0) >= LT_PHASED || !em0) ? 2 : 1;
+                want = (shadow_phase || !__any_sync(full, ln.qtype == 1)) ? 2 : 1;
                 active = ln.qtype == want;
                 am = __ballot_sync(full, active);
             }

@@ -310,7 +310,9 @@ LT_DEVINL void lbvh_run(unsigned amask, LbvhState<R>& s, int* stack, const LbvhN
                         const TriRec<R>* __restrict__ tris, V3<R> o, V3<R> d, V3<R> inv, R eps, bool anyhit, int skip, Stats& st,
                         int max_steps) {
     // (dropping stale stack entries at pop time — entry distance kept beside the node — was measured:
-    //  fewer node visits but 6-9 % slower overall on both the 28- and the 1 M-triangle scene.)
+    //  fewer node visits but 6-9 % slower overall on both the 28- and the 1 M-triangle scene.
+    //  prefetch.global.L1 of the children while the slab tests run: both children 3x slower, the chosen
+    //  child 1.4x slower, the pushed far child -1.5 %: the loads are latency-bound but L1 requests are not free.)
     for (int step = 0; step < max_steps; ++step) {
         const bool at_node = s.cur >= 0, at_leaf = (s.cur < 0) & (s.cur != LT_LBVH_DONE);
         const unsigned nm = __ballot_sync(amask, at_node), lm = __ballot_sync(amask, at_leaf);

@@ -59,6 +59,9 @@ LT_DEVINL void flush_film_warp(double* film, int32_t pix, double acc[3]) {
 #ifndef LT_MIN_BLOCKS_F32
 #define LT_MIN_BLOCKS_F32 5
 #endif
+#ifndef LT_MIN_BLOCKS_F32_LBVH
+#define LT_MIN_BLOCKS_F32_LBVH 8          // memory-latency bound: C3 probe 5: 2.29, 6: 2.53, 7: 2.64, 8: 2.74, 10: 2.73, 12: 2.72 Grays/s
+#endif
 #ifndef LT_MIN_BLOCKS_F64
 #define LT_MIN_BLOCKS_F64 3
 #endif
@@ -67,7 +70,8 @@ LT_DEVINL void flush_film_warp(double* film, int32_t pix, double acc[3]) {
 #endif
 
 template <typename R, int TRAV, int SEM>
-__global__ void __launch_bounds__(LT_BLOCK, sizeof(R) == 4 ? LT_MIN_BLOCKS_F32 : LT_MIN_BLOCKS_F64) walk_megakernel(const WalkParams<R> P) {
+__global__ void __launch_bounds__(LT_BLOCK, sizeof(R) == 4 ? (TRAV == LT_TRAV_LBVH ? LT_MIN_BLOCKS_F32_LBVH : LT_MIN_BLOCKS_F32) : LT_MIN_BLOCKS_F64)
+walk_megakernel(const WalkParams<R> P) {
     extern __shared__ __align__(16) char smem[];
     const TriRec<R>* tris = P.S.tris;
     const MatRec<R>* mats = P.S.mats;

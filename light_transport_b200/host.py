@@ -24,8 +24,8 @@ TRAVERSAL = {"compat": 0, "nearest": 1, "lbvh": 2}
 SEMANTICS = {"reference": 0, "iterative": 1}
 REAL = {"f32": 0, "f64": 1}
 SCHEDULER = {"megakernel": 0, "wavefront": 1}
-# measured: the megakernel wins in float32, the wavefront scheduler in float64
-AUTO_SCHEDULER = {"f32": "megakernel", "f64": "wavefront"}
+# measured: megakernel 16.2 (f32) / 4.9 (f64) Grays/s, wavefront scheduler 11.4 / 3.9
+AUTO_SCHEDULER = {"f32": "megakernel", "f64": "megakernel"}
 
 PD = C.POINTER(C.c_double)
 PI32 = C.POINTER(C.c_int32)

@@ -94,6 +94,7 @@ static void fill_view(const lt_scene* s, SceneView<R>& v) {
     v.lbvh = s->lbvh_nodes;
     v.n_tris = s->n_tris; v.n_mats = s->n_mats; v.n_lights = s->n_lights;
     v.n_cnodes = s->n_cnodes; v.n_cleaves = s->n_cleaves; v.n_lbvh_nodes = s->n_lbvh_nodes;
+    v.n_cflat = s->n_cflat;
 }
 
 template <typename R> static int build_compat_arrays(lt_scene* s);
@@ -190,6 +191,9 @@ static int build_compat_arrays(lt_scene* s) {
             leaves.push_back(l);
         }
     if (leaves.size() > 64) { set_error("COMPAT traversal supports at most 64 leaves (got %zu)", leaves.size()); return LT_E_INVALID; }
+    int flat = 0;
+    for (auto& l : leaves) { l.flat_base = flat; flat += l.n_prims; }
+    s->n_cflat = flat;
     for (auto& l : leaves)                          // R/src/bvh_new.py:436: visited[leaf_idx] = True on the NODE list
         for (int k = 0; k < l.n_prims; ++k) {
             int p = l.prim_off + k;
@@ -215,6 +219,7 @@ static size_t staged_bytes(const lt_scene* s, int trav, int real) {
     size_t b = al(tri * s->n_tris) + al(mat * s->n_mats);
     if (trav == LT_TRAV_COMPAT) b += al(nod * s->n_cnodes) + al(lef * s->n_cleaves);
     if (trav == LT_TRAV_COMPAT && r == 4) b += al((size_t)((s->n_cleaves + 1) / 2) * 96);   // slab_pairs_bytes
+    if (trav == LT_TRAV_COMPAT) b += 32;                                                     // flattened primitive table
     return b;
 }
 

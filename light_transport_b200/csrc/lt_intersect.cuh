@@ -109,6 +109,16 @@ LT_DEVINL void build_slab_pairs(float* tab, const CompatLeaf<float>* leaves, int
     }
 }
 
+// flattened leaf-order primitive sequence (position -> primitive index), 32 entries, for compat_query's small-scene path
+template <typename R>
+LT_DEVINL void build_flat_prims(uint8_t* tab, const CompatLeaf<R>* leaves, int n_leaves) {
+    for (int li = threadIdx.x; li < n_leaves; li += blockDim.x)
+        for (int i = 0; i < leaves[li].n_prims; ++i)
+            if (leaves[li].flat_base + i < 32) tab[leaves[li].flat_base + i] = (uint8_t)(leaves[li].prim_off + i);
+}
+// the small-scene path needs positions and primitive indices that fit 32-bit masks / bytes
+LT_DEVINL bool compat_small(int n_leaves, int n_cflat, int n_tris) { return n_leaves <= 32 && n_cflat <= 32 && n_tris <= 256; }
+
 LT_DEVINL uint64_t slab_pairs_mask(const float* tab, int n_leaves, V3<float> o, V3<float> inv) {
     const float widen = 1.0f + 2.0f * ((3.0f * 5.9604644775390625e-08f) / (1.0f - 3.0f * 5.9604644775390625e-08f));
     const float4* tx = reinterpret_cast<const float4*>(tab) + (__float_as_uint(inv.x) >> 31);
@@ -163,7 +173,7 @@ LT_DEVINL uint64_t slab_pairs_mask(const float* tab, int n_leaves, V3<float> o, 
 // warp-uniform (`amask` = the lanes running this query together) so the lanes stay in lock step.
 template <typename R>
 LT_DEVINL void compat_query(unsigned amask, const CompatNode<R>* nodes, const CompatLeaf<R>* leaves, int n_leaves, const float* slabtab,
-                            const TriRec<R>* tris, V3<R> o, V3<R> d, R eps, R tlimit, bool anyhit, int skip, int& prim, R& best,
+                            const uint8_t* flatprim, const TriRec<R>* tris, V3<R> o, V3<R> d, R eps, R tlimit, bool anyhit, int skip, int& prim, R& best,
                             Stats& st) {
     V3<R> inv = mk<R>((R)1 / d.x, (R)1 / d.y, (R)1 / d.z);
     prim = -1;
@@ -210,7 +220,44 @@ LT_DEVINL void compat_query(unsigned amask, const CompatNode<R>* nodes, const Co
         }
         st.box_tests += n_leaves;
     }
-    // phase (b) part 2: every lane walks its own hit leaves in list (= descending node) order
+    // phase (b) part 2, small scenes (<= 32 leaves and <= 32 referenced primitives, `flatprim` given): which
+    // leaves a lane processes depends only on the hit mask and the kill masks, not on the triangle tests, so
+    // the leaf walk is pure bit arithmetic (a short per-lane loop, no warp votes) that yields the set of
+    // primitives to test as a mask over the flattened leaf-order primitive sequence.  The tests then run two
+    // per round — the descent leaf's primitives first, then ascending positions: exactly the reference's order,
+    // so "first found wins ties" is kept — with half the rounds and twice the independent arithmetic per round.
+    if (flatprim) {
+        uint32_t lv = (uint32_t)lvis, cur = 0, rest = 0;
+        const uint32_t h = (uint32_t)hm;
+        if (first >= 0) {
+            const CompatLeaf<R>& lf = leaves[first];
+            lv |= (1u << first) | (uint32_t)lf.kill;
+            cur = (0xffffffffu >> (32 - lf.n_prims)) << lf.flat_base;
+        }
+        for (uint32_t cand = h & ~lv; cand; cand = h & ~lv) {
+            const int li = __ffs((int)cand) - 1;
+            const CompatLeaf<R>& lf = leaves[li];
+            lv |= (1u << li) | (uint32_t)lf.kill;
+            rest |= (0xffffffffu >> (32 - lf.n_prims)) << lf.flat_base;
+        }
+        for (;;) {
+            if (anyhit && prim >= 0) { cur = 0; rest = 0; }
+            if (!cur) { cur = rest; rest = 0; }
+            int p1 = -1, p2 = -1;
+            if (cur) { p1 = __ffs((int)cur) - 1; cur &= cur - 1; }
+            if (!cur) { cur = rest; rest = 0; }
+            if (cur) { p2 = __ffs((int)cur) - 1; cur &= cur - 1; }
+            if (!__any_sync(amask, p1 >= 0)) break;
+            const int k1 = p1 >= 0 ? (int)flatprim[p1] : 0, k2 = p2 >= 0 ? (int)flatprim[p2] : 0;
+            R t1, t2;
+            const bool h1 = tri_intersect(tris[k1], o, d, t1), h2 = tri_intersect(tris[k2], o, d, t2);
+            st.tri_tests += (p1 >= 0) + (p2 >= 0);
+            if ((p1 >= 0) & h1 & (k1 != skip) & (eps < t1) & (t1 < best)) { best = t1; prim = k1; }
+            if ((p2 >= 0) & h2 & (k2 != skip) & (eps < t2) & (t2 < best)) { best = t2; prim = k2; }
+        }
+        return;
+    }
+    // phase (b) part 2, general: every lane walks its own hit leaves in list (= descending node) order
     for (;;) {
         int li = first;
         first = -1;

@@ -78,6 +78,7 @@ walk_megakernel(const WalkParams<R> P) {
     const CompatNode<R>* cnodes = P.S.cnodes;
     const CompatLeaf<R>* cleaves = P.S.cleaves;
     const float* slabtab = nullptr;
+    const uint8_t* flatprim = nullptr;
     if (TRAV != LT_TRAV_LBVH) {
         char* cur = smem;
         tris = stage_array(cur, P.S.tris, P.S.n_tris);
@@ -87,9 +88,16 @@ walk_megakernel(const WalkParams<R> P) {
             cleaves = stage_array(cur, P.S.cleaves, P.S.n_cleaves);
         }
         __syncthreads();
-        if (TRAV == LT_TRAV_COMPAT && sizeof(R) == 4) {     // float32: leaf bounds re-laid for slab_pairs_mask
-            build_slab_pairs(reinterpret_cast<float*>(cur), reinterpret_cast<const CompatLeaf<float>*>(cleaves), P.S.n_cleaves);
-            slabtab = reinterpret_cast<const float*>(cur);
+        if (TRAV == LT_TRAV_COMPAT) {
+            if (sizeof(R) == 4) {                           // float32: leaf bounds re-laid for slab_pairs_mask
+                build_slab_pairs(reinterpret_cast<float*>(cur), reinterpret_cast<const CompatLeaf<float>*>(cleaves), P.S.n_cleaves);
+                slabtab = reinterpret_cast<const float*>(cur);
+                cur += (slab_pairs_bytes(P.S.n_cleaves) + 15) / 16 * 16;
+            }
+            if (compat_small(P.S.n_cleaves, P.S.n_cflat, P.S.n_tris)) {
+                build_flat_prims<R>(reinterpret_cast<uint8_t*>(cur), cleaves, P.S.n_cleaves);
+                flatprim = reinterpret_cast<const uint8_t*>(cur);
+            }
             __syncthreads();
         }
     }
@@ -199,7 +207,7 @@ walk_megakernel(const WalkParams<R> P) {
                 R t = ts.best;
                 const bool anyhit = ln.qtype == 2;
                 if (TRAV == LT_TRAV_COMPAT)
-                    compat_query<R>(am, cnodes, cleaves, P.S.n_cleaves, slabtab, tris, ln.o, ln.d, eps, ln.tlimit, anyhit, ln.skip, prim, t, st);
+                    compat_query<R>(am, cnodes, cleaves, P.S.n_cleaves, slabtab, flatprim, tris, ln.o, ln.d, eps, ln.tlimit, anyhit, ln.skip, prim, t, st);
                 else if (TRAV == LT_TRAV_NEAREST)
                     nearest_query<R>(tris, P.S.n_tris, ln.o, ln.d, eps, ln.tlimit, anyhit, ln.skip, prim, t, st);
                 (void)anyhit;
@@ -278,9 +286,16 @@ __global__ void __launch_bounds__(LT_BLOCK) intersect_kernel(const IntersectPara
     Stats st;
     extern __shared__ __align__(16) char smem[];
     const float* slabtab = nullptr;
-    if (TRAV == LT_TRAV_COMPAT && sizeof(R) == 4) {     // dynamic shared memory = slab_pairs_bytes(n_cleaves)
-        build_slab_pairs(reinterpret_cast<float*>(smem), reinterpret_cast<const CompatLeaf<float>*>(P.S.cleaves), P.S.n_cleaves);
-        slabtab = reinterpret_cast<const float*>(smem);
+    const uint8_t* flatprim = nullptr;
+    if (TRAV == LT_TRAV_COMPAT) {                       // dynamic shared memory = 32 + slab_pairs_bytes(n_cleaves)
+        if (compat_small(P.S.n_cleaves, P.S.n_cflat, P.S.n_tris)) {
+            build_flat_prims<R>(reinterpret_cast<uint8_t*>(smem), P.S.cleaves, P.S.n_cleaves);
+            flatprim = reinterpret_cast<const uint8_t*>(smem);
+        }
+        if (sizeof(R) == 4) {
+            build_slab_pairs(reinterpret_cast<float*>(smem + 32), reinterpret_cast<const CompatLeaf<float>*>(P.S.cleaves), P.S.n_cleaves);
+            slabtab = reinterpret_cast<const float*>(smem + 32);
+        }
         __syncthreads();
     }
     const unsigned full = 0xffffffffu;
@@ -297,7 +312,7 @@ __global__ void __launch_bounds__(LT_BLOCK) intersect_kernel(const IntersectPara
             int prim;
             R t;
             if (TRAV == LT_TRAV_COMPAT)
-                compat_query<R>(am, P.S.cnodes, P.S.cleaves, P.S.n_cleaves, slabtab, P.S.tris, o, d, (R)P.eps, Lim<R>::inf(), false, -1, prim, t, st);
+                compat_query<R>(am, P.S.cnodes, P.S.cleaves, P.S.n_cleaves, slabtab, flatprim, P.S.tris, o, d, (R)P.eps, Lim<R>::inf(), false, -1, prim, t, st);
             else if (TRAV == LT_TRAV_NEAREST)
                 nearest_query<R>(P.S.tris, P.S.n_tris, o, d, (R)P.eps, Lim<R>::inf(), false, -1, prim, t, st);
             else

@@ -42,6 +42,8 @@ struct alignas(16) CompatLeaf {
     R bmin[3], bmax[3];
     int32_t prim_off, n_prims;
     uint64_t kill;     // list positions of the leaves this leaf marks visited through its primitive indices (Q9)
+    int32_t flat_base; // position of its first primitive in the flattened (leaf-list order) primitive sequence
+    int32_t pad;
 };
 // BVH2 node for the GPU LBVH: child boxes live in the parent so that one 64-byte fetch decides both
 // children.  ref >= 0: interior node index; ref < 0: leaf holding primitive ~ref.
@@ -63,6 +65,7 @@ struct SceneView {
     const CompatLeaf<R>* cleaves;
     const LbvhNode* lbvh;         // root = node 0
     int32_t n_tris, n_mats, n_lights, n_cnodes, n_cleaves, n_lbvh_nodes;
+    int32_t n_cflat;              // primitives referenced by the COMPAT leaves (flattened sequence length)
 };
 
 }  // namespace lt

@@ -78,6 +78,21 @@ __global__ void __launch_bounds__(WfCfg<R>::NT, WfCfg<R>::MINB) walk_wavefront(c
             cleaves = stage_array(cur, P.S.cleaves, P.S.n_cleaves);
         }
     }
+    // the megakernel's traversal tables (lt_intersect.cuh), built from the global copy: the barrier below publishes them
+    const float* slabtab = nullptr;
+    const uint8_t* flatprim = nullptr;
+    if (TRAV == LT_TRAV_COMPAT) {
+        if (sizeof(R) == 4) {
+            build_slab_pairs(reinterpret_cast<float*>(cur), reinterpret_cast<const CompatLeaf<float>*>(P.S.cleaves), P.S.n_cleaves);
+            slabtab = reinterpret_cast<const float*>(cur);
+            cur += (slab_pairs_bytes(P.S.n_cleaves) + 15) / 16 * 16;
+        }
+        if (compat_small(P.S.n_cleaves, P.S.n_cflat, P.S.n_tris)) {
+            build_flat_prims<R>(reinterpret_cast<uint8_t*>(cur), P.S.cleaves, P.S.n_cleaves);
+            flatprim = reinterpret_cast<const uint8_t*>(cur);
+            cur += 32;
+        }
+    }
     uint32_t* lanes = reinterpret_cast<uint32_t*>(cur);
     cur += (size_t)NWORDS * NT * 4;
     uint16_t* queue = reinterpret_cast<uint16_t*>(cur);          // [class][NT]
@@ -162,7 +177,7 @@ __global__ void __launch_bounds__(WfCfg<R>::NT, WfCfg<R>::MINB) walk_wavefront(c
             R t;
             const bool anyhit = ln.qtype == 2;
             if (TRAV == LT_TRAV_COMPAT)
-                compat_query<R>(am, cnodes, cleaves, P.S.n_cleaves, nullptr, tris, ln.o, ln.d, eps, ln.tlimit, anyhit, ln.skip, prim, t, st);
+                compat_query<R>(am, cnodes, cleaves, P.S.n_cleaves, slabtab, flatprim, tris, ln.o, ln.d, eps, ln.tlimit, anyhit, ln.skip, prim, t, st);
             else if (TRAV == LT_TRAV_NEAREST)
                 nearest_query<R>(tris, P.S.n_tris, ln.o, ln.d, eps, ln.tlimit, anyhit, ln.skip, prim, t, st);
             else

@@ -154,6 +154,17 @@ LT_DEVINL uint64_t slab_pairs_mask(const float* tab, int n_leaves, V3<float> o, 
     return n_leaves >= 64 ? hm : hm & ((1ull << n_leaves) - 1ull);
 }
 
+// per-warp shared-memory scratch of compat_query's pooled triangle tests: LT_POOL_CAP items per lane and pass
+#define LT_POOL_CAP 8
+#define LT_POOL_SLOTS (32 * LT_POOL_CAP)
+template <typename R>
+struct WarpScratch {
+    uint16_t* items = nullptr;    // [LT_POOL_SLOTS]  owner lane << 8 | primitive index
+    R* res = nullptr;             // [LT_POOL_SLOTS]  t of a valid hit, else +inf
+};
+LT_DEVINL float shfl_real(float v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+LT_DEVINL double shfl_real(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
 // ---- COMPAT --------------------------------------------------------------------------------------
 // intersect_bvh keeps a `visited` list over NODES, starts at the root and (a) follows near children
 // while interior bounds are hit, then (b) repeatedly jumps to the LAST unvisited index (its scan has
@@ -174,7 +185,7 @@ LT_DEVINL uint64_t slab_pairs_mask(const float* tab, int n_leaves, V3<float> o, 
 template <typename R>
 LT_DEVINL void compat_query(unsigned amask, const CompatNode<R>* nodes, const CompatLeaf<R>* leaves, int n_leaves, const float* slabtab,
                             const uint8_t* flatprim, const TriRec<R>* tris, V3<R> o, V3<R> d, R eps, R tlimit, bool anyhit, int skip, int& prim, R& best,
-                            Stats& st) {
+                            Stats& st, bool live = true, WarpScratch<R> ws = WarpScratch<R>()) {
     V3<R> inv = mk<R>((R)1 / d.x, (R)1 / d.y, (R)1 / d.z);
     prim = -1;
     best = tlimit;
@@ -182,7 +193,7 @@ LT_DEVINL void compat_query(unsigned amask, const CompatNode<R>* nodes, const Co
     // if its bounds are hit: it is processed before every other leaf).
     int cur = 0, first = -1;
     uint64_t lvis = 0;
-    bool done = false, descending = true;
+    bool done = !live, descending = live;     // a lane without a query of its own only helps with the pooled triangle tests
     while (__any_sync(amask, descending)) {
         if (descending) {
             const CompatNode<R>& nd = nodes[cur];
@@ -239,6 +250,56 @@ LT_DEVINL void compat_query(unsigned amask, const CompatNode<R>* nodes, const Co
             const CompatLeaf<R>& lf = leaves[li];
             lv |= (1u << li) | (uint32_t)lf.kill;
             rest |= (0xffffffffu >> (32 - lf.n_prims)) << lf.flat_base;
+        }
+        if (ws.items && amask == 0xffffffffu) {
+            // Pooled tests: per-lane candidate counts have a long tail (a ray through the cone's overlapping leaf
+            // boxes holds 5-8 candidates while the average is 2), and a warp iterates as long as its worst lane.
+            // So the whole warp — including the lanes that sit this phase out — shares the tests: every lane
+            // appends its (lane, primitive) items to a per-warp list in shared memory at the offset a warp scan
+            // gives it, lane j tests item base+j on the owner's ray (fetched with shuffles), and every owner
+            // folds its own results in list order (strict <: first found still wins ties).
+            const unsigned full = 0xffffffffu;
+            const int lane = threadIdx.x & 31;
+            for (;;) {
+                if (anyhit && prim >= 0) { cur = 0; rest = 0; }
+                const int c = min(LT_POOL_CAP, __popc(cur) + __popc(rest));
+                int incl = c;
+#pragma unroll
+                for (int dlt = 1; dlt < 32; dlt <<= 1) {
+                    const int v = __shfl_up_sync(full, incl, dlt);
+                    if (lane >= dlt) incl += v;
+                }
+                const int total = __shfl_sync(full, incl, 31);
+                if (total == 0) break;
+                const int off = incl - c;
+                for (int i = 0; i < c; ++i) {
+                    if (!cur) { cur = rest; rest = 0; }
+                    const int p = __ffs((int)cur) - 1;
+                    cur &= cur - 1;
+                    ws.items[off + i] = (uint16_t)((lane << 8) | flatprim[p]);
+                }
+                __syncwarp();
+                for (int base = 0; base < total; base += 32) {
+                    const int slot = base + lane;
+                    const bool has = slot < total;
+                    const int item = has ? (int)ws.items[slot] : (lane << 8);
+                    const int owner = item >> 8, k = item & 255;
+                    const V3<R> oo = mk<R>(shfl_real(o.x, owner), shfl_real(o.y, owner), shfl_real(o.z, owner));
+                    const V3<R> dd = mk<R>(shfl_real(d.x, owner), shfl_real(d.y, owner), shfl_real(d.z, owner));
+                    const int sk = __shfl_sync(full, skip, owner);
+                    R t;
+                    const bool hh = tri_intersect(tris[k], oo, dd, t);
+                    if (has) ws.res[slot] = (hh & (k != sk) & (eps < t)) ? t : Lim<R>::inf();
+                }
+                st.tri_tests += c;
+                __syncwarp();
+                for (int i = 0; i < c; ++i) {
+                    const R t = ws.res[off + i];
+                    if (t < best) { best = t; prim = (int)(ws.items[off + i] & 255); }
+                }
+                __syncwarp();
+            }
+            return;
         }
         for (;;) {
             if (anyhit && prim >= 0) { cur = 0; rest = 0; }

@@ -65,6 +65,12 @@ LT_DEVINL void flush_film_warp(double* film, int32_t pix, double acc[3]) {
 #ifndef LT_MIN_BLOCKS_F64
 #define LT_MIN_BLOCKS_F64 3
 #endif
+// COMPAT: triangle tests of a warp pooled across its lanes (lt_intersect.cuh).  Measured on C2: float64 5.36 -> 6.03
+// Grays/s (the test is expensive at the fp64 rate, balancing pays), float32 18.0 -> 16.9 (list + scan + two warp
+// syncs cost more than the idle lanes they fill): on for float64 only.
+#ifndef LT_POOLED
+#define LT_POOLED (sizeof(R) == 8)
+#endif
 #ifndef LT_PHASED
 #define LT_PHASED 16          // lanes waiting for a shadow query that trigger a shadow phase; 0 = no phase alignment
 #endif
@@ -134,6 +140,11 @@ walk_megakernel(const WalkParams<R> P) {
     __syncwarp();
     double acc[3] = {0, 0, 0};
     int32_t acc_pix = -1;
+    WarpScratch<R> ws;
+    constexpr bool pooled = TRAV == LT_TRAV_COMPAT && LT_POOLED;
+    __shared__ uint16_t pool_items[pooled ? LT_BLOCK / 32 : 1][pooled ? LT_POOL_SLOTS : 1];
+    __shared__ R pool_res[pooled ? LT_BLOCK / 32 : 1][pooled ? LT_POOL_SLOTS : 1];
+    if (pooled && flatprim) { ws.items = pool_items[threadIdx.x >> 5]; ws.res = pool_res[threadIdx.x >> 5]; }
 
     for (int64_t g = gwarp; g * ppw < P.total_paths; g += nwarps) {
         // the granule: indices [g*ppw, g*ppw + g_n); (pixel, sample) of its first index from one 64-bit division,
@@ -201,14 +212,21 @@ walk_megakernel(const WalkParams<R> P) {
                     if (sm) atomicAdd(cnt + C_SHADOW, (unsigned)__popc(sm));
                 }
             }
+            // ---- the one ray query of this iteration
+            int prim = ts.prim;
+            R t = ts.best;
+            if (TRAV == LT_TRAV_COMPAT) {
+                if (LT_POOLED) {
+                    // the whole warp enters: lanes without a query of their own help with the pooled triangle tests
+                    compat_query<R>(full, cnodes, cleaves, P.S.n_cleaves, slabtab, flatprim, tris, ln.o, ln.d, eps, ln.tlimit, ln.qtype == 2, ln.skip,
+                                    prim, t, st, active, ws);
+                } else if (active) {
+                    compat_query<R>(am, cnodes, cleaves, P.S.n_cleaves, slabtab, flatprim, tris, ln.o, ln.d, eps, ln.tlimit, ln.qtype == 2, ln.skip, prim, t, st);
+                }
+            }
             if (active) {
-                // ---- the one ray query of this iteration
-                int prim = ts.prim;
-                R t = ts.best;
                 const bool anyhit = ln.qtype == 2;
-                if (TRAV == LT_TRAV_COMPAT)
-                    compat_query<R>(am, cnodes, cleaves, P.S.n_cleaves, slabtab, flatprim, tris, ln.o, ln.d, eps, ln.tlimit, anyhit, ln.skip, prim, t, st);
-                else if (TRAV == LT_TRAV_NEAREST)
+                if (TRAV == LT_TRAV_NEAREST)
                     nearest_query<R>(tris, P.S.n_tris, ln.o, ln.d, eps, ln.tlimit, anyhit, ln.skip, prim, t, st);
                 (void)anyhit;
                 int stt;

@@ -222,7 +222,9 @@ def test_wavefront_replay_f64_matches_reference(R_lts, R_mirror, scene_file, pat
     assert np.allclose(film, samples.sum(axis=2), rtol=1e-12, atol=1e-12)
     _, s_mk, c_mk = R.render(scheduler="megakernel", **kw)
     assert np.array_equal(samples, s_mk)                      # identical per-path results, bit for bit
-    for k in ("rays_ext", "rays_shadow", "max_frames", "tri_tests"):
+    # (tri_tests is not compared: a shadow query stops testing at its first hit, and how many tests are already in
+    #  flight at that point differs between the schedulers — two per round, or a pooled warp-wide round)
+    for k in ("rays_ext", "rays_shadow", "max_frames"):
         assert cnt[k] == c_mk[k], k
 
 

@@ -218,7 +218,7 @@ static size_t staged_bytes(const lt_scene* s, int trav, int real) {
     if (trav == LT_TRAV_LBVH) return 0;
     size_t b = al(tri * s->n_tris) + al(mat * s->n_mats);
     if (trav == LT_TRAV_COMPAT) b += al(nod * s->n_cnodes) + al(lef * s->n_cleaves);
-    if (trav == LT_TRAV_COMPAT && r == 4) b += al((size_t)((s->n_cleaves + 1) / 2) * 96);   // slab_pairs_bytes
+    if (trav == LT_TRAV_COMPAT && r == 4) b += al((size_t)((s->n_cleaves + 1) / 2) * 96) + (8 * 4 * 12 * 4 + 32);   // slab_pairs_bytes + LT_CHAIN_BYTES
     if (trav == LT_TRAV_COMPAT) b += 32;                                                     // flattened primitive table
     return b;
 }

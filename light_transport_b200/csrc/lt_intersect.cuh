@@ -154,6 +154,75 @@ LT_DEVINL uint64_t slab_pairs_mask(const float* tab, int n_leaves, V3<float> o, 
     return n_leaves >= 64 ? hm : hm & ((1ull << n_leaves) - 1ull);
 }
 
+// ---- float32 initial descent without a dependent chain ---------------------------------------------------
+// intersect_bvh's initial descent follows the NEAR child while interior bounds are hit, and "near" is decided by
+// the sign of the direction component on the node's split axis — so the chain of nodes a ray can visit is a
+// function of its direction OCTANT alone.  build_chains() walks the eight chains once per CTA and lays their
+// interior boxes out like the leaf pairs (near/far already selected for the octant); a ray then evaluates its
+// whole chain branch-free, two nodes per step, and the descent's outcome is bit arithmetic on the hit mask:
+// root missed -> nothing is visited; all interior boxes hit -> the chain's leaf is the first leaf processed (its
+// own bounds test is the leaf's bit of the hit mask); otherwise the descent stopped at the first missed node.
+// Replaces ~6 dependent {load node, slab test, branch} levels per ray.  Chains longer than 8 interior nodes (or a
+// root that is a leaf) keep the generic loop.
+#define LT_CHAIN_PAIRS 4
+#define LT_CHAIN_FLOATS (8 * LT_CHAIN_PAIRS * 12)
+#define LT_CHAIN_BYTES (LT_CHAIN_FLOATS * 4 + 32)
+struct ChainTab {
+    const float* tab = nullptr;       // [octant][pair][axis]{near_a, near_b, far_a, far_b}
+    const uint16_t* meta = nullptr;   // [octant] interior nodes on the chain | leaf list position << 8; 0xffff = generic descent
+};
+
+LT_DEVINL void build_chains(float* tab, uint16_t* meta, const CompatNode<float>* nodes) {
+    if (threadIdx.x < 8) {
+        const int oct = threadIdx.x;
+        float* t = tab + oct * LT_CHAIN_PAIRS * 12;
+        int cur = 0, j = 0;
+        bool ok = true;
+        while (nodes[cur].n_prims == 0) {
+            if (j >= 2 * LT_CHAIN_PAIRS) { ok = false; break; }
+            for (int s2 = j; s2 < 2 * LT_CHAIN_PAIRS; ++s2)          // this node, and padding for the slots behind it
+                for (int k = 0; k < 3; ++k) {
+                    const bool neg = (oct >> k) & 1;
+                    float* b = t + (s2 >> 1) * 12 + k * 4 + (s2 & 1);
+                    b[0] = neg ? nodes[cur].bmax[k] : nodes[cur].bmin[k];
+                    b[2] = neg ? nodes[cur].bmin[k] : nodes[cur].bmax[k];
+                }
+            cur = ((oct >> nodes[cur].axis) & 1) ? nodes[cur].second : cur + 1;
+            ++j;
+        }
+        meta[oct] = (ok && j >= 1) ? (uint16_t)(j | (nodes[cur].axis << 8)) : (uint16_t)0xffffu;
+        // meta[8]: pairs any chain needs (the evaluation loop is warp-uniform)
+        const unsigned need = (ok && j >= 1) ? (unsigned)((j + 1) >> 1) : 0u;
+        unsigned mx = need;
+        for (int d = 4; d > 0; d >>= 1) mx = max(mx, __shfl_xor_sync(0xffu, mx, d));
+        if (oct == 0) meta[8] = (uint16_t)mx;
+    }
+}
+
+LT_DEVINL uint32_t chain_mask(const float* tab_oct, int n_pairs, V3<float> o, V3<float> inv) {
+    const float widen = 1.0f + 2.0f * ((3.0f * 5.9604644775390625e-08f) / (1.0f - 3.0f * 5.9604644775390625e-08f));
+    const float4* t4 = reinterpret_cast<const float4*>(tab_oct);
+    const float2 nox = make_float2(-o.x, -o.x), noy = make_float2(-o.y, -o.y), noz = make_float2(-o.z, -o.z);
+    const float2 ivx = make_float2(inv.x, inv.x), ivy = make_float2(inv.y, inv.y), ivz = make_float2(inv.z, inv.z);
+    const float2 w2 = make_float2(widen, widen);
+    uint32_t m = 0;
+    for (int p = 0; p < n_pairs; ++p) {
+        const float4 X = t4[3 * p], Y = t4[3 * p + 1], Z = t4[3 * p + 2];
+        const float2 nx = __fmul2_rn(__fadd2_rn(make_float2(X.x, X.y), nox), ivx);
+        const float2 fx = __fmul2_rn(__fadd2_rn(make_float2(X.z, X.w), nox), ivx);
+        const float2 ny = __fmul2_rn(__fadd2_rn(make_float2(Y.x, Y.y), noy), ivy);
+        const float2 fy = __fmul2_rn(__fadd2_rn(make_float2(Y.z, Y.w), noy), ivy);
+        const float2 nz = __fmul2_rn(__fadd2_rn(make_float2(Z.x, Z.y), noz), ivz);
+        const float2 fz = __fmul2_rn(__fadd2_rn(make_float2(Z.z, Z.w), noz), ivz);
+        const float t0a = fmaxf(fmaxf(nx.x, ny.x), fmaxf(nz.x, 0.0f));
+        const float t0b = fmaxf(fmaxf(nx.y, ny.y), fmaxf(nz.y, 0.0f));
+        const float2 t1 = __fmul2_rn(make_float2(fminf(fminf(fx.x, fy.x), fz.x), fminf(fminf(fx.y, fy.y), fz.y)), w2);
+        if (!(t0a > t1.x)) m |= 1u << (2 * p);
+        if (!(t0b > t1.y)) m |= 2u << (2 * p);
+    }
+    return m;
+}
+
 // per-warp shared-memory scratch of compat_query's pooled triangle tests: LT_POOL_CAP items per lane and pass
 #define LT_POOL_CAP 8
 #define LT_POOL_SLOTS (32 * LT_POOL_CAP)
@@ -185,7 +254,7 @@ LT_DEVINL double shfl_real(double v, int src) { return __shfl_sync(0xffffffffu, 
 template <typename R>
 LT_DEVINL void compat_query(unsigned amask, const CompatNode<R>* nodes, const CompatLeaf<R>* leaves, int n_leaves, const float* slabtab,
                             const uint8_t* flatprim, const TriRec<R>* tris, V3<R> o, V3<R> d, R eps, R tlimit, bool anyhit, int skip, int& prim, R& best,
-                            Stats& st, bool live = true, WarpScratch<R> ws = WarpScratch<R>()) {
+                            Stats& st, bool live = true, WarpScratch<R> ws = WarpScratch<R>(), ChainTab chain = ChainTab()) {
     V3<R> inv = mk<R>((R)1 / d.x, (R)1 / d.y, (R)1 / d.z);
     prim = -1;
     best = tlimit;
@@ -194,6 +263,22 @@ LT_DEVINL void compat_query(unsigned amask, const CompatNode<R>* nodes, const Co
     int cur = 0, first = -1;
     uint64_t lvis = 0;
     bool done = !live, descending = live;     // a lane without a query of its own only helps with the pooled triangle tests
+    int chain_leaf = -1;
+    if (sizeof(R) == 4 && chain.tab && live) {            // float32: the descent as one branch-free chain evaluation
+        const V3<float> of = mk<float>((float)o.x, (float)o.y, (float)o.z), invf = mk<float>((float)inv.x, (float)inv.y, (float)inv.z);
+        const unsigned oct = (__float_as_uint(invf.x) >> 31) | ((__float_as_uint(invf.y) >> 31) << 1) | ((__float_as_uint(invf.z) >> 31) << 2);
+        const unsigned meta = chain.meta[oct];
+        if (meta != 0xffffu) {
+            const int n_int = (int)(meta & 255u);
+            const uint32_t allm = (1u << n_int) - 1u;
+            const uint32_t cm = chain_mask(chain.tab + oct * LT_CHAIN_PAIRS * 12, (int)chain.meta[8], of, invf) & allm;
+            const bool all = cm == allm;
+            st.box_tests += all ? n_int + 1 : __ffs((int)~cm);
+            done = !(cm & 1u);
+            if (all) { chain_leaf = (int)(meta >> 8); lvis |= 1ull << chain_leaf; }
+            descending = false;
+        }
+    }
     while (__any_sync(amask, descending)) {
         if (descending) {
             const CompatNode<R>& nd = nodes[cur];
@@ -231,6 +316,7 @@ LT_DEVINL void compat_query(unsigned amask, const CompatNode<R>* nodes, const Co
         }
         st.box_tests += n_leaves;
     }
+    if (chain_leaf >= 0) first = ((hm >> chain_leaf) & 1ull) ? chain_leaf : -1;
     // phase (b) part 2, small scenes (<= 32 leaves and <= 32 referenced primitives, `flatprim` given): which
     // leaves a lane processes depends only on the hit mask and the kill masks, not on the triangle tests, so
     // the leaf walk is pure bit arithmetic (a short per-lane loop, no warp votes) that yields the set of

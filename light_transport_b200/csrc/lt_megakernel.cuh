@@ -85,6 +85,7 @@ walk_megakernel(const WalkParams<R> P) {
     const CompatLeaf<R>* cleaves = P.S.cleaves;
     const float* slabtab = nullptr;
     const uint8_t* flatprim = nullptr;
+    ChainTab chain;
     if (TRAV != LT_TRAV_LBVH) {
         char* cur = smem;
         tris = stage_array(cur, P.S.tris, P.S.n_tris);
@@ -103,6 +104,13 @@ walk_megakernel(const WalkParams<R> P) {
             if (compat_small(P.S.n_cleaves, P.S.n_cflat, P.S.n_tris)) {
                 build_flat_prims<R>(reinterpret_cast<uint8_t*>(cur), cleaves, P.S.n_cleaves);
                 flatprim = reinterpret_cast<const uint8_t*>(cur);
+            }
+            cur += 32;
+            if (sizeof(R) == 4) {                           // float32: per-octant descent chains
+                build_chains(reinterpret_cast<float*>(cur), reinterpret_cast<uint16_t*>(cur + LT_CHAIN_FLOATS * 4),
+                             reinterpret_cast<const CompatNode<float>*>(cnodes));
+                chain.tab = reinterpret_cast<const float*>(cur);
+                chain.meta = reinterpret_cast<const uint16_t*>(cur + LT_CHAIN_FLOATS * 4);
             }
             __syncthreads();
         }
@@ -219,9 +227,10 @@ walk_megakernel(const WalkParams<R> P) {
                 if (LT_POOLED) {
                     // the whole warp enters: lanes without a query of their own help with the pooled triangle tests
                     compat_query<R>(full, cnodes, cleaves, P.S.n_cleaves, slabtab, flatprim, tris, ln.o, ln.d, eps, ln.tlimit, ln.qtype == 2, ln.skip,
-                                    prim, t, st, active, ws);
+                                    prim, t, st, active, ws, chain);
                 } else if (active) {
-                    compat_query<R>(am, cnodes, cleaves, P.S.n_cleaves, slabtab, flatprim, tris, ln.o, ln.d, eps, ln.tlimit, ln.qtype == 2, ln.skip, prim, t, st);
+                    compat_query<R>(am, cnodes, cleaves, P.S.n_cleaves, slabtab, flatprim, tris, ln.o, ln.d, eps, ln.tlimit, ln.qtype == 2, ln.skip, prim, t, st,
+                                    true, ws, chain);
                 }
             }
             if (active) {
@@ -305,6 +314,7 @@ __global__ void __launch_bounds__(LT_BLOCK) intersect_kernel(const IntersectPara
     extern __shared__ __align__(16) char smem[];
     const float* slabtab = nullptr;
     const uint8_t* flatprim = nullptr;
+    ChainTab chain;
     if (TRAV == LT_TRAV_COMPAT) {                       // dynamic shared memory = 32 + slab_pairs_bytes(n_cleaves)
         if (compat_small(P.S.n_cleaves, P.S.n_cflat, P.S.n_tris)) {
             build_flat_prims<R>(reinterpret_cast<uint8_t*>(smem), P.S.cleaves, P.S.n_cleaves);
@@ -313,6 +323,10 @@ __global__ void __launch_bounds__(LT_BLOCK) intersect_kernel(const IntersectPara
         if (sizeof(R) == 4) {
             build_slab_pairs(reinterpret_cast<float*>(smem + 32), reinterpret_cast<const CompatLeaf<float>*>(P.S.cleaves), P.S.n_cleaves);
             slabtab = reinterpret_cast<const float*>(smem + 32);
+            char* c2 = smem + 32 + (slab_pairs_bytes(P.S.n_cleaves) + 15) / 16 * 16;
+            build_chains(reinterpret_cast<float*>(c2), reinterpret_cast<uint16_t*>(c2 + LT_CHAIN_FLOATS * 4), reinterpret_cast<const CompatNode<float>*>(P.S.cnodes));
+            chain.tab = reinterpret_cast<const float*>(c2);
+            chain.meta = reinterpret_cast<const uint16_t*>(c2 + LT_CHAIN_FLOATS * 4);
         }
         __syncthreads();
     }
@@ -330,7 +344,8 @@ __global__ void __launch_bounds__(LT_BLOCK) intersect_kernel(const IntersectPara
             int prim;
             R t;
             if (TRAV == LT_TRAV_COMPAT)
-                compat_query<R>(am, P.S.cnodes, P.S.cleaves, P.S.n_cleaves, slabtab, flatprim, P.S.tris, o, d, (R)P.eps, Lim<R>::inf(), false, -1, prim, t, st);
+                compat_query<R>(am, P.S.cnodes, P.S.cleaves, P.S.n_cleaves, slabtab, flatprim, P.S.tris, o, d, (R)P.eps, Lim<R>::inf(), false, -1, prim, t, st, true,
+                                WarpScratch<R>(), chain);
             else if (TRAV == LT_TRAV_NEAREST)
                 nearest_query<R>(P.S.tris, P.S.n_tris, o, d, (R)P.eps, Lim<R>::inf(), false, -1, prim, t, st);
             else

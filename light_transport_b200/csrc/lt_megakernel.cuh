@@ -71,6 +71,9 @@ LT_DEVINL void flush_film_warp(double* film, int32_t pix, double acc[3]) {
 #ifndef LT_POOLED
 #define LT_POOLED (sizeof(R) == 8)
 #endif
+#ifndef LT_EARLY_ROOT
+#define LT_EARLY_ROOT 1
+#endif
 #ifndef LT_PHASED
 #define LT_PHASED 16          // lanes waiting for a shadow query that trigger a shadow phase; 0 = no phase alignment
 #endif
@@ -200,7 +203,7 @@ walk_megakernel(const WalkParams<R> P) {
                 active = ln.qtype == want;
                 am = __ballot_sync(full, active);
             }
-            uint32_t it_memo = 0, it_lidx = 0, it_fovf = 0, it_maxf = 0;    // this iteration's per-lane events, reduced below
+            uint32_t it_memo = 0, it_lidx = 0, it_fovf = 0, it_maxf = 0, it_early = 0;    // this iteration's per-lane events, reduced below
             if (TRAV == LT_TRAV_LBVH) {
                 if (active && !tracing) {
                     lbvh_begin<R>(ts, P.S.n_tris, ln.tlimit, true);
@@ -251,6 +254,19 @@ walk_megakernel(const WalkParams<R> P) {
                     ln.qtype = 1;
                     ln.tlimit = Lim<R>::inf();
                 }
+                // COMPAT: a new extension ray that misses the ROOT bounds is a miss (the descent ends at once and no leaf is
+                // visited), and a miss ends the whole path (see advance()).  A quarter of the walk's rays on the
+                // Cornell scene are like that (Q3 sends them through a wall).  Decided here, the lane is refilled
+                // ahead of the next extension phase instead of idling through one; the ray is counted as traced.
+                if (TRAV == LT_TRAV_COMPAT && LT_EARLY_ROOT && alive && ln.qtype == 1) {
+                    const V3<R> inv = mk<R>((R)1 / ln.d.x, (R)1 / ln.d.y, (R)1 / ln.d.z);
+                    if (!slab(cnodes[0].bmin, cnodes[0].bmax, ln.o, inv)) {
+                        st.box_tests++;
+                        it_early++;
+                        ln.memo |= 1;
+                        alive = advance<R, SEM, LT_LOCAL_FRAMES>(P, ln, frames, gtid, true, adv_rand0, it_memo);
+                    }
+                }
                 if (!alive) {
                     // ---- tally (R/src/path_tracing.py:297-298)
                     acc[0] += (double)ln.L.x; acc[1] += (double)ln.L.y; acc[2] += (double)ln.L.z;
@@ -268,6 +284,10 @@ walk_megakernel(const WalkParams<R> P) {
                     if (memo) atomicAdd(cnt + C_MEMO, memo);
                     if (maxf) atomicMax(cnt + C_MAXF, maxf);
                 }
+            }
+            if (TRAV == LT_TRAV_COMPAT && LT_EARLY_ROOT) {
+                const unsigned early = __reduce_add_sync(full, it_early);
+                if (lane == 0 && early) atomicAdd(cnt + C_EXT, early);
             }
             if (__any_sync(full, (it_lidx | it_fovf) != 0)) {
                 const unsigned a = __reduce_add_sync(full, it_lidx), b = __reduce_add_sync(full, it_fovf);

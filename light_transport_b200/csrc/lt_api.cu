@@ -95,6 +95,7 @@ static void fill_view(const lt_scene* s, SceneView<R>& v) {
     v.n_tris = s->n_tris; v.n_mats = s->n_mats; v.n_lights = s->n_lights;
     v.n_cnodes = s->n_cnodes; v.n_cleaves = s->n_cleaves; v.n_lbvh_nodes = s->n_lbvh_nodes;
     v.n_cflat = s->n_cflat;
+    for (int c = 0; c < 3; ++c) { v.bbox_min[c] = s->bbox_min[c]; v.bbox_max[c] = s->bbox_max[c]; }
 }
 
 template <typename R> static int build_compat_arrays(lt_scene* s);
@@ -553,6 +554,18 @@ int lt_scene_create(lt_ctx* ctx, const lt_scene_desc* d, lt_scene** out) {
     s->ctx = ctx;
     s->n_tris = d->n_tris; s->n_mats = d->n_mats; s->n_lights = d->n_lights;
     const size_t n3 = 3 * (size_t)d->n_tris;
+    // scene bounds for the all-primitive scan's early miss (it only makes sense for small scenes)
+    for (int c = 0; c < 3; ++c) { s->bbox_min[c] = -INFINITY; s->bbox_max[c] = INFINITY; }
+    if (d->n_tris <= 65536 && d->n_tris > 0) {
+        for (int c = 0; c < 3; ++c) { s->bbox_min[c] = INFINITY; s->bbox_max[c] = -INFINITY; }
+        const double* vs[3] = {d->tri_v0, d->tri_v1, d->tri_v2};
+        for (int a = 0; a < 3; ++a)
+            for (size_t i = 0; i < n3; ++i) {
+                const int c = (int)(i % 3);
+                s->bbox_min[c] = std::min(s->bbox_min[c], vs[a][i]);
+                s->bbox_max[c] = std::max(s->bbox_max[c], vs[a][i]);
+            }
+    }
     cudaStream_t st = ctx->stream;
     int rc;
     if ((rc = upload_raw(&s->d_v0, d->tri_v0, n3, st)) || (rc = upload_raw(&s->d_v1, d->tri_v1, n3, st)) ||

@@ -49,6 +49,7 @@ struct lt_scene {
     lt_ctx* ctx = nullptr;
     int n_tris = 0, n_mats = 0, n_lights = 0;
     int n_cnodes = 0, n_cleaves = 0, n_cflat = 0;
+    double bbox_min[3], bbox_max[3];   // bounds of all vertices (computed for small scenes, else +-inf)
     int n_lbvh_nodes = 0;
     lt::SceneArrays<float> f32;
     lt::SceneArrays<double> f64;

@@ -258,10 +258,17 @@ walk_megakernel(const WalkParams<R> P) {
                 // visited), and a miss ends the whole path (see advance()).  A quarter of the walk's rays on the
                 // Cornell scene are like that (Q3 sends them through a wall).  Decided here, the lane is refilled
                 // ahead of the next extension phase instead of idling through one; the ray is counted as traced.
-                if (TRAV == LT_TRAV_COMPAT && LT_EARLY_ROOT && alive && ln.qtype == 1) {
+                // NEAREST: the same with the bounds of all vertices — a ray that misses them (widened like every slab
+                // test, so conservatively) cannot hit a triangle.
+                if ((TRAV == LT_TRAV_COMPAT || TRAV == LT_TRAV_NEAREST) && LT_EARLY_ROOT && alive && ln.qtype == 1) {
                     const V3<R> inv = mk<R>((R)1 / ln.d.x, (R)1 / ln.d.y, (R)1 / ln.d.z);
-                    if (!slab(cnodes[0].bmin, cnodes[0].bmax, ln.o, inv)) {
-                        st.box_tests++;
+                    R bmin[3], bmax[3];
+                    for (int c = 0; c < 3; ++c) {
+                        bmin[c] = TRAV == LT_TRAV_COMPAT ? cnodes[0].bmin[c] : (R)P.S.bbox_min[c];
+                        bmax[c] = TRAV == LT_TRAV_COMPAT ? cnodes[0].bmax[c] : (R)P.S.bbox_max[c];
+                    }
+                    if (!slab(bmin, bmax, ln.o, inv)) {
+                        if (TRAV == LT_TRAV_COMPAT) st.box_tests++;
                         it_early++;
                         ln.memo |= 1;
                         alive = advance<R, SEM, LT_LOCAL_FRAMES>(P, ln, frames, gtid, true, adv_rand0, it_memo);
@@ -285,7 +292,7 @@ walk_megakernel(const WalkParams<R> P) {
                     if (maxf) atomicMax(cnt + C_MAXF, maxf);
                 }
             }
-            if (TRAV == LT_TRAV_COMPAT && LT_EARLY_ROOT) {
+            if ((TRAV == LT_TRAV_COMPAT || TRAV == LT_TRAV_NEAREST) && LT_EARLY_ROOT) {
                 const unsigned early = __reduce_add_sync(full, it_early);
                 if (lane == 0 && early) atomicAdd(cnt + C_EXT, early);
             }

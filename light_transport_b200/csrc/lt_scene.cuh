@@ -66,6 +66,7 @@ struct SceneView {
     const LbvhNode* lbvh;         // root = node 0
     int32_t n_tris, n_mats, n_lights, n_cnodes, n_cleaves, n_lbvh_nodes;
     int32_t n_cflat;              // primitives referenced by the COMPAT leaves (flattened sequence length)
+    double bbox_min[3], bbox_max[3];   // bounds of all vertices (small scenes; +-inf when not computed): NEAREST early miss
 };
 
 }  // namespace lt

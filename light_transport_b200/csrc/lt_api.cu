@@ -91,6 +91,8 @@ static void fill_view(const lt_scene* s, SceneView<R>& v) {
     const SceneArrays<R>& a = s->arrays<R>();
     v.tris = a.tris; v.mats = a.mats; v.lights = a.lights; v.cnodes = a.cnodes;
     v.cleaves = a.cleaves;
+    v.nleaves = a.nleaves;
+    v.n_nleaves = a.nleaves ? s->n_nleaves : 0;
     v.lbvh = s->lbvh_nodes;
     v.n_tris = s->n_tris; v.n_mats = s->n_mats; v.n_lights = s->n_lights;
     v.n_cnodes = s->n_cnodes; v.n_cleaves = s->n_cleaves; v.n_lbvh_nodes = s->n_lbvh_nodes;
@@ -166,6 +168,28 @@ static int ensure_arrays(lt_scene* s) {
     if ((rc = upload(&a.mats, mats))) return rc;
     if ((rc = upload(&a.lights, lights))) return rc;
     if (s->h_nodes.n_nodes > 0 && (rc = build_compat_arrays<R>(s))) return rc;
+    if (!s->h_small_v.empty()) {
+        // NEAREST on a small scene: bounds of every triangle, so the all-primitive scan can cull like COMPAT does
+        // (lt_intersect.cuh).  float32 bounds are rounded OUTWARDS from the float64 vertices: culling must stay conservative.
+        std::vector<CompatLeaf<R>> nl(n);
+        for (int i = 0; i < n; ++i) {
+            CompatLeaf<R>& l = nl[i];
+            memset(&l, 0, sizeof l);
+            for (int c = 0; c < 3; ++c) {
+                double lo = INFINITY, hi = -INFINITY;
+                for (int v = 0; v < 3; ++v) { const double x = s->h_small_v[((size_t)i * 3 + v) * 3 + c]; lo = std::min(lo, x); hi = std::max(hi, x); }
+                R rlo = (R)lo, rhi = (R)hi;
+                if (sizeof(R) == 4) {
+                    if ((double)rlo > lo) rlo = (R)nextafterf((float)rlo, -INFINITY);
+                    if ((double)rhi < hi) rhi = (R)nextafterf((float)rhi, INFINITY);
+                }
+                l.bmin[c] = rlo; l.bmax[c] = rhi;
+            }
+            l.prim_off = i; l.n_prims = 1; l.kill = 0; l.flat_base = i;
+        }
+        if ((rc = upload(&a.nleaves, nl))) return rc;
+        s->n_nleaves = n;
+    }
     LT_CUDA_OK(cudaStreamSynchronize(st));
     return LT_OK;
 }
@@ -221,6 +245,8 @@ static size_t staged_bytes(const lt_scene* s, int trav, int real) {
     if (trav == LT_TRAV_COMPAT) b += al(nod * s->n_cnodes) + al(lef * s->n_cleaves);
     if (trav == LT_TRAV_COMPAT && r == 4) b += al((size_t)((s->n_cleaves + 1) / 2) * 96) + (8 * 4 * 12 * 4 + 32);   // slab_pairs_bytes + LT_CHAIN_BYTES
     if (trav == LT_TRAV_COMPAT) b += 32;                                                     // flattened primitive table
+    if (trav == LT_TRAV_NEAREST && s->n_nleaves > 0)                                          // per-triangle bounds + the same tables
+        b += al(lef * s->n_nleaves) + (r == 4 ? al((size_t)((s->n_nleaves + 1) / 2) * 96) : 0) + 32;
     return b;
 }
 
@@ -565,6 +591,13 @@ int lt_scene_create(lt_ctx* ctx, const lt_scene_desc* d, lt_scene** out) {
                 s->bbox_min[c] = std::min(s->bbox_min[c], vs[a][i]);
                 s->bbox_max[c] = std::max(s->bbox_max[c], vs[a][i]);
             }
+    }
+    if (d->n_tris <= LT_NEAREST_BOXES) {
+        s->h_small_v.resize((size_t)d->n_tris * 9);
+        const double* vs[3] = {d->tri_v0, d->tri_v1, d->tri_v2};
+        for (int i = 0; i < d->n_tris; ++i)
+            for (int v = 0; v < 3; ++v)
+                for (int c = 0; c < 3; ++c) s->h_small_v[((size_t)i * 3 + v) * 3 + c] = vs[v][3 * (size_t)i + c];
     }
     cudaStream_t st = ctx->stream;
     int rc;

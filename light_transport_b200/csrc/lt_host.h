@@ -13,13 +13,15 @@ struct SceneArrays {
     LightRec<R>* lights = nullptr;
     CompatNode<R>* cnodes = nullptr;
     CompatLeaf<R>* cleaves = nullptr;   // leaves in descending node order
+    CompatLeaf<R>* nleaves = nullptr;   // NEAREST on small scenes: one bounds record per triangle, in primitive order
     void release() {
         if (tris) cudaFree(tris);
         if (mats) cudaFree(mats);
         if (lights) cudaFree(lights);
         if (cnodes) cudaFree(cnodes);
         if (cleaves) cudaFree(cleaves);
-        tris = nullptr; mats = nullptr; lights = nullptr; cnodes = nullptr; cleaves = nullptr;
+        if (nleaves) cudaFree(nleaves);
+        tris = nullptr; mats = nullptr; lights = nullptr; cnodes = nullptr; cleaves = nullptr; nleaves = nullptr;
     }
 };
 
@@ -50,6 +52,8 @@ struct lt_scene {
     int n_tris = 0, n_mats = 0, n_lights = 0;
     int n_cnodes = 0, n_cleaves = 0, n_cflat = 0;
     double bbox_min[3], bbox_max[3];   // bounds of all vertices (computed for small scenes, else +-inf)
+    std::vector<double> h_small_v;     // [tri][vertex][3] of scenes with <= LT_NEAREST_BOXES triangles (per-triangle bounds, built per precision)
+    int n_nleaves = 0;
     int n_lbvh_nodes = 0;
     lt::SceneArrays<float> f32;
     lt::SceneArrays<double> f64;

@@ -165,6 +165,7 @@ LT_DEVINL uint64_t slab_pairs_mask(const float* tab, int n_leaves, V3<float> o, 
 // Replaces ~6 dependent {load node, slab test, branch} levels per ray.  Chains longer than 8 interior nodes (or a
 // root that is a leaf) keep the generic loop.
 #define LT_CHAIN_PAIRS 4
+#define LT_NEAREST_BOXES 32   // scenes up to this many triangles get per-triangle bounds for the NEAREST scan
 #define LT_CHAIN_FLOATS (8 * LT_CHAIN_PAIRS * 12)
 #define LT_CHAIN_BYTES (LT_CHAIN_FLOATS * 4 + 32)
 struct ChainTab {
@@ -254,7 +255,7 @@ LT_DEVINL double shfl_real(double v, int src) { return __shfl_sync(0xffffffffu, 
 template <typename R>
 LT_DEVINL void compat_query(unsigned amask, const CompatNode<R>* nodes, const CompatLeaf<R>* leaves, int n_leaves, const float* slabtab,
                             const uint8_t* flatprim, const TriRec<R>* tris, V3<R> o, V3<R> d, R eps, R tlimit, bool anyhit, int skip, int& prim, R& best,
-                            Stats& st, bool live = true, WarpScratch<R> ws = WarpScratch<R>(), ChainTab chain = ChainTab()) {
+                            Stats& st, bool live = true, WarpScratch<R> ws = WarpScratch<R>(), ChainTab chain = ChainTab(), bool descent = true) {
     V3<R> inv = mk<R>((R)1 / d.x, (R)1 / d.y, (R)1 / d.z);
     prim = -1;
     best = tlimit;
@@ -262,7 +263,8 @@ LT_DEVINL void compat_query(unsigned amask, const CompatNode<R>* nodes, const Co
     // if its bounds are hit: it is processed before every other leaf).
     int cur = 0, first = -1;
     uint64_t lvis = 0;
-    bool done = !live, descending = live;     // a lane without a query of its own only helps with the pooled triangle tests
+    bool done = !live, descending = live && descent;     // a lane without a query of its own only helps with the pooled triangle tests;
+                                                         // descent == false: NEAREST over per-triangle bounds (no tree, no kills)
     int chain_leaf = -1;
     if (sizeof(R) == 4 && chain.tab && live) {            // float32: the descent as one branch-free chain evaluation
         const V3<float> of = mk<float>((float)o.x, (float)o.y, (float)o.z), invf = mk<float>((float)inv.x, (float)inv.y, (float)inv.z);

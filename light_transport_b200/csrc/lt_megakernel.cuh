@@ -97,7 +97,19 @@ walk_megakernel(const WalkParams<R> P) {
             cnodes = stage_array(cur, P.S.cnodes, P.S.n_cnodes);
             cleaves = stage_array(cur, P.S.cleaves, P.S.n_cleaves);
         }
+        if (TRAV == LT_TRAV_NEAREST && P.S.n_nleaves > 0) cleaves = stage_array(cur, P.S.nleaves, P.S.n_nleaves);
         __syncthreads();
+        if (TRAV == LT_TRAV_NEAREST && P.S.n_nleaves > 0) {
+            // small scene: the all-primitive scan culls with per-triangle bounds through COMPAT's machinery (no descent, no kills)
+            if (sizeof(R) == 4) {
+                build_slab_pairs(reinterpret_cast<float*>(cur), reinterpret_cast<const CompatLeaf<float>*>(cleaves), P.S.n_nleaves);
+                slabtab = reinterpret_cast<const float*>(cur);
+                cur += (slab_pairs_bytes(P.S.n_nleaves) + 15) / 16 * 16;
+            }
+            build_flat_prims<R>(reinterpret_cast<uint8_t*>(cur), cleaves, P.S.n_nleaves);
+            flatprim = reinterpret_cast<const uint8_t*>(cur);
+            __syncthreads();
+        }
         if (TRAV == LT_TRAV_COMPAT) {
             if (sizeof(R) == 4) {                           // float32: leaf bounds re-laid for slab_pairs_mask
                 build_slab_pairs(reinterpret_cast<float*>(cur), reinterpret_cast<const CompatLeaf<float>*>(cleaves), P.S.n_cleaves);
@@ -238,8 +250,13 @@ walk_megakernel(const WalkParams<R> P) {
             }
             if (active) {
                 const bool anyhit = ln.qtype == 2;
-                if (TRAV == LT_TRAV_NEAREST)
-                    nearest_query<R>(tris, P.S.n_tris, ln.o, ln.d, eps, ln.tlimit, anyhit, ln.skip, prim, t, st);
+                if (TRAV == LT_TRAV_NEAREST) {
+                    if (flatprim)
+                        compat_query<R>(am, nullptr, cleaves, P.S.n_nleaves, slabtab, flatprim, tris, ln.o, ln.d, eps, ln.tlimit, anyhit, ln.skip, prim, t, st,
+                                        true, WarpScratch<R>(), ChainTab(), false);
+                    else
+                        nearest_query<R>(tris, P.S.n_tris, ln.o, ln.d, eps, ln.tlimit, anyhit, ln.skip, prim, t, st);
+                }
                 (void)anyhit;
                 int stt;
                 R adv_rand0 = (R)0;

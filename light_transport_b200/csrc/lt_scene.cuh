@@ -63,9 +63,11 @@ struct SceneView {
     const LightRec<R>* lights;
     const CompatNode<R>* cnodes;
     const CompatLeaf<R>* cleaves;
+    const CompatLeaf<R>* nleaves;  // NEAREST, small scenes: per-triangle bounds in primitive order (kill = 0), else null
     const LbvhNode* lbvh;         // root = node 0
     int32_t n_tris, n_mats, n_lights, n_cnodes, n_cleaves, n_lbvh_nodes;
     int32_t n_cflat;              // primitives referenced by the COMPAT leaves (flattened sequence length)
+    int32_t n_nleaves;
     double bbox_min[3], bbox_max[3];   // bounds of all vertices (small scenes; +-inf when not computed): NEAREST early miss
 };
 

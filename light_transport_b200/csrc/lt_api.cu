@@ -22,6 +22,30 @@ void set_error(const char* fmt, ...) {
 }
 
 // ---- pointer staging: caller data may live on the host or on the device -------------------------
+// ---- device memory (see lt_host.h) ---------------------------------------------------------------
+static cudaStream_t g_alloc_stream[64] = {};
+static cudaStream_t alloc_stream() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return nullptr;
+    if (!g_alloc_stream[dev]) {
+        cudaStreamCreateWithFlags(&g_alloc_stream[dev], cudaStreamNonBlocking);
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
+    return g_alloc_stream[dev];
+}
+cudaError_t lt_dev_malloc_impl(void** p, size_t bytes) {
+    cudaStream_t st = alloc_stream();
+    cudaError_t e = cudaMallocAsync(p, bytes, st);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(st);
+}
+cudaError_t lt_dev_free_impl(void* p) { return p ? cudaFreeAsync(p, alloc_stream()) : cudaSuccess; }
+
 static bool is_device_ptr(const void* p) {
     cudaPointerAttributes a;
     cudaError_t e = cudaPointerGetAttributes(&a, p);
@@ -36,12 +60,12 @@ struct InBuf {   // read-only input
     int init(const T* p, size_t n, cudaStream_t s) {
         if (!p || n == 0) return LT_OK;
         if (is_device_ptr(p)) { dev = p; return LT_OK; }
-        LT_CUDA_OK(cudaMalloc(&owned, n * sizeof(T)));
+        LT_CUDA_OK(lt_dev_malloc(&owned, n * sizeof(T)));
         LT_CUDA_OK(cudaMemcpyAsync(owned, p, n * sizeof(T), cudaMemcpyHostToDevice, s));
         dev = owned;
         return LT_OK;
     }
-    ~InBuf() { if (owned) cudaFree(owned); }
+    ~InBuf() { if (owned) lt_dev_free(owned); }
 };
 template <typename T>
 struct OutBuf {  // output; `accumulate`: host destination receives += instead of =
@@ -56,7 +80,7 @@ struct OutBuf {  // output; `accumulate`: host destination receives += instead o
         accumulate = acc;
         if (is_device_ptr(p)) { dev = p; return LT_OK; }
         host = p;
-        LT_CUDA_OK(cudaMalloc(&owned, n * sizeof(T)));
+        LT_CUDA_OK(lt_dev_malloc(&owned, n * sizeof(T)));
         if (acc) LT_CUDA_OK(cudaMemsetAsync(owned, 0, n * sizeof(T), s));
         dev = owned;
         return LT_OK;
@@ -74,14 +98,14 @@ struct OutBuf {  // output; `accumulate`: host destination receives += instead o
         }
         return LT_OK;
     }
-    ~OutBuf() { if (owned) cudaFree(owned); }
+    ~OutBuf() { if (owned) lt_dev_free(owned); }
 };
 
 template <typename T>
 static int upload(T** dst, const std::vector<T>& v) {
-    if (*dst) { cudaFree(*dst); *dst = nullptr; }
+    if (*dst) { lt_dev_free(*dst); *dst = nullptr; }
     if (v.empty()) return LT_OK;
-    LT_CUDA_OK(cudaMalloc(dst, v.size() * sizeof(T)));
+    LT_CUDA_OK(lt_dev_malloc(dst, v.size() * sizeof(T)));
     LT_CUDA_OK(cudaMemcpy(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
     return LT_OK;
 }
@@ -128,7 +152,7 @@ __global__ void build_tris_kernel(const double* __restrict__ v0, const double* _
 
 template <typename T>
 static int upload_raw(T** dst, const T* src, size_t n, cudaStream_t st) {
-    LT_CUDA_OK(cudaMalloc(dst, std::max<size_t>(n, 1) * sizeof(T)));
+    LT_CUDA_OK(lt_dev_malloc(dst, std::max<size_t>(n, 1) * sizeof(T)));
     if (n) LT_CUDA_OK(cudaMemcpyAsync(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice, st));
     return LT_OK;
 }
@@ -140,7 +164,7 @@ static int ensure_arrays(lt_scene* s) {
     if (a.tris) return LT_OK;
     cudaStream_t st = s->ctx->stream;
     const int n = s->n_tris;
-    LT_CUDA_OK(cudaMalloc(&a.tris, (size_t)n * sizeof(TriRec<R>)));
+    LT_CUDA_OK(lt_dev_malloc(&a.tris, (size_t)n * sizeof(TriRec<R>)));
     build_tris_kernel<R><<<(n + 255) / 256, 256, 0, st>>>(s->d_v0, s->d_v1, s->d_v2, s->d_n, s->d_mat, s->d_light, n, a.tris);
     LT_CUDA_OK(cudaGetLastError());
     std::vector<MatRec<R>> mats(s->n_mats);
@@ -377,9 +401,9 @@ static int do_render(lt_scene* s, const lt_render_params* p, const double* rand0
         P.arena_frames = D - local_frames;
         size_t bytes = (size_t)P.arena_frames * LT_ARENA_VALUES * (size_t)P.arena_threads * sizeof(R);
         if (bytes > ctx->arena_bytes) {
-            if (ctx->arena) cudaFree(ctx->arena);
+            if (ctx->arena) lt_dev_free(ctx->arena);
             ctx->arena = nullptr; ctx->arena_bytes = 0;
-            LT_CUDA_OK(cudaMalloc(&ctx->arena, bytes));
+            LT_CUDA_OK(lt_dev_malloc(&ctx->arena, bytes));
             ctx->arena_bytes = bytes;
         }
         P.arena = reinterpret_cast<R*>(ctx->arena);
@@ -530,8 +554,8 @@ int lt_init(int device, lt_ctx** out) {
     LT_CUDA_OK(cudaGetDeviceProperties(&c->prop, device));
     LT_CUDA_OK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
-    LT_CUDA_OK(cudaMalloc(&c->d_counters, sizeof(lt_counters)));
-    LT_CUDA_OK(cudaMalloc(&c->d_granule, sizeof(unsigned long long)));
+    LT_CUDA_OK(lt_dev_malloc(&c->d_counters, sizeof(lt_counters)));
+    LT_CUDA_OK(lt_dev_malloc(&c->d_granule, sizeof(unsigned long long)));
     LT_CUDA_OK(cudaEventCreate(&c->ev0));
     LT_CUDA_OK(cudaEventCreate(&c->ev1));
     *out = c;
@@ -541,10 +565,10 @@ int lt_init(int device, lt_ctx** out) {
 void lt_destroy(lt_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    if (c->arena) cudaFree(c->arena);
-    if (c->film) cudaFree(c->film);
-    if (c->d_counters) cudaFree(c->d_counters);
-    if (c->d_granule) cudaFree(c->d_granule);
+    if (c->arena) lt_dev_free(c->arena);
+    if (c->film) lt_dev_free(c->film);
+    if (c->d_counters) lt_dev_free(c->d_counters);
+    if (c->d_granule) lt_dev_free(c->d_granule);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -624,13 +648,13 @@ void lt_scene_destroy(lt_scene* s) {
     cudaSetDevice(s->ctx->device);
     s->f32.release();
     s->f64.release();
-    if (s->lbvh_nodes) cudaFree(s->lbvh_nodes);
-    if (s->d_v0) cudaFree(s->d_v0);
-    if (s->d_v1) cudaFree(s->d_v1);
-    if (s->d_v2) cudaFree(s->d_v2);
-    if (s->d_n) cudaFree(s->d_n);
-    if (s->d_mat) cudaFree(s->d_mat);
-    if (s->d_light) cudaFree(s->d_light);
+    if (s->lbvh_nodes) lt_dev_free(s->lbvh_nodes);
+    if (s->d_v0) lt_dev_free(s->d_v0);
+    if (s->d_v1) lt_dev_free(s->d_v1);
+    if (s->d_v2) lt_dev_free(s->d_v2);
+    if (s->d_n) lt_dev_free(s->d_n);
+    if (s->d_mat) lt_dev_free(s->d_mat);
+    if (s->d_light) lt_dev_free(s->d_light);
     delete s;
 }
 
@@ -704,9 +728,9 @@ int lt_render_image(lt_scene* s, const lt_render_params* p, const double* rand0,
     LT_CUDA_OK(cudaSetDevice(ctx->device));
     const size_t n = (size_t)p->width * p->height * 3;
     if (n > ctx->film_values) {
-        if (ctx->film) cudaFree(ctx->film);
+        if (ctx->film) lt_dev_free(ctx->film);
         ctx->film = nullptr; ctx->film_values = 0;
-        LT_CUDA_OK(cudaMalloc(&ctx->film, n * sizeof(double)));
+        LT_CUDA_OK(lt_dev_malloc(&ctx->film, n * sizeof(double)));
         ctx->film_values = n;
     }
     LT_CUDA_OK(cudaMemsetAsync(ctx->film, 0, n * sizeof(double), ctx->stream));
@@ -778,7 +802,7 @@ int lt_measure_fp32_peak(lt_ctx* ctx, double* tflops) {
     LT_CUDA_OK(cudaSetDevice(ctx->device));
     const int blocks = ctx->prop.multiProcessorCount * 8, threads = 256, iters = 1 << 15;
     float* d = nullptr;
-    LT_CUDA_OK(cudaMalloc(&d, (size_t)blocks * threads * sizeof(float)));
+    LT_CUDA_OK(lt_dev_malloc(&d, (size_t)blocks * threads * sizeof(float)));
     fma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(d, 1 << 10);
     double best = 0;
     for (int rep = 0; rep < 5; ++rep) {
@@ -791,7 +815,7 @@ int lt_measure_fp32_peak(lt_ctx* ctx, double* tflops) {
         double tf = 2.0 * 8.0 * iters * (double)blocks * threads / (ms * 1e-3) / 1e12;
         best = std::max(best, tf);
     }
-    cudaFree(d);
+    lt_dev_free(d);
     *tflops = best;
     return LT_OK;
 }

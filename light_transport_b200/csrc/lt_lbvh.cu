@@ -286,8 +286,8 @@ __global__ void emit_kernel(const Box* __restrict__ prim_boxes, const uint32_t* 
 template <typename T>
 struct Tmp {
     T* p = nullptr;
-    cudaError_t alloc(size_t n) { return cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)); }
-    ~Tmp() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t n) { return lt_dev_malloc(&p, std::max<size_t>(n, 1) * sizeof(T)); }
+    ~Tmp() { if (p) lt_dev_free(p); }
 };
 
 }  // namespace lt
@@ -304,7 +304,7 @@ extern "C" int lt_bvh_build(lt_scene* s, int flags, lt_bvh_stats* out) {
     lt_bvh_stats stats;
     memset(&stats, 0, sizeof stats);
     stats.n_prims = n;
-    if (s->lbvh_nodes) { cudaFree(s->lbvh_nodes); s->lbvh_nodes = nullptr; s->n_lbvh_nodes = 0; }
+    if (s->lbvh_nodes) { lt_dev_free(s->lbvh_nodes); s->lbvh_nodes = nullptr; s->n_lbvh_nodes = 0; }
     if (n < 2) {   // a single primitive needs no hierarchy; the traversal tests it directly
         if (out) *out = stats;
         return LT_OK;
@@ -346,7 +346,7 @@ extern "C" int lt_bvh_build(lt_scene* s, int flags, lt_bvh_stats* out) {
     karras_kernel<<<iblocks, LB_THREADS, 0, st>>>(ki, n, left.p, right.p, par_i.p, par_l.p);
     refit_kernel<<<blocks, LB_THREADS, 0, st>>>(prim_boxes.p, vi, n, left.p, right.p, par_i.p, par_l.p, node_boxes.p, arrive.p, maxd.p);
     depth_kernel<<<blocks, LB_THREADS, 0, st>>>(n, par_i.p, par_l.p, maxd.p);
-    LT_CUDA_OK(cudaMalloc(&s->lbvh_nodes, (size_t)(n - 1) * sizeof(LbvhNode)));
+    LT_CUDA_OK(lt_dev_malloc(&s->lbvh_nodes, (size_t)(n - 1) * sizeof(LbvhNode)));
     emit_kernel<<<iblocks, LB_THREADS, 0, st>>>(prim_boxes.p, vi, n, left.p, right.p, node_boxes.p, s->lbvh_nodes);
     cudaEventRecord(e3, st);
     LT_CUDA_OK(cudaGetLastError());
@@ -367,7 +367,7 @@ extern "C" int lt_bvh_build(lt_scene* s, int flags, lt_bvh_stats* out) {
     for (int k = 0; k < 3; ++k) { stats.root_bmin[k] = root.lo[k]; stats.root_bmax[k] = root.hi[k]; }
     if (out) *out = stats;
     if (depth > LT_LBVH_STACK) {
-        cudaFree(s->lbvh_nodes); s->lbvh_nodes = nullptr; s->n_lbvh_nodes = 0;
+        lt_dev_free(s->lbvh_nodes); s->lbvh_nodes = nullptr; s->n_lbvh_nodes = 0;
         set_error("LBVH depth %d exceeds the traversal stack (%d)", depth, LT_LBVH_STACK);
         return LT_E_OVERFLOW;
     }

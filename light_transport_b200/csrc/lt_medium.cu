@@ -213,10 +213,10 @@ extern "C" int lt_medium_walk(lt_ctx* ctx, const lt_medium_params* p, uint64_t n
     unsigned long long* d_hist = nullptr;
     double *d_rbins = nullptr, *d_tot = nullptr;
     unsigned long long* d_cnt = nullptr;
-    LT_CUDA_OK(cudaMalloc(&d_hist, sizeof(unsigned long long) * (D + 1)));
-    LT_CUDA_OK(cudaMalloc(&d_rbins, sizeof(double) * std::max(NB, 1)));
-    LT_CUDA_OK(cudaMalloc(&d_tot, sizeof(double) * 6));
-    LT_CUDA_OK(cudaMalloc(&d_cnt, sizeof(unsigned long long) * 3));
+    LT_CUDA_OK(lt_dev_malloc(&d_hist, sizeof(unsigned long long) * (D + 1)));
+    LT_CUDA_OK(lt_dev_malloc(&d_rbins, sizeof(double) * std::max(NB, 1)));
+    LT_CUDA_OK(lt_dev_malloc(&d_tot, sizeof(double) * 6));
+    LT_CUDA_OK(lt_dev_malloc(&d_cnt, sizeof(unsigned long long) * 3));
     LT_CUDA_OK(cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * (D + 1), st));
     LT_CUDA_OK(cudaMemsetAsync(d_rbins, 0, sizeof(double) * std::max(NB, 1), st));
     LT_CUDA_OK(cudaMemsetAsync(d_tot, 0, sizeof(double) * 6, st));
@@ -257,7 +257,7 @@ extern "C" int lt_medium_walk(lt_ctx* ctx, const lt_medium_params* p, uint64_t n
     totals->rr_gained = h_tot[4]; totals->sum_mu = h_tot[5];
     totals->n_collisions = h_cnt[0]; totals->n_segments = h_cnt[1]; totals->n_scatters = h_cnt[2];
     if (kernel_ms) LT_CUDA_OK(cudaEventElapsedTime(kernel_ms, ctx->ev0, ctx->ev1));
-    cudaFree(d_hist); cudaFree(d_rbins); cudaFree(d_tot); cudaFree(d_cnt);
+    lt_dev_free(d_hist); lt_dev_free(d_rbins); lt_dev_free(d_tot); lt_dev_free(d_cnt);
     return LT_OK;
 }
 

@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, RAY_SETS, load_scene
+from conftest import GOLDEN, RAY_SETS, load_scene, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -120,4 +120,36 @@ def test_lbvh_mesh_vs_oracle(oracle):
     p_o, t_o, _ = oracle.intersect(S, o[:k], d[:k], "nearest")
     assert np.array_equal(p_l[:k], p_o) and np.array_equal(t_l[:k][p_o >= 0], t_o[p_o >= 0])
     assert (p_l >= 28).mean() > 0.2                            # the mesh is actually being hit
+    R.close()
+
+
+def test_compat_beyond_the_small_scene_paths(oracle):
+    """COMPAT on a scene with more than 32 leaves / referenced primitives (the Cornell scene + a 4x4 displaced grid = 60
+    triangles): the kernels' small-scene tables (32-bit masks, two tests per round, descent chains) do not apply and the
+    general 64-bit leaf walk runs.  Ids and t bit-exact against the oracle in float64, walk replayed on Philox streams."""
+    from light_transport_b200 import host, scenes, _pack, compat_bvh
+    base, _, cam, f = load_scene("lts_scene.npz")
+    ps = _pack.from_arrays(scenes.heightfield(nx=4, ny=4), base=base)
+    nodes = compat_bvh.build_compat_nodes(ps.tri_v0, ps.tri_v1, ps.tri_v2)
+    n_leaves = int((nodes.n_prims > 0).sum())
+    assert ps.n_tris == 60 and 32 < n_leaves <= 64 and len(nodes.n_prims) <= 128
+    R = host.Renderer(ps, nodes)
+    S = oracle.OracleScene(ps, nodes)
+    rng = np.random.default_rng(11)
+    n = 20000
+    o = np.concatenate([np.tile(cam, (n // 2, 1)), rng.uniform(-6, 6, (n // 2, 3))])
+    d = rng.normal(size=(n, 3)); d[: n // 2, 2] = -np.abs(d[: n // 2, 2]) - 0.5
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    p_o, t_o, _ = oracle.intersect(S, o, d, "compat")
+    p_g, t_g, _ = R.intersect(o, d, "compat", "f64")
+    assert np.array_equal(p_g, p_o) and np.array_equal(t_g[p_o >= 0], t_o[p_o >= 0])
+    assert (p_o >= 28).mean() > 0.05                           # the added triangles are being hit
+    p_f, _, _ = R.intersect(o, d, "compat", "f32")
+    assert (p_f != p_o).mean() < 0.02
+    kw = dict(width=48, height=32, spp=4, max_depth=8, camera=cam, f_distance=f, seed=5, semantics="reference", traversal="compat")
+    for sched in ("megakernel", "wavefront"):
+        film, samples, cnt = R.render(real="f64", return_samples=True, scheduler=sched, **kw)
+        o_film, o_samples, o_cnt = oracle.render(S, return_samples=True, **kw)
+        assert (rel_err(samples, o_samples) > 1e-9).sum() == 0
+        assert cnt["rays_ext"] == o_cnt["rays_ext"] and cnt["rays_shadow"] == o_cnt["rays_shadow"]
     R.close()

@@ -474,6 +474,31 @@ LT_DEVINL bool slab_t(R lx, R ly, R lz, R hx, R hy, R hz, V3<R> o, V3<R> inv, R 
     return t0 <= t1;
 }
 
+// Both child boxes of one LbvhNode.  float32: the per-axis words hold {lo0, lo1, hi0, hi1}, so the six subtractions
+// and six products of the two slab tests are three add.f32x2 + ... each half rounded like the scalar instruction;
+// the widening is applied once to the minimum of the far distances (rounding is monotone: min(w*f_i) == w*min(f_i),
+// bit for bit).  float64: the same arithmetic as slab_t on the re-laid node.
+LT_DEVINL void slab_t2(float4 X, float4 Y, float4 Z, V3<float> o, V3<float> inv, float best, float& t0n, float& t1n, bool& h0, bool& h1) {
+    const float eps32 = 5.9604644775390625e-08f;
+    const float widen = 1.0f + 2.0f * ((3.0f * eps32) / (1.0f - 3.0f * eps32));
+    const float2 nox = make_float2(-o.x, -o.x), noy = make_float2(-o.y, -o.y), noz = make_float2(-o.z, -o.z);
+    const float2 ivx = make_float2(inv.x, inv.x), ivy = make_float2(inv.y, inv.y), ivz = make_float2(inv.z, inv.z);
+    const float2 ax = __fmul2_rn(__fadd2_rn(make_float2(X.x, X.y), nox), ivx), bx = __fmul2_rn(__fadd2_rn(make_float2(X.z, X.w), nox), ivx);
+    const float2 ay = __fmul2_rn(__fadd2_rn(make_float2(Y.x, Y.y), noy), ivy), by = __fmul2_rn(__fadd2_rn(make_float2(Y.z, Y.w), noy), ivy);
+    const float2 az = __fmul2_rn(__fadd2_rn(make_float2(Z.x, Z.y), noz), ivz), bz = __fmul2_rn(__fadd2_rn(make_float2(Z.z, Z.w), noz), ivz);
+    const float bw = best * widen;
+    t0n = fmaxf(fmaxf(fminf(ax.x, bx.x), fminf(ay.x, by.x)), fmaxf(fminf(az.x, bz.x), 0.0f));
+    t1n = fmaxf(fmaxf(fminf(ax.y, bx.y), fminf(ay.y, by.y)), fmaxf(fminf(az.y, bz.y), 0.0f));
+    const float f0 = fminf(fminf(fminf(fmaxf(ax.x, bx.x), fmaxf(ay.x, by.x)), fmaxf(az.x, bz.x)) * widen, bw);
+    const float f1 = fminf(fminf(fminf(fmaxf(ax.y, bx.y), fmaxf(ay.y, by.y)), fmaxf(az.y, bz.y)) * widen, bw);
+    h0 = t0n <= f0;
+    h1 = t1n <= f1;
+}
+LT_DEVINL void slab_t2(float4 X, float4 Y, float4 Z, V3<double> o, V3<double> inv, double best, double& t0n, double& t1n, bool& h0, bool& h1) {
+    h0 = slab_t<double>((double)X.x, (double)Y.x, (double)Z.x, (double)X.z, (double)Y.z, (double)Z.z, o, inv, best, t0n);
+    h1 = slab_t<double>((double)X.y, (double)Y.y, (double)Z.y, (double)X.w, (double)Y.w, (double)Z.w, o, inv, best, t1n);
+}
+
 #define LT_LBVH_DONE ((int)0x80000000)
 
 // Warp-scheduled traversal.  Every lane holds either an interior node (cur >= 0), a leaf (cur < 0) or
@@ -516,12 +541,12 @@ LT_DEVINL void lbvh_run(unsigned amask, LbvhState<R>& s, int* stack, const LbvhN
         if (__popc(nm) >= __popc(lm)) {
             if (at_node) {
                 const float4* p = reinterpret_cast<const float4*>(nodes + s.cur);
-                float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
-                int4 r = __ldg(reinterpret_cast<const int4*>(p + 3));
+                const float4 X = __ldg(p), Y = __ldg(p + 1), Z = __ldg(p + 2);
+                const int4 r = __ldg(reinterpret_cast<const int4*>(p + 3));
                 R t0n, t1n;
                 st.box_tests += 2;
-                bool h0 = slab_t<R>((R)a.x, (R)a.y, (R)a.z, (R)a.w, (R)b.x, (R)b.y, o, inv, s.best, t0n);
-                bool h1 = slab_t<R>((R)b.z, (R)b.w, (R)c.x, (R)c.y, (R)c.z, (R)c.w, o, inv, s.best, t1n);
+                bool h0, h1;
+                slab_t2(X, Y, Z, o, inv, s.best, t0n, t1n, h0, h1);
                 bool swap = t1n < t0n;
                 int nearc = swap ? r.y : r.x, farc = swap ? r.x : r.y;
                 if (h0 & h1) { stack[s.sp++] = farc; s.cur = nearc; }

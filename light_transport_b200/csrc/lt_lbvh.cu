@@ -276,9 +276,9 @@ __global__ void emit_kernel(const Box* __restrict__ prim_boxes, const uint32_t* 
     Box b0 = c0 >= 0 ? node_boxes[c0] : prim_boxes[sorted_prim[~c0]];
     Box b1 = c1 >= 0 ? node_boxes[c1] : prim_boxes[sorted_prim[~c1]];
     LbvhNode nd;
-    nd.a = make_float4(b0.lo[0], b0.lo[1], b0.lo[2], b0.hi[0]);
-    nd.b = make_float4(b0.hi[1], b0.hi[2], b1.lo[0], b1.lo[1]);
-    nd.c = make_float4(b1.lo[2], b1.hi[0], b1.hi[1], b1.hi[2]);
+    nd.x = make_float4(b0.lo[0], b1.lo[0], b0.hi[0], b1.hi[0]);
+    nd.y = make_float4(b0.lo[1], b1.lo[1], b0.hi[1], b1.hi[1]);
+    nd.z = make_float4(b0.lo[2], b1.lo[2], b0.hi[2], b1.hi[2]);
     nd.d = make_int4(c0 >= 0 ? c0 : ~(int)sorted_prim[~c0], c1 >= 0 ? c1 : ~(int)sorted_prim[~c1], 0, 0);
     out[i] = nd;
 }

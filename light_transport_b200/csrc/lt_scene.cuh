@@ -48,9 +48,9 @@ struct alignas(16) CompatLeaf {
 // BVH2 node for the GPU LBVH: child boxes live in the parent so that one 64-byte fetch decides both
 // children.  ref >= 0: interior node index; ref < 0: leaf holding primitive ~ref.
 struct alignas(16) LbvhNode {
-    float4 a;   // lo0.x lo0.y lo0.z hi0.x
-    float4 b;   // hi0.y hi0.z lo1.x lo1.y
-    float4 c;   // lo1.z hi1.x hi1.y hi1.z
+    float4 x;   // lo0.x lo1.x hi0.x hi1.x   one 128-bit word per axis, the two children side by side: the float32
+    float4 y;   // lo0.y lo1.y hi0.y hi1.y   node step subtracts and multiplies both children at once (add/mul.f32x2)
+    float4 z;   // lo0.z lo1.z hi0.z hi1.z
     int4 d;     // ref0 ref1 - -
 };
 #define LT_LBVH_STACK 96

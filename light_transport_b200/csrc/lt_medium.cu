@@ -54,20 +54,24 @@ LT_DEVINL void medium_rand4<float>(const MediumDev& P, uint64_t photon, uint32_t
     u01(o[1], 0u, u[2]); u01(o[3], 0u, u[3]);
 }
 
-// add `value` to bins[bin] for the lanes with `pred`: lanes sharing a bin are summed first (match_any +
-// shuffles), then one lane per distinct bin issues the shared-memory atomic
+// add `value` to bins[bin] for the lanes with `pred`: lanes sharing a bin are summed first, then one lane per
+// distinct bin issues the shared-memory atomic (a CAS loop for double / 64-bit bins, so worth aggregating).
+// Every lane walks ITS OWN peer group (match_any) with per-lane shuffle sources, so the loop runs as many
+// times as the largest group has members (2-4 for 32 lanes over 64 bins), not once per active lane: that
+// 32-iteration form was 47 % of the kernel's instructions.
 template <typename T>
 LT_DEVINL void warp_bin_add(T* bins, int bin, T value, bool pred) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    unsigned m = __ballot_sync(full, pred);
-    if (!m) return;
-    unsigned peers = __match_any_sync(full, pred ? bin : -1 - lane);
+    if (!__any_sync(full, pred)) return;
+    const unsigned peers = __match_any_sync(full, pred ? bin : -1 - lane);
     T sum = 0;
-    for (unsigned rest = m; rest; rest &= rest - 1) {
-        int src = __ffs(rest) - 1;
-        T v = __shfl_sync(full, value, src);
-        if ((peers >> src) & 1u) sum += v;
+    unsigned rest = pred ? peers : 0u;
+    while (__any_sync(full, rest != 0u)) {
+        const int src = rest ? __ffs(rest) - 1 : lane;
+        const T v = __shfl_sync(full, value, src);
+        if (rest) sum += v;
+        rest &= rest - 1;
     }
     if (pred && (__ffs(peers) - 1) == lane) atomicAdd(&bins[bin], sum);
 }

@@ -157,11 +157,16 @@ def time_to_rmse(R, cam, depth, args, size=256, target=0.01, chunk=32, ref_facto
     ref = torch.empty_like(film)
     R.render(spp=ref_spp, seed=999, film=film, **kw)
     R.finalize(film, ref_spp, out=ref)
-    film.zero_()
     img = torch.empty_like(film)
+    spp_max = WORKLOAD["spp"] * 4
+    # one untimed progressive pass (render + finalize + the RMSE reduction) so that lazily loaded kernels are resident
+    R.render(spp=spp_max, s0=0, s1=chunk, seed=8, film=film, **kw)
+    R.finalize(film, chunk, out=img)
+    float(torch.sqrt(torch.mean((img - ref) ** 2)))
+    film.zero_()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    done, rmse, spp_max = 0, float("inf"), WORKLOAD["spp"] * 4
+    done, rmse = 0, float("inf")
     while done < spp_max:                      # progressive passes share one job (spp_max) so counters stay disjoint
         R.render(spp=spp_max, s0=done, s1=done + chunk, seed=7, film=film, **kw)
         done += chunk

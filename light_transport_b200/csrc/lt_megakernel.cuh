@@ -169,15 +169,23 @@ walk_megakernel(const WalkParams<R> P) {
     __shared__ R pool_res[pooled ? LT_BLOCK / 32 : 1][pooled ? LT_POOL_SLOTS : 1];
     if (pooled && flatprim) { ws.items = pool_items[threadIdx.x >> 5]; ws.res = pool_res[threadIdx.x >> 5]; }
 
-    for (int64_t g = gwarp; g * ppw < P.total_paths; g += nwarps) {
-        // the granule: indices [g*ppw, g*ppw + g_n); (pixel, sample) of its first index from one 64-bit division,
-        // 32-bit ones per path
+    // The warp's granules [g*ppw, g*ppw + g_n), g = gwarp, gwarp + nwarps, ...: (pixel, sample) of a granule's first index
+    // from one 64-bit division, 32-bit ones per path.  Lanes move on to the next granule as soon as the current one
+    // has no index left — the warp drains only once, at the end of its whole list (draining per granule left 43 % of
+    // the lane slots of a small job like C1 idle: two paths per lane and granule).
+    int64_t g = gwarp;
+    int32_t g_n = 0, g_pix = 0, next = 0;
+    uint32_t g_s = 0;
+    auto load_granule = [&]() {
         const int64_t g_first = g * ppw;
-        const int32_t g_n = (int32_t)min((int64_t)ppw, P.total_paths - g_first);
-        const int32_t g_pix = (int32_t)(g_first / P.ns);
-        const uint32_t g_s = (uint32_t)(g_first - (int64_t)g_pix * P.ns);
-        int32_t next = 0;
-        if (lane == 0) atomicAdd(cnt + C_PATHS, (unsigned)g_n);            // every started path is tallied exactly once
+        g_n = g_first < P.total_paths ? (int32_t)min((int64_t)ppw, P.total_paths - g_first) : 0;
+        g_pix = (int32_t)(g_first / P.ns);
+        g_s = (uint32_t)(g_first - (int64_t)g_pix * P.ns);
+        next = 0;
+        if (lane == 0 && g_n > 0) atomicAdd(cnt + C_PATHS, (unsigned)g_n);   // every started path is tallied exactly once
+    };
+    load_granule();
+    {
         for (;;) {
             // ---- regeneration: idle lanes take the next indices of the granule (not ahead of a shadow phase, which
             // they could not join: they are refilled together before the next extension phase)
@@ -186,6 +194,7 @@ walk_megakernel(const WalkParams<R> P) {
             bool need = ln.qtype == 0;
             unsigned m = shadow_phase ? 0u : __ballot_sync(full, need);
             if (m) {
+                if (next >= g_n && g_n > 0) { g += nwarps; load_granule(); }        // warp-uniform
                 int32_t mine = next + __popc(m & ((1u << lane) - 1u));
                 next += __popc(m);
                 if (need && mine < g_n) {
@@ -202,7 +211,10 @@ walk_megakernel(const WalkParams<R> P) {
             }
             bool active = ln.qtype != 0;
             unsigned am = __ballot_sync(full, active);
-            if (!am) break;
+            if (!am) {
+                if (g_n > 0) continue;       // nobody holds a ray, but the list is not exhausted: the next pass refills
+                break;
+            }
             int want = ln.qtype;
             if (phased) {
                 // Phase alignment: an iteration serves EITHER extension OR shadow queries, so the lanes that shade

@@ -89,7 +89,8 @@ typedef struct {
     uint64_t seed;               /* Philox4x32-10 key (used when rand0 == NULL) */
     int32_t pixel0, pixel1;      /* optional pixel sub-range [pixel0,pixel1) in row-major order; 0,0 = all */
     int32_t paths_per_warp;      /* megakernel work granule; 0 = auto */
-    int32_t flags;               /* bits 8-15: LBVH traversal steps per megakernel iteration (0 = default 16); rest reserved */
+    int32_t flags;               /* bits 8-15: LBVH traversal steps per megakernel iteration (0 = default 24);
+                                    bit 16 / bit 17: force phase-aligned iterations off / on (default: from the scene); rest reserved */
 } lt_render_params;
 
 typedef struct {

@@ -393,6 +393,8 @@ static int do_render(lt_scene* s, const lt_render_params* p, const double* rand0
     }
     P.paths_per_warp = (int32_t)ppw;
     P.lbvh_chunk = ((p->flags >> 8) & 0xff) ? ((p->flags >> 8) & 0xff) : 24;
+    // phase-aligned iterations pay where most extension hits spawn a shadow query (flags bit 16 / 17 force off / on: A/B runs)
+    P.phased = (p->flags & (1 << 17)) ? 1 : (p->flags & (1 << 16)) ? 0 : (s->diffuse_area_share >= 0.5 ? 1 : 0);
     // suspended-frame storage for REFERENCE walks: a frame at stack depth k has bounce >= k and can still
     // recurse at bounce D-1, so up to D suspended frames; the megakernel keeps the first LT_LOCAL_FRAMES locally
     P.arena = nullptr; P.arena_frames = 0; P.arena_threads = (int64_t)grid * block;
@@ -615,6 +617,19 @@ int lt_scene_create(lt_ctx* ctx, const lt_scene_desc* d, lt_scene** out) {
                 s->bbox_min[c] = std::min(s->bbox_min[c], vs[a][i]);
                 s->bbox_max[c] = std::max(s->bbox_max[c], vs[a][i]);
             }
+    }
+    if (d->n_tris <= 65536 && d->n_tris > 0) {      // how much of the surface spawns shadow rays: picks the walk's phase policy
+        double all = 0, dif = 0;
+        for (int i = 0; i < d->n_tris; ++i) {
+            double ab[3], ac[3];
+            for (int c = 0; c < 3; ++c) { ab[c] = d->tri_v1[3 * i + c] - d->tri_v0[3 * i + c]; ac[c] = d->tri_v2[3 * i + c] - d->tri_v0[3 * i + c]; }
+            const double cx = ab[1] * ac[2] - ab[2] * ac[1], cy = ab[2] * ac[0] - ab[0] * ac[2], cz = ab[0] * ac[1] - ab[1] * ac[0];
+            const double area = 0.5 * std::sqrt(cx * cx + cy * cy + cz * cz);
+            const int m = d->tri_mat[i];
+            all += area;
+            if (m >= 0 && m < d->n_mats && (d->mat_flags[m] & 1)) dif += area;
+        }
+        s->diffuse_area_share = all > 0 ? dif / all : 1.0;
     }
     if (d->n_tris <= LT_NEAREST_BOXES) {
         s->h_small_v.resize((size_t)d->n_tris * 9);

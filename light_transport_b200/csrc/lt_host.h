@@ -64,6 +64,7 @@ struct lt_scene {
     double bbox_min[3], bbox_max[3];   // bounds of all vertices (computed for small scenes, else +-inf)
     std::vector<double> h_small_v;     // [tri][vertex][3] of scenes with <= LT_NEAREST_BOXES triangles (per-triangle bounds, built per precision)
     int n_nleaves = 0;
+    double diffuse_area_share = 1.0;   // share of the triangle area whose material is diffuse (scenes up to 65536 triangles; else 1)
     int n_lbvh_nodes = 0;
     lt::SceneArrays<float> f32;
     lt::SceneArrays<double> f64;

@@ -78,7 +78,7 @@ LT_DEVINL void flush_film_warp(double* film, int32_t pix, double acc[3]) {
 #define LT_PHASED 16          // lanes waiting for a shadow query that trigger a shadow phase; 0 = no phase alignment
 #endif
 
-template <typename R, int TRAV, int SEM>
+template <typename R, int TRAV, int SEM, int PH = 1>
 __global__ void __launch_bounds__(LT_BLOCK, sizeof(R) == 4 ? (TRAV == LT_TRAV_LBVH ? LT_MIN_BLOCKS_F32_LBVH : LT_MIN_BLOCKS_F32) : LT_MIN_BLOCKS_F64)
 walk_megakernel(const WalkParams<R> P) {
     extern __shared__ __align__(16) char smem[];
@@ -189,7 +189,7 @@ walk_megakernel(const WalkParams<R> P) {
         for (;;) {
             // ---- regeneration: idle lanes take the next indices of the granule (not ahead of a shadow phase, which
             // they could not join: they are refilled together before the next extension phase)
-            const bool phased = TRAV != LT_TRAV_LBVH && LT_PHASED > 0;
+            const bool phased = PH && TRAV != LT_TRAV_LBVH && LT_PHASED > 0;
             const bool shadow_phase = phased && __popc(__ballot_sync(full, ln.qtype == 2)) >= LT_PHASED;
             bool need = ln.qtype == 0;
             unsigned m = shadow_phase ? 0u : __ballot_sync(full, need);
@@ -223,6 +223,9 @@ walk_megakernel(const WalkParams<R> P) {
                 // query sit the iteration out.  A shadow phase runs once LT_PHASED lanes wait for one (or nobody has
                 // an extension ray).  Measured on C2: off 15.5, strict alternation 16.2, threshold 8/12/16/20/24/28:
                 // 16.2/16.3/16.4/16.4/16.2/16.2 Grays/s, with 83 % instead of 99 % of the traversal lanes busy.
+                // It pays where most extension hits spawn a shadow query; in the mirror box of C4a (one diffuse wall
+                // in six) the waiting costs more than the convergence gives: 10.9 aligned vs 12.5 Grays/s not aligned.
+                // The host picks the variant (PH) from the scene's diffuse share of surface area.
                 want = (shadow_phase || !__any_sync(full, ln.qtype == 1)) ? 2 : 1;
                 active = ln.qtype == want;
                 am = __ballot_sync(full, active);

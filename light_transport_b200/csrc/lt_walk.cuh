@@ -25,6 +25,7 @@ struct WalkParams {
     int32_t width, height, spp, s0, ns, max_depth, rr_start, n_light_idx, semantics, traversal;
     int32_t pixel0, paths_per_warp;
     int32_t lbvh_chunk;           // megakernel, LBVH: voted traversal steps per loop iteration
+    int32_t phased;               // megakernel, COMPAT / NEAREST: phase-aligned iterations (see lt_megakernel.cuh)
     int64_t total_paths;          // (pixel1 - pixel0) * ns
     double rr_floor, eps, cam[3], f_distance, top, bottom, step_x, step_y;
     uint64_t seed;

@@ -9,13 +9,20 @@
 
 namespace lt {
 
-template <typename R, int TRAV, int SEM>
-static int launch_one(const WalkParams<R>& P, int grid, size_t smem, cudaStream_t stream) {
-    auto k = walk_megakernel<R, TRAV, SEM>;
+template <typename R, int TRAV, int SEM, int PH>
+static int launch_ph(const WalkParams<R>& P, int grid, size_t smem, cudaStream_t stream) {
+    auto k = walk_megakernel<R, TRAV, SEM, PH>;
     if (smem > 48 * 1024) LT_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, LT_BLOCK, smem, stream>>>(P);
     LT_CUDA_OK(cudaGetLastError());
     return LT_OK;
+}
+// PH: phase-aligned iterations (lt_megakernel.cuh) — a compile-time variant because the aligned loop relies on the
+// query kind being warp-uniform.  The LBVH walk is never aligned.
+template <typename R, int TRAV, int SEM>
+static int launch_one(const WalkParams<R>& P, int grid, size_t smem, cudaStream_t stream) {
+    if (TRAV != LT_TRAV_LBVH && !P.phased) return launch_ph<R, TRAV, SEM, 0>(P, grid, smem, stream);
+    return launch_ph<R, TRAV, SEM, 1>(P, grid, smem, stream);
 }
 
 template <typename R, int TRAV>

@@ -85,9 +85,9 @@ LT_DEVINL V3<double> normalize_fast(V3<double> v) { return normalize(v); }
 template <typename R> LT_DEVINL R rabs(R x);
 template <> LT_DEVINL float rabs<float>(float x) { return fabsf(x); }
 template <> LT_DEVINL double rabs<double>(double x) { return fabs(x); }
-template <typename R> LT_DEVINL R rsqrt_(R x);
-template <> LT_DEVINL float rsqrt_<float>(float x) { return sqrtf(x); }
-template <> LT_DEVINL double rsqrt_<double>(double x) { return __dsqrt_rn(x); }
+template <typename R> LT_DEVINL R real_sqrt(R x);
+template <> LT_DEVINL float real_sqrt<float>(float x) { return sqrtf(x); }
+template <> LT_DEVINL double real_sqrt<double>(double x) { return __dsqrt_rn(x); }
 template <typename R> LT_DEVINL R comp(V3<R> v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : v.z); }
 
 template <typename R> struct Lim;

@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(LM_BLOCK) medium_kernel(const MediumDev P) {
                     id = P.first_photon + (uint64_t)mine;
                     R u[4];
                     medium_rand4<R>(P, id, 0xffffffffu, u);
-                    R mu = (R)1 - (R)2 * u[0], s2 = (R)1 - mu * mu, sn = rsqrt_<R>(s2 > 0 ? s2 : (R)0), ph = two_pi * u[1];
+                    R mu = (R)1 - (R)2 * u[0], s2 = (R)1 - mu * mu, sn = real_sqrt<R>(s2 > 0 ? s2 : (R)0), ph = two_pi * u[1];
                     R sp, cp;
                     if (sizeof(R) == 4) { float s_, c_; sincosf((float)ph, &s_, &c_); sp = s_; cp = c_; } else { double s_, c_; sincos((double)ph, &s_, &c_); sp = (R)s_; cp = (R)c_; }
                     d[0] = sn * cp; d[1] = sn * sp; d[2] = mu;
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(LM_BLOCK) medium_kernel(const MediumDev P) {
                 else {
                     k++;
                     n_coll++;
-                    shell = NB > 0 ? (Rs > 0 ? (int)(rsqrt_<R>(r2) / Rs * (R)NB) : 0) : 0;
+                    shell = NB > 0 ? (Rs > 0 ? (int)(real_sqrt<R>(r2) / Rs * (R)NB) : 0) : 0;
                     if (shell >= NB) shell = NB - 1;
                     if (P.mode == 0) {
                         if (u[1] >= a) { t_abs += (double)w; dep = (double)w; deposit = NB > 0; fin = true; }
@@ -158,17 +158,17 @@ __global__ void __launch_bounds__(LM_BLOCK) medium_kernel(const MediumDev P) {
                         mu = mu > (R)1 ? (R)1 : (mu < (R)-1 ? (R)-1 : mu);
                         t_mu += (double)mu;
                         n_scat++;
-                        R sn = rsqrt_<R>((R)1 - mu * mu), ph = two_pi * u[3], sp, cp;
+                        R sn = real_sqrt<R>((R)1 - mu * mu), ph = two_pi * u[3], sp, cp;
                         if (sizeof(R) == 4) { float s_, c_; sincosf((float)ph, &s_, &c_); sp = s_; cp = c_; } else { double s_, c_; sincos((double)ph, &s_, &c_); sp = (R)s_; cp = (R)c_; }
                         R nd0, nd1, nd2;
                         if (rabs(d[2]) > (R)0.99999) { nd0 = sn * cp; nd1 = sn * sp; nd2 = d[2] > 0 ? mu : -mu; }
                         else {
-                            R den = rsqrt_<R>((R)1 - d[2] * d[2]);
+                            R den = real_sqrt<R>((R)1 - d[2] * d[2]);
                             nd0 = sn * (d[0] * d[2] * cp - d[1] * sp) / den + d[0] * mu;
                             nd1 = sn * (d[1] * d[2] * cp + d[0] * sp) / den + d[1] * mu;
                             nd2 = -sn * cp * den + d[2] * mu;
                         }
-                        R nn = rsqrt_<R>(nd0 * nd0 + nd1 * nd1 + nd2 * nd2);
+                        R nn = real_sqrt<R>(nd0 * nd0 + nd1 * nd1 + nd2 * nd2);
                         d[0] = nd0 / nn; d[1] = nd1 / nn; d[2] = nd2 / nn;
                     }
                 }

@@ -131,13 +131,13 @@ LT_DEVINL R cosine_sample(V3<R> n, V3<R> d_in, R u0, R u1, V3<R>& out) {
         dx = r * c; dy = r * s;
     }
     R zz = (R)1 - dx * dx - dy * dy;
-    R z = rsqrt_<R>(zz > 0 ? zz : (R)0);
+    R z = real_sqrt<R>(zz > 0 ? zz : (R)0);
     V3<R> v2;
     if (rabs(n.x) > rabs(n.y)) {
-        R s = rsqrt_<R>(n.x * n.x + n.z * n.z);
+        R s = real_sqrt<R>(n.x * n.x + n.z * n.z);
         v2 = mk<R>(-n.z / s, (R)0, n.x / s);
     } else {
-        R s = rsqrt_<R>(n.y * n.y + n.z * n.z);
+        R s = real_sqrt<R>(n.y * n.y + n.z * n.z);
         v2 = mk<R>((R)0, n.z / s, -n.y / s);
     }
     V3<R> v3 = cross(n, v2);
@@ -323,7 +323,7 @@ LT_DEVINL int shade_extension_with(const WalkParams<R>& P, Lane<R>& ln, int prim
         R cos_theta = -(dot(ln.d, n));
         R sq = (R)1 - (Nr * Nr) * ((R)1 - cos_theta * cos_theta);
         if (sq > 0 && rand_0 > reflection_prob) {
-            R k = Nr * cos_theta - rsqrt_<R>(sq);
+            R k = Nr * cos_theta - real_sqrt<R>(sq);
             V3<R> td = normalize(mk<R>(ln.d.x * Nr + n.x * k, ln.d.y * Nr + n.y * k, ln.d.z * Nr + n.z * k));
             ln.o = mk<R>(p.x + (-eps * n.x), p.y + (-eps * n.y), p.z + (-eps * n.z));
             ln.d = td;

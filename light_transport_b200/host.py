@@ -204,7 +204,8 @@ class Renderer:
 
     def render(self, *, width, height, spp, max_depth, camera, f_distance, s0=0, s1=None, semantics="reference",
                traversal="compat", real="f32", rand0=None, rand1=None, light_idx=None, seed=0, rr_start=None,
-               film=None, return_samples=False, pixel_range=None, paths_per_warp=0, image=None, scheduler="megakernel", lbvh_chunk=0):
+               film=None, return_samples=False, pixel_range=None, paths_per_warp=0, image=None, scheduler="megakernel", lbvh_chunk=0,
+               phased=None):
         """One pass of the walk over samples ``[s0,s1)`` of every pixel.  Returns
         ``(film_sum, samples|None, counters)``; ``film`` may be a preallocated float64 buffer (numpy or a
         CUDA tensor / device address of H*W*3 doubles) that is accumulated into."""
@@ -218,6 +219,8 @@ class Renderer:
         p.rr_floor, p.eps, p.f_distance, p.seed = 0.05, _pack_eps(), float(f_distance), int(seed)
         p.paths_per_warp = int(paths_per_warp)
         p.flags = (int(lbvh_chunk) & 0xff) << 8          # LBVH traversal steps per megakernel iteration (0 = default)
+        if phased is not None:                           # phase-aligned iterations: None = chosen from the scene, True / False = forced (A/B)
+            p.flags |= (1 << 17) if phased else (1 << 16)
         cam = np.asarray(camera, dtype=np.float64)
         for k in range(3):
             p.camera[k] = float(cam[k])

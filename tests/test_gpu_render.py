@@ -313,3 +313,21 @@ def test_ragged_and_degenerate_inputs(oracle):
             _, s_g, _ = R1.render(traversal=trav, real="f64", scheduler=sched, return_samples=True, **kw)
             assert (rel_err(s_g, s_o) > REL_TOL).sum() == 0, (trav, sched)
     R1.close()
+
+
+@pytest.mark.parametrize("scene_file", ["lts_scene.npz", "mirror_scene.npz"])
+@pytest.mark.parametrize("trav", ["compat", "nearest"])
+def test_scheduling_policies_do_not_change_paths(R_lts, R_mirror, scene_file, trav):
+    """Phase-aligned iterations, granule size and scheduler only decide WHEN a lane traces and shades: every path's
+    float64 radiance and the ray counts are identical whichever policy runs (the host picks the phase policy from the
+    scene's diffuse share of surface area; here both are forced)."""
+    R = _renderer(scene_file, R_lts, R_mirror)
+    ps, nodes, cam, f = load_scene(scene_file)
+    kw = dict(width=40, height=24, spp=6, max_depth=32, camera=cam, f_distance=f, seed=13, semantics="reference", traversal=trav,
+              real="f64", return_samples=True)
+    _, s_on, c_on = R.render(phased=True, **kw)
+    _, s_off, c_off = R.render(phased=False, **kw)
+    _, s_small, c_small = R.render(paths_per_warp=64, **kw)
+    assert np.array_equal(s_on, s_off) and np.array_equal(s_on, s_small)
+    for k in ("paths", "rays_ext", "rays_shadow", "rays_memo", "max_frames"):
+        assert c_on[k] == c_off[k] == c_small[k], k

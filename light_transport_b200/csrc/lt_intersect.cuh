@@ -95,6 +95,11 @@ LT_DEVINL bool slab(const float* bmin, const float* bmax, V3<float> o, V3<float>
 //     each half rounded exactly like the scalar instruction.
 // 13.5 instructions per leaf instead of 27.5.
 #define LT_SLAB_PAIR_FLOATS 24
+#ifndef LT_SLAB_UNROLL
+#define LT_SLAB_UNROLL 4      // pairs per trip of the leaf-bounds loop; measured on C2: 1: 20.1, 2: 20.0, 4: 20.6, 5: 19.9 Grays/s
+#endif
+#define LT_PRAGMA_(x) _Pragma(#x)
+#define LT_PRAGMA_UNROLL(n) LT_PRAGMA_(unroll n)
 LT_DEVINL int slab_pairs_bytes(int n_leaves) { return ((n_leaves + 1) >> 1) * LT_SLAB_PAIR_FLOATS * 4; }
 
 LT_DEVINL void build_slab_pairs(float* tab, const CompatLeaf<float>* leaves, int n_leaves) {
@@ -132,7 +137,7 @@ LT_DEVINL uint64_t slab_pairs_mask(const float* tab, int n_leaves, V3<float> o, 
     for (int p0 = 0; p0 < n_pairs; p0 += 16) {          // 32 leaves per 32-bit word
         const int pe = min(n_pairs - p0, 16);
         uint32_t m = 0, bit = 1u;
-#pragma unroll 4
+LT_PRAGMA_UNROLL(LT_SLAB_UNROLL)
         for (int q = 0; q < pe; ++q) {
             const int p = p0 + q;
             const float4 X = tx[6 * p], Y = ty[6 * p], Z = tz[6 * p];

@@ -90,7 +90,8 @@ typedef struct {
     int32_t pixel0, pixel1;      /* optional pixel sub-range [pixel0,pixel1) in row-major order; 0,0 = all */
     int32_t paths_per_warp;      /* megakernel work granule; 0 = auto */
     int32_t flags;               /* bits 8-15: LBVH traversal steps per megakernel iteration (0 = default 24);
-                                    bit 16 / bit 17: force phase-aligned iterations off / on (default: from the scene); rest reserved */
+                                    bit 16 / bit 17: force phase-aligned iterations off / on (default: from the scene);
+                                    bits 20-23: resident CTAs per SM of the LBVH walk (0 = default); rest reserved */
 } lt_render_params;
 
 typedef struct {
@@ -103,12 +104,19 @@ typedef struct {
 } lt_counters;
 
 typedef struct {
-    int32_t n_prims, n_nodes, max_depth, reserved;
+    int32_t n_prims, n_nodes;    /* triangles; 8-wide nodes of the traversal hierarchy */
+    int32_t max_depth;           /* levels of the 8-wide hierarchy (= traversal stack entries needed) */
+    int32_t binary_depth;        /* depth of the Karras tree it was collapsed from */
     float build_ms;              /* device time of the whole build */
     float sort_ms;
     double root_bmin[3], root_bmax[3];
-    double sah_cost;
+    double sah_cost;             /* (sum over wide nodes of area(node) + sum over leaf slots of area(slot) * triangles) / area(root) */
+    float collapse_ms;           /* of build_ms: collapse + quantise + triangle records */
+    float reserved;
+    int64_t bytes;               /* nodes (80 B) + float32 triangle records (48 B): what a float32 traversal touches */
 } lt_bvh_stats;
+/* lt_bvh_build flags */
+#define LT_BVH_KEEP_BINARY 1     /* also keep the binary (Karras) nodes: A/B arm of the traversal, build variant LT_WIDE=0 */
 
 int lt_init(int device, lt_ctx **out);
 void lt_destroy(lt_ctx *);
@@ -179,8 +187,12 @@ int lt_medium_walk(lt_ctx *, const lt_medium_params *, uint64_t n_photons, uint6
                    lt_medium_totals *totals, float *kernel_ms);
 double lt_henyey_greenstein(double cos_theta, double g);
 
-/* measured FP32 FMA throughput of this device (TFLOP/s), for the roofline denominator */
+/* roofline denominators measured on this device: FP32 / FP64 FMA throughput (TFLOP/s), and the L2 -> SM bandwidth (GB/s) of
+ * 128-bit gathers of `granule_bytes` from a `buffer_bytes` buffer that fits the L2 (mode 0: streaming, 1: one random granule
+ * per lane - the access pattern of an incoherent hierarchy traversal) */
 int lt_measure_fp32_peak(lt_ctx *, double *tflops);
+int lt_measure_fp64_peak(lt_ctx *, double *tflops);
+int lt_measure_l2_bandwidth(lt_ctx *, int64_t buffer_bytes, int granule_bytes, int mode, double *gbs);
 
 const char *lt_last_error(void);
 const char *lt_version(void);

@@ -118,6 +118,7 @@ static void fill_view(const lt_scene* s, SceneView<R>& v) {
     v.nleaves = a.nleaves;
     v.n_nleaves = a.nleaves ? s->n_nleaves : 0;
     v.lbvh = s->lbvh_nodes;
+    v.wnodes = s->wnodes; v.wtris = s->wtris; v.wleaf_prims = s->wleaf_prims; v.wbvh_depth = s->wbvh_depth;
     v.n_tris = s->n_tris; v.n_mats = s->n_mats; v.n_lights = s->n_lights;
     v.n_cnodes = s->n_cnodes; v.n_cleaves = s->n_cleaves; v.n_lbvh_nodes = s->n_lbvh_nodes;
     v.n_cflat = s->n_cflat;
@@ -264,7 +265,7 @@ static size_t staged_bytes(const lt_scene* s, int trav, int real) {
     size_t mat = r == 8 ? sizeof(MatRec<double>) : sizeof(MatRec<float>);
     size_t nod = r == 8 ? sizeof(CompatNode<double>) : sizeof(CompatNode<float>);
     size_t lef = r == 8 ? sizeof(CompatLeaf<double>) : sizeof(CompatLeaf<float>);
-    if (trav == LT_TRAV_LBVH) return 0;
+    if (trav == LT_TRAV_LBVH) return LT_WIDE ? (size_t)std::max(s->wbvh_depth, 1) * LT_BLOCK * sizeof(uint2) : 0;   // traversal stacks
     size_t b = al(tri * s->n_tris) + al(mat * s->n_mats);
     if (trav == LT_TRAV_COMPAT) b += al(nod * s->n_cnodes) + al(lef * s->n_cleaves);
     if (trav == LT_TRAV_COMPAT && r == 4) b += al((size_t)((s->n_cleaves + 1) / 2) * 96) + (8 * 4 * 12 * 4 + 32);   // slab_pairs_bytes + LT_CHAIN_BYTES
@@ -278,7 +279,7 @@ static int check_traversal(const lt_scene* s, int trav) {
     if (trav == LT_TRAV_COMPAT) {
         if (s->n_cnodes == 0) { set_error("COMPAT traversal needs lt_scene_set_compat_bvh"); return LT_E_NO_BVH; }
     } else if (trav == LT_TRAV_LBVH) {
-        if (!s->lbvh_nodes && s->n_tris > 1) { set_error("LBVH traversal needs lt_bvh_build"); return LT_E_NO_BVH; }
+        if (!s->wtris) { set_error("LBVH traversal needs lt_bvh_build"); return LT_E_NO_BVH; }
     } else if (trav != LT_TRAV_NEAREST) {
         set_error("unknown traversal %d", trav);
         return LT_E_INVALID;
@@ -359,8 +360,8 @@ static int do_render(lt_scene* s, const lt_render_params* p, const double* rand0
     P.film = bf.dev; P.samples = bs.dev;
     P.counters = reinterpret_cast<unsigned long long*>(ctx->d_counters);
 
-    const size_t staged = staged_bytes(s, p->traversal, p->real);
     const bool wavefront = p->scheduler == LT_SCHED_WAVEFRONT;
+    const size_t staged = (wavefront && p->traversal == LT_TRAV_LBVH) ? 0 : staged_bytes(s, p->traversal, p->real);
     const size_t smem = wavefront ? wavefront_smem_bytes<R>(staged) : staged;
     if (smem > (size_t)ctx->prop.sharedMemPerBlockOptin) {
         set_error("scene needs %zu B of shared memory for traversal %d; use LT_TRAV_LBVH for large scenes", smem, p->traversal);
@@ -370,6 +371,7 @@ static int do_render(lt_scene* s, const lt_render_params* p, const double* rand0
     if (wavefront) { if ((rc = wavefront_kernel_attrs<R>(p->traversal, p->semantics, &regs, &bps, smem))) return rc; }
     else if ((rc = walk_kernel_attrs<R>(p->traversal, p->semantics, &regs, &local_bytes, &bps, smem))) return rc;
     if (bps < 1) bps = 1;
+    if (((p->flags >> 20) & 0xf) && !wavefront) bps = std::min(bps, (p->flags >> 20) & 0xf);     // A/B: fewer resident CTAs per SM
     const int block = wavefront ? WfCfg<R>::NT : LT_BLOCK;
     int grid = ctx->prop.multiProcessorCount * bps;
     int64_t ppw = p->paths_per_warp;
@@ -392,7 +394,7 @@ static int do_render(lt_scene* s, const lt_render_params* p, const double* rand0
         if (granules < nwarps) grid = (int)std::max<int64_t>(1, (granules * 32 + block - 1) / block);
     }
     P.paths_per_warp = (int32_t)ppw;
-    P.lbvh_chunk = ((p->flags >> 8) & 0xff) ? ((p->flags >> 8) & 0xff) : 24;
+    P.lbvh_chunk = ((p->flags >> 8) & 0xff) ? ((p->flags >> 8) & 0xff) : (LT_WIDE ? 8 : 24);
     // phase-aligned iterations pay where most extension hits spawn a shadow query (flags bit 16 / 17 force off / on: A/B runs)
     P.phased = (p->flags & (1 << 17)) ? 1 : (p->flags & (1 << 16)) ? 0 : (s->diffuse_area_share >= 0.5 ? 1 : 0);
     // suspended-frame storage for REFERENCE walks: a frame at stack depth k has bounce >= k and can still
@@ -530,6 +532,36 @@ __global__ void fma_peak_kernel(float* out, int iters) {
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
 
+__global__ void fma64_peak_kernel(double* out, int iters) {
+    double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 0.999, b = 1e-3;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, b); a1 = fma(a1, m, b); a2 = fma(a2, m, b); a3 = fma(a3, m, b);
+        a4 = fma(a4, m, b); a5 = fma(a5, m, b); a6 = fma(a6, m, b); a7 = fma(a7, m, b);
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// L2 -> SM bandwidth of the access pattern a hierarchy traversal makes: every thread gathers `granule` bytes (a multiple of
+// 16, as 128-bit ld.global.cg loads that bypass L1) from pseudo-random granule-aligned offsets of a buffer that fits the L2.
+// mode 0: consecutive lanes read consecutive granules (streaming); mode 1: every lane its own random granule (incoherent).
+__global__ void l2_gather_kernel(const uint4* __restrict__ buf, uint32_t n_granules, int words, int iters, int mode, uint4* __restrict__ sink) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+    uint4 acc = make_uint4(0, 0, 0, 0);
+    uint32_t x = tid * 2654435761u + 12345u;
+    for (int it = 0; it < iters; ++it) {
+        uint32_t g;
+        if (mode == 0) g = (uint32_t)(((uint64_t)it * nthreads + tid) % n_granules);
+        else { x ^= x << 13; x ^= x >> 17; x ^= x << 5; g = x % n_granules; }
+        const uint4* p = buf + (size_t)g * words;
+        for (int w = 0; w < words; ++w) {
+            const uint4 v = __ldcg(p + w);
+            acc.x ^= v.x; acc.y ^= v.y; acc.z ^= v.z; acc.w ^= v.w;
+        }
+    }
+    if ((acc.x ^ acc.y ^ acc.z ^ acc.w) == 0x9e3779b9u) sink[tid & 1023] = acc;     // keeps the loads alive
+}
+
 }  // namespace lt
 
 using namespace lt;
@@ -664,6 +696,9 @@ void lt_scene_destroy(lt_scene* s) {
     s->f32.release();
     s->f64.release();
     if (s->lbvh_nodes) lt_dev_free(s->lbvh_nodes);
+    if (s->wnodes) lt_dev_free(s->wnodes);
+    if (s->wtris) lt_dev_free(s->wtris);
+    if (s->wleaf_prims) lt_dev_free(s->wleaf_prims);
     if (s->d_v0) lt_dev_free(s->d_v0);
     if (s->d_v1) lt_dev_free(s->d_v1);
     if (s->d_v2) lt_dev_free(s->d_v2);
@@ -809,6 +844,62 @@ int lt_film_finalize(lt_ctx* ctx, const double* film_sum, int64_t n, int64_t spp
     LT_CUDA_OK(cudaGetLastError());
     if ((rc = out.finish(st))) return rc;
     LT_CUDA_OK(cudaStreamSynchronize(st));
+    return LT_OK;
+}
+
+int lt_measure_fp64_peak(lt_ctx* ctx, double* tflops) {
+    if (!ctx || !tflops) { set_error("null argument"); return LT_E_INVALID; }
+    LT_CUDA_OK(cudaSetDevice(ctx->device));
+    const int blocks = ctx->prop.multiProcessorCount * 8, threads = 256, iters = 1 << 13;
+    double* d = nullptr;
+    LT_CUDA_OK(lt_dev_malloc(&d, (size_t)blocks * threads * sizeof(double)));
+    fma64_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(d, 1 << 8);
+    double best = 0;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(ctx->ev0, ctx->stream);
+        fma64_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(d, iters);
+        cudaEventRecord(ctx->ev1, ctx->stream);
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        float ms = 0;
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+        if (e != cudaSuccess) { lt_dev_free(d); LT_CUDA_OK(e); }
+        best = std::max(best, 2.0 * 8.0 * iters * (double)blocks * threads / (ms * 1e-3) / 1e12);
+    }
+    lt_dev_free(d);
+    *tflops = best;
+    return LT_OK;
+}
+
+int lt_measure_l2_bandwidth(lt_ctx* ctx, int64_t buffer_bytes, int granule_bytes, int mode, double* gbs) {
+    if (!ctx || !gbs || buffer_bytes < (1 << 20) || granule_bytes < 16 || granule_bytes % 16 || (mode != 0 && mode != 1)) {
+        set_error("lt_measure_l2_bandwidth: bad argument");
+        return LT_E_INVALID;
+    }
+    LT_CUDA_OK(cudaSetDevice(ctx->device));
+    const int words = granule_bytes / 16;
+    const uint32_t n_granules = (uint32_t)(buffer_bytes / granule_bytes);
+    uint4 *buf = nullptr, *sink = nullptr;
+    LT_CUDA_OK(lt_dev_malloc(&buf, (size_t)n_granules * granule_bytes));
+    if (lt_dev_malloc(&sink, 1024 * sizeof(uint4)) != cudaSuccess) { lt_dev_free(buf); set_error("out of memory"); return LT_E_CUDA; }
+    const int blocks = ctx->prop.multiProcessorCount * 8, threads = 256;
+    const int iters = (int)std::max<int64_t>(64, (int64_t)(4ll << 30) / ((int64_t)blocks * threads * granule_bytes));   // ~4 GB per launch
+    cudaMemsetAsync(buf, 1, (size_t)n_granules * granule_bytes, ctx->stream);
+    l2_gather_kernel<<<blocks, threads, 0, ctx->stream>>>(buf, n_granules, words, iters, mode, sink);   // warms the L2
+    double best = 0;
+    cudaError_t e = cudaSuccess;
+    for (int rep = 0; rep < 3 && e == cudaSuccess; ++rep) {
+        cudaEventRecord(ctx->ev0, ctx->stream);
+        l2_gather_kernel<<<blocks, threads, 0, ctx->stream>>>(buf, n_granules, words, iters, mode, sink);
+        cudaEventRecord(ctx->ev1, ctx->stream);
+        e = cudaStreamSynchronize(ctx->stream);
+        float ms = 0;
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+        if (e == cudaSuccess) best = std::max(best, (double)iters * blocks * threads * granule_bytes / (ms * 1e-3) / 1e9);
+    }
+    lt_dev_free(buf);
+    lt_dev_free(sink);
+    LT_CUDA_OK(e);
+    *gbs = best;
     return LT_OK;
 }
 

@@ -522,7 +522,7 @@ struct LbvhState {
 };
 
 template <typename R>
-LT_DEVINL void lbvh_begin(LbvhState<R>& s, int n_tris, R tlimit, bool live) {
+LT_DEVINL void lbvh2_begin(LbvhState<R>& s, int n_tris, R tlimit, bool live) {
     s.prim = -1;
     s.best = tlimit;
     s.sp = 0;
@@ -532,7 +532,7 @@ LT_DEVINL void lbvh_begin(LbvhState<R>& s, int n_tris, R tlimit, bool live) {
 // Runs at most `max_steps` warp-voted steps (every lane of `amask` must call it, finished or idle lanes
 // with cur == LT_LBVH_DONE).  Returns when all lanes are done or the budget is used up.
 template <typename R>
-LT_DEVINL void lbvh_run(unsigned amask, LbvhState<R>& s, int* stack, const LbvhNode* __restrict__ nodes,
+LT_DEVINL void lbvh2_run(unsigned amask, LbvhState<R>& s, int* stack, const LbvhNode* __restrict__ nodes,
                         const TriRec<R>* __restrict__ tris, V3<R> o, V3<R> d, V3<R> inv, R eps, bool anyhit, int skip, Stats& st,
                         int max_steps) {
     // (dropping stale stack entries at pop time — entry distance kept beside the node — was measured:
@@ -573,15 +573,247 @@ LT_DEVINL void lbvh_run(unsigned amask, LbvhState<R>& s, int* stack, const LbvhN
 }
 
 template <typename R>
-LT_DEVINL void lbvh_query(unsigned amask, const LbvhNode* __restrict__ nodes, const TriRec<R>* __restrict__ tris, int n_tris,
+LT_DEVINL void lbvh2_query(unsigned amask, const LbvhNode* __restrict__ nodes, const TriRec<R>* __restrict__ tris, int n_tris,
                           V3<R> o, V3<R> d, R eps, R tlimit, bool anyhit, int skip, int& prim, R& best, Stats& st) {
     int stack[LT_LBVH_STACK];
     LbvhState<R> s;
-    lbvh_begin<R>(s, n_tris, tlimit, true);
+    lbvh2_begin<R>(s, n_tris, tlimit, true);
     V3<R> inv = mk<R>((R)1 / d.x, (R)1 / d.y, (R)1 / d.z);
-    lbvh_run<R>(amask, s, stack, nodes, tris, o, d, inv, eps, anyhit, skip, st, 0x7fffffff);
+    lbvh2_run<R>(amask, s, stack, nodes, tris, o, d, inv, eps, anyhit, skip, st, 0x7fffffff);
     prim = s.prim;
     best = s.best;
+}
+
+// ---- 8-wide compressed hierarchy (WNode / WTri, lt_scene.cuh) -------------------------------------------------------
+// Same query semantics as the binary LBVH above (true closest hit, eps < t < tlimit, ties -> lowest primitive index), on
+// the hierarchy lt_bvh_build collapses from the Karras tree.  Per-lane state is two 64-bit GROUPS:
+//   G = (child_base, hits << 24 | imask)   interior children of one node still to visit
+//   T = (tri_base, triangle hit bits)      triangles of one node's leaf slots still to test
+// and a stack of postponed groups (8 bytes per wide level) that lives in SHARED memory in the walk and intersect kernels
+// (entry k of a lane at stack[k * stride], so a warp's access is one conflict-free 256-byte row).
+// A node step fetches ONE 80-byte node and decides all eight children; children are ordered front to back by the ray's
+// direction octant without any sorting: slot s is visited in descending order of s ^ (7 ^ octant) because the builder
+// placed each child in the slot whose diagonal it lies furthest along.
+// Every iteration the warp votes between a node step and a triangle step (as the binary traversal does).
+template <typename R>
+struct WState {
+    uint2 G, T;
+    int sp;                   // stack entries in use; < 0: no query in flight
+    int prim, leaf;           // best primitive so far and its position in the leaf-ordered triangle array
+    R best;
+};
+#ifndef LT_WBVH_TRI_WEIGHT
+#define LT_WBVH_TRI_WEIGHT 2  // a triangle step runs when (lanes waiting for one) * weight >= lanes waiting for a node step
+#endif
+
+template <typename R>
+LT_DEVINL void wbvh_begin(WState<R>& s, int n_tris, R tlimit, bool live) {
+    s.prim = -1; s.leaf = -1;
+    s.best = tlimit;
+    s.sp = live ? 0 : -1;
+    s.G = make_uint2(0u, (live && n_tris > 1) ? 0x80000000u : 0u);     // the root: "slot 7 ^ octinv" of a virtual parent
+    s.T = make_uint2(0u, (live && n_tris == 1) ? 1u : 0u);             // a single triangle has no node
+}
+
+LT_DEVINL uint32_t octinv_of(V3<float> inv) {
+    return 7u ^ ((__float_as_uint(inv.x) >> 31) | ((__float_as_uint(inv.y) >> 31) << 1) | ((__float_as_uint(inv.z) >> 31) << 2));
+}
+LT_DEVINL uint32_t octinv_of(V3<double> inv) {
+    return 7u ^ ((uint32_t)(__double2hiint(inv.x) >> 31 & 1) | ((uint32_t)(__double2hiint(inv.y) >> 31 & 1) << 1) |
+                 ((uint32_t)(__double2hiint(inv.z) >> 31 & 1) << 2));
+}
+
+// hit word of a node from the eight per-child hit flags: interior children land on bit 24 + (slot ^ octinv), a leaf slot
+// on `count` bits from its triangle offset (Ylitie et al. 2017, section 4.3)
+LT_DEVINL uint32_t whit_bits(uint32_t meta4, uint32_t octinv4, uint32_t hit4 /* 0x01 per hit child byte */) {
+    const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;          // bits 3 and 4 both set: 24..31
+    const uint32_t inner_mask4 = (is_inner4 >> 4) * 7u;                       // 0x07 in the bytes of interior children
+    const uint32_t bit_index4 = (meta4 ^ (octinv4 & inner_mask4)) & 0x1f1f1f1fu;
+    const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+    uint32_t m = 0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+        if ((hit4 >> (8 * c)) & 1u) m |= ((child_bits4 >> (8 * c)) & 0xffu) << ((bit_index4 >> (8 * c)) & 0xffu);
+    return m;
+}
+
+// float32 node step.  A quantised plane q of axis k decodes, and turns into a ray distance, in ONE byte-permute and ONE
+// fused multiply-add: prmt drops the byte into bits 16..23 of the float 0x4B000000 (= 2^23 + q * 2^16), so
+//     t = f * A + B,   A = 2^(e-16) / d,   B = (p - 128 * 2^e - o) / d
+// (the constant 2^23 of the pattern is folded into B).  Rounding: |error(t)| <= ~2e-7 * (|t| + 2.5 * node extent / |d_k|);
+// the relative part is covered by the reference's (1 + 2 gamma_3) widening of the far distance, the absolute part by the
+// 2 % of a quantum (= 8e-5 node extents) the builder adds to every quantised plane.  A zero direction component gives
+// NaN distances, which fminf / fmaxf drop: the axis does not constrain the ray (conservative).
+LT_DEVINL void wnode_step(const WNode* __restrict__ nodes, uint32_t idx, V3<float> o, V3<float> inv, float best, uint32_t octinv, uint2& G, uint2& T) {
+    const uint4* p = reinterpret_cast<const uint4*>(nodes + idx);
+    const uint4 w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2), w3 = __ldg(p + 3), w4 = __ldg(p + 4);
+    const float widen = 1.0f + 2.0f * ((3.0f * 5.9604644775390625e-08f) / (1.0f - 3.0f * 5.9604644775390625e-08f));
+    const float sx = __uint_as_float(((w0.w & 0xffu) - 16u) << 23), sy = __uint_as_float((((w0.w >> 8) & 0xffu) - 16u) << 23),
+                sz = __uint_as_float((((w0.w >> 16) & 0xffu) - 16u) << 23);
+    const float Ax = sx * inv.x, Ay = sy * inv.y, Az = sz * inv.z;
+    const float Bx = (__uint_as_float(w0.x) - sx * 8388608.0f - o.x) * inv.x, By = (__uint_as_float(w0.y) - sy * 8388608.0f - o.y) * inv.y,
+                Bz = (__uint_as_float(w0.z) - sz * 8388608.0f - o.z) * inv.z;
+    const bool ngx = inv.x < 0.0f, ngy = inv.y < 0.0f, ngz = inv.z < 0.0f;
+    const float bw = best * widen;
+    uint32_t hitmask = 0;
+    const uint32_t octinv4 = octinv * 0x01010101u;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {                       // children 0..3, 4..7
+        const uint32_t nx = h ? (ngx ? w2.w : w2.y) : (ngx ? w2.z : w2.x), fx = h ? (ngx ? w2.y : w2.w) : (ngx ? w2.x : w2.z);
+        const uint32_t ny = h ? (ngy ? w3.w : w3.y) : (ngy ? w3.z : w3.x), fy = h ? (ngy ? w3.y : w3.w) : (ngy ? w3.x : w3.z);
+        const uint32_t nz = h ? (ngz ? w4.w : w4.y) : (ngz ? w4.z : w4.x), fz = h ? (ngz ? w4.y : w4.w) : (ngz ? w4.x : w4.z);
+        uint32_t hit4 = 0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const uint32_t sel = 0x7044u | ((uint32_t)c << 8);
+            const float tnx = fmaf(__uint_as_float(__byte_perm(nx, 0x4B000000u, sel)), Ax, Bx), tfx = fmaf(__uint_as_float(__byte_perm(fx, 0x4B000000u, sel)), Ax, Bx);
+            const float tny = fmaf(__uint_as_float(__byte_perm(ny, 0x4B000000u, sel)), Ay, By), tfy = fmaf(__uint_as_float(__byte_perm(fy, 0x4B000000u, sel)), Ay, By);
+            const float tnz = fmaf(__uint_as_float(__byte_perm(nz, 0x4B000000u, sel)), Az, Bz), tfz = fmaf(__uint_as_float(__byte_perm(fz, 0x4B000000u, sel)), Az, Bz);
+            const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));
+            const float tf = fminf(fminf(fminf(tfx, tfy), tfz) * widen, bw);
+            if (tn <= tf) hit4 |= 1u << (8 * c);
+        }
+        hitmask |= whit_bits(h ? w1.w : w1.z, octinv4, hit4);
+    }
+    G = make_uint2(w1.x, (hitmask & 0xff000000u) | (w0.w >> 24));
+    T = make_uint2(w1.y, hitmask & 0x00ffffffu);
+}
+
+// float64 node step (parity path): planes decoded exactly (p + q * 2^e is exact in double), slab test as in the binary tree
+LT_DEVINL void wnode_step(const WNode* __restrict__ nodes, uint32_t idx, V3<double> o, V3<double> inv, double best, uint32_t octinv, uint2& G, uint2& T) {
+    const uint4* p = reinterpret_cast<const uint4*>(nodes + idx);
+    const uint4 w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2), w3 = __ldg(p + 3), w4 = __ldg(p + 4);
+    const double px = (double)__uint_as_float(w0.x), py = (double)__uint_as_float(w0.y), pz = (double)__uint_as_float(w0.z);
+    const double sx = (double)__uint_as_float((w0.w & 0xffu) << 23), sy = (double)__uint_as_float(((w0.w >> 8) & 0xffu) << 23),
+                 sz = (double)__uint_as_float(((w0.w >> 16) & 0xffu) << 23);
+    const uint32_t qw[3][4] = {{w2.x, w2.y, w2.z, w2.w}, {w3.x, w3.y, w3.z, w3.w}, {w4.x, w4.y, w4.z, w4.w}};
+    uint32_t hitmask = 0;
+    const uint32_t octinv4 = octinv * 0x01010101u;
+    for (int h = 0; h < 2; ++h) {
+        uint32_t hit4 = 0;
+        const uint32_t meta4 = h ? w1.w : w1.z;
+        for (int c = 0; c < 4; ++c) {
+            if (((meta4 >> (8 * c)) & 0xffu) == 0u) continue;
+            const int sh = 8 * c;
+            const double lx = px + (double)((qw[0][h] >> sh) & 0xffu) * sx, hx = px + (double)((qw[0][2 + h] >> sh) & 0xffu) * sx;
+            const double ly = py + (double)((qw[1][h] >> sh) & 0xffu) * sy, hy = py + (double)((qw[1][2 + h] >> sh) & 0xffu) * sy;
+            const double lz = pz + (double)((qw[2][h] >> sh) & 0xffu) * sz, hz = pz + (double)((qw[2][2 + h] >> sh) & 0xffu) * sz;
+            double tn;
+            if (slab_t<double>(lx, ly, lz, hx, hy, hz, o, inv, best, tn)) hit4 |= 1u << sh;
+        }
+        hitmask |= whit_bits(meta4, octinv4, hit4);
+    }
+    G = make_uint2(w1.x, (hitmask & 0xff000000u) | (w0.w >> 24));
+    T = make_uint2(w1.y, hitmask & 0x00ffffffu);
+}
+
+// triangle of the leaf-ordered array: float32 tests the compact record, float64 the full record of the primitive
+LT_DEVINL bool wtri_test(const WTri* __restrict__ wtris, const int32_t* __restrict__, const TriRec<float>* __restrict__, uint32_t ti, V3<float> o,
+                         V3<float> d, float& t_out, int& prim) {
+    const float4* p = reinterpret_cast<const float4*>(wtris + ti);
+    const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+    const float eps = 0.0000001f;
+    const V3<float> v0 = mk<float>(a.x, a.y, a.z), ab = mk<float>(b.x, b.y, b.z), ac = mk<float>(c.x, c.y, c.z);
+    prim = __float_as_int(a.w);
+    const V3<float> pvec = cross(d, ac);
+    const float det = dot(ab, pvec);
+    const float inv_det = 1.0f / det;
+    const V3<float> tvec = o - v0;
+    const float u = dot(tvec, pvec) * inv_det;
+    const V3<float> qvec = cross(tvec, ab);
+    const float v = dot(d, qvec) * inv_det;
+    const float t = dot(ac, qvec) * inv_det;
+    const bool miss = (fabsf(det) <= eps * b.w) | ((-eps < det) & (det < eps)) | (u < 0) | (u > 1) | (v < 0) | (u + v > 1);
+    t_out = t;
+    return !miss & (t > eps);
+}
+LT_DEVINL bool wtri_test(const WTri* __restrict__, const int32_t* __restrict__ leaf_prims, const TriRec<double>* __restrict__ tris, uint32_t ti,
+                         V3<double> o, V3<double> d, double& t_out, int& prim) {
+    prim = __ldg(leaf_prims + ti);
+    return tri_intersect(tris[prim], o, d, t_out);
+}
+
+// Runs at most `max_steps` warp-voted steps (every lane of `amask` calls it; lanes without a query have sp < 0).
+template <typename R>
+LT_DEVINL void wbvh_run(unsigned amask, WState<R>& s, uint2* stack, int stride, const WNode* __restrict__ nodes, const WTri* __restrict__ wtris,
+                        const int32_t* __restrict__ leaf_prims, const TriRec<R>* __restrict__ tris, V3<R> o, V3<R> d, V3<R> inv, R eps, bool anyhit,
+                        int skip, Stats& st, int max_steps) {
+    const uint32_t octinv = octinv_of(inv);
+    for (int step = 0; step < max_steps; ++step) {
+        const bool live = s.sp >= 0;
+        const bool want_tri = live & (s.T.y != 0u);
+        const bool want_node = live & !want_tri & ((s.G.y & 0xff000000u) != 0u);
+        const unsigned nm = __ballot_sync(amask, want_node), tm = __ballot_sync(amask, want_tri);
+        if (!(nm | tm)) break;
+        if (__popc(tm) * LT_WBVH_TRI_WEIGHT >= __popc(nm)) {
+            if (want_tri) {
+                const uint32_t j = (uint32_t)__ffs((int)s.T.y) - 1u;
+                s.T.y &= s.T.y - 1u;
+                const uint32_t ti = s.T.x + j;
+                R t;
+                int k;
+                st.tri_tests++;
+                const bool h = wtri_test(wtris, leaf_prims, tris, ti, o, d, t, k);
+                if (h & (k != skip) & (eps < t) & ((t < s.best) | ((t == s.best) & (k < s.prim)))) {
+                    s.best = t;
+                    s.prim = k;
+                    s.leaf = (int)ti;
+                }
+                if (anyhit && s.prim >= 0) { s.sp = -1; s.G.y = 0u; s.T.y = 0u; }
+            }
+        } else if (want_node) {
+            const uint32_t hits = s.G.y;
+            const uint32_t bit = 31u - (uint32_t)__clz((int)hits);
+            const uint32_t rest = hits & ~(1u << bit);
+            const uint32_t slot = (bit - 24u) ^ octinv;
+            const uint32_t idx = s.G.x + (uint32_t)__popc(hits & 0xffu & ~(0xffffffffu << slot));
+            if (rest & 0xff000000u) { stack[s.sp * stride] = make_uint2(s.G.x, rest); s.sp++; }
+            st.box_tests += 8;
+            wnode_step(nodes, idx, o, inv, s.best, octinv, s.G, s.T);
+        }
+        // a lane that has nothing left in hand takes the next postponed group, or is done
+        if (s.sp >= 0 && s.T.y == 0u && !(s.G.y & 0xff000000u)) {
+            if (s.sp > 0) {
+                s.sp--;
+                const uint2 e = stack[s.sp * stride];
+                if (e.y & 0xff000000u) s.G = e; else s.T = e;
+            } else {
+                s.sp = -1;
+            }
+        }
+    }
+}
+
+template <typename R>
+LT_DEVINL void wbvh_query(unsigned amask, uint2* stack, int stride, const WNode* __restrict__ nodes, const WTri* __restrict__ wtris,
+                          const int32_t* __restrict__ leaf_prims, const TriRec<R>* __restrict__ tris, int n_tris, V3<R> o, V3<R> d, R eps, R tlimit,
+                          bool anyhit, int skip, int& prim, R& best, int& leaf, Stats& st) {
+    WState<R> s;
+    wbvh_begin<R>(s, n_tris, tlimit, true);
+    V3<R> inv = mk<R>((R)1 / d.x, (R)1 / d.y, (R)1 / d.z);
+    wbvh_run<R>(amask, s, stack, stride, nodes, wtris, leaf_prims, tris, o, d, inv, eps, anyhit, skip, st, 0x7fffffff);
+    prim = s.prim;
+    best = s.best;
+    leaf = s.leaf;
+}
+
+// LT_WIDE: 1 = the 8-wide compressed hierarchy (shipped), 0 = the binary Karras tree (A/B build variant; needs
+// lt_bvh_build(..., LT_BVH_KEEP_BINARY, ...))
+#ifndef LT_WIDE
+#define LT_WIDE 1
+#endif
+
+// whole-query form with a thread-local stack (record / wavefront / explicit-ray kernels)
+template <typename R>
+LT_DEVINL void lbvh_query(unsigned amask, const SceneView<R>& S, const TriRec<R>* __restrict__ tris, V3<R> o, V3<R> d, R eps, R tlimit, bool anyhit,
+                          int skip, int& prim, R& best, Stats& st) {
+#if LT_WIDE
+    uint2 stack[LT_WBVH_MAX_DEPTH];
+    int leaf;
+    wbvh_query<R>(amask, stack, 1, S.wnodes, S.wtris, S.wleaf_prims, tris, S.n_tris, o, d, eps, tlimit, anyhit, skip, prim, best, leaf, st);
+#else
+    lbvh2_query<R>(amask, S.lbvh, tris, S.n_tris, o, d, eps, tlimit, anyhit, skip, prim, best, st);
+#endif
 }
 
 }  // namespace lt

@@ -7,7 +7,15 @@
 //      the scatter ranks keys with warp match_any so it is stable without atomics
 //   4. Karras 2012 hierarchy (one thread per internal node; ties broken by position)
 //   5. bottom-up refit with per-node arrival counters
-//   6. emit 64-byte nodes that carry both child boxes (four 128-bit loads per visited node)
+//   6. collapse the binary tree top-down, level by level, into an 8-wide hierarchy: a wide node starts from the two
+//      children of its binary node and keeps opening the child with the largest surface area until it holds eight
+//      (subtrees of <= 3 triangles become leaf slots); children are assigned to slots by direction octant so that a
+//      traversal visits them front to back with bit arithmetic only; child boxes are quantised to 8 bits per plane on the
+//      node's own grid -> 80-byte nodes (WNode) in breadth-first order, 48-byte float32 triangle records (WTri) in LEAF
+//      order, and a leaf-order -> primitive index for the float64 traversal.
+// Primitives that are large against the scene (extent > 1/16 of the scene's) get the top key bit: the Karras root then
+// splits the large ones from the rest, and a handful of wall-sized triangles no longer inflate the boxes of every
+// ancestor they would otherwise share with a fine mesh.
 #include <algorithm>
 #include <cfloat>
 #include <cstring>
@@ -84,11 +92,14 @@ LT_DEVINL uint64_t spread21(uint64_t x) {   // insert two zero bits after each o
     return x;
 }
 
+#define LB_BIG_FRACTION (1.0f / 16.0f)
 __global__ void morton_kernel(const Box* __restrict__ boxes, int n, const float* __restrict__ cb, uint64_t* __restrict__ keys,
                               uint32_t* __restrict__ vals) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint64_t code = 0;
+    const float scene_ext = fmaxf(fmaxf(cb[3] - cb[0], cb[4] - cb[1]), cb[5] - cb[2]);
+    float prim_ext = 0.f;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         float cen = 0.5f * (boxes[i].lo[k] + boxes[i].hi[k]);
@@ -96,7 +107,9 @@ __global__ void morton_kernel(const Box* __restrict__ boxes, int n, const float*
         float u = ext > 0.f ? (cen - cb[k]) / ext : 0.f;
         uint64_t q = (uint64_t)fminf(fmaxf(u * 2097152.0f, 0.f), 2097151.0f);
         code |= spread21(q) << (2 - k);
+        prim_ext = fmaxf(prim_ext, boxes[i].hi[k] - boxes[i].lo[k]);
     }
+    if (prim_ext > LB_BIG_FRACTION * scene_ext) code |= 1ull << 63;     // large primitives: their own subtree under the root
     keys[i] = code;
     vals[i] = (uint32_t)i;
 }
@@ -197,7 +210,8 @@ LT_DEVINL int delta(const uint64_t* __restrict__ keys, int n, int i, int j) {
 
 // children encoding in build arrays: >= 0 internal node, < 0 leaf at sorted position ~c
 __global__ void karras_kernel(const uint64_t* __restrict__ keys, int n, int* __restrict__ left, int* __restrict__ right,
-                              int* __restrict__ parent_internal, int* __restrict__ parent_leaf) {
+                              int* __restrict__ parent_internal, int* __restrict__ parent_leaf, int* __restrict__ rng_lo,
+                              int* __restrict__ rng_hi) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
     int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
@@ -220,6 +234,8 @@ __global__ void karras_kernel(const uint64_t* __restrict__ keys, int n, int* __r
     int rc = (hi == gamma + 1) ? ~(gamma + 1) : gamma + 1;
     left[i] = lc;
     right[i] = rc;
+    rng_lo[i] = lo;          // the node covers sorted positions [lo, hi]
+    rng_hi[i] = hi;
     if (lc >= 0) parent_internal[lc] = i; else parent_leaf[~lc] = i;
     if (rc >= 0) parent_internal[rc] = i; else parent_leaf[~rc] = i;
     if (i == 0) parent_internal[0] = -1;
@@ -235,11 +251,10 @@ LT_DEVINL Box load_box_cg(const Box* p) {
 }
 __global__ void refit_kernel(const Box* __restrict__ prim_boxes, const uint32_t* __restrict__ sorted_prim, int n, const int* __restrict__ left,
                              const int* __restrict__ right, const int* __restrict__ parent_internal, const int* __restrict__ parent_leaf,
-                             Box* __restrict__ node_boxes, int* __restrict__ arrive, int* __restrict__ max_depth) {
+                             Box* __restrict__ node_boxes, int* __restrict__ arrive) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int node = parent_leaf[i];
-    int depth = 1;
     while (node >= 0) {
         __threadfence();
         if (atomicAdd(&arrive[node], 1) == 0) return;   // first child to arrive stops; second proceeds
@@ -253,21 +268,19 @@ __global__ void refit_kernel(const Box* __restrict__ prim_boxes, const uint32_t*
         node_boxes[node] = b;
         __threadfence();
         node = parent_internal[node];
-        depth++;
     }
-    (void)max_depth;
 }
 
 __global__ void depth_kernel(int n, const int* __restrict__ parent_internal, const int* __restrict__ parent_leaf, int* __restrict__ max_depth) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int d = 0;
-    for (int node = parent_leaf[i]; node >= 0; node = parent_internal[node]) d++;
-    for (int o = 16; o > 0; o >>= 1) d = max(d, __shfl_xor_sync(__activemask(), d, o));
+    int d = 0;                                        // lanes past the end take part in the reduction with 0
+    if (i < n)
+        for (int node = parent_leaf[i]; node >= 0; node = parent_internal[node]) d++;
+    d = __reduce_max_sync(0xffffffffu, d);
     if ((threadIdx.x & 31) == 0) atomicMax(max_depth, d);
 }
 
-// ---- 6. emit traversal nodes ---------------------------------------------------------------------------
+// ---- 6a. binary traversal nodes (A/B arm of the traversal, flag LT_BVH_KEEP_BINARY) ----------------------------------
 __global__ void emit_kernel(const Box* __restrict__ prim_boxes, const uint32_t* __restrict__ sorted_prim, int n, const int* __restrict__ left,
                             const int* __restrict__ right, const Box* __restrict__ node_boxes, LbvhNode* __restrict__ out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -283,19 +296,252 @@ __global__ void emit_kernel(const Box* __restrict__ prim_boxes, const uint32_t* 
     out[i] = nd;
 }
 
+// ---- 6b. collapse into the 8-wide hierarchy -----------------------------------------------------------------------
+struct TreeView {
+    const int *left, *right, *rng_lo, *rng_hi;
+    const Box *node_boxes, *prim_boxes;
+    const uint32_t* sorted_prim;
+};
+#define WB_EMPTY ((int)0x80000000)
+LT_DEVINL Box ref_box(const TreeView& t, int c) { return c >= 0 ? t.node_boxes[c] : t.prim_boxes[t.sorted_prim[~c]]; }
+LT_DEVINL int ref_count(const TreeView& t, int c) { return c >= 0 ? t.rng_hi[c] - t.rng_lo[c] + 1 : 1; }
+LT_DEVINL bool ref_is_leaf(const TreeView& t, int c) { return ref_count(t, c) <= LT_WBVH_LEAF_MAX; }
+__host__ __device__ inline float box_area(const Box& b) {
+    const float x = b.hi[0] - b.lo[0], y = b.hi[1] - b.lo[1], z = b.hi[2] - b.lo[2];
+    return 2.0f * (x * y + y * z + z * x);
+}
+
+// One thread per wide node of the current level: choose its (up to) eight children, count what it will allocate.
+__global__ void collapse_kernel(TreeView t, const int* __restrict__ wb, int level_start, int level_n, int* __restrict__ slots,
+                                uint32_t* __restrict__ cnt_int, uint32_t* __restrict__ cnt_tri) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= level_n) return;
+    const int w = level_start + k, b = wb[w];
+    int c[8];
+    float a[8];
+    int n = 2;
+    c[0] = t.left[b]; c[1] = t.right[b];
+    for (int i = 0; i < 2; ++i) a[i] = ref_is_leaf(t, c[i]) ? -1.0f : box_area(ref_box(t, c[i]));
+    while (n < 8) {
+        int best = -1;
+        float ba = -1.0f;
+        for (int i = 0; i < n; ++i)
+            if (a[i] > ba) { ba = a[i]; best = i; }
+        if (best < 0) break;                               // only leaf slots left
+        const int x = c[best];
+        c[best] = t.left[x];
+        c[n] = t.right[x];
+        a[best] = ref_is_leaf(t, c[best]) ? -1.0f : box_area(ref_box(t, c[best]));
+        a[n] = ref_is_leaf(t, c[n]) ? -1.0f : box_area(ref_box(t, c[n]));
+        ++n;
+    }
+    uint32_t ni = 0, nt = 0;
+    for (int i = 0; i < 8; ++i) {
+        slots[8 * (size_t)w + i] = i < n ? c[i] : WB_EMPTY;
+        if (i < n) {
+            if (ref_is_leaf(t, c[i])) nt += (uint32_t)ref_count(t, c[i]);
+            else ni += 1;
+        }
+    }
+    cnt_int[k] = ni;
+    cnt_tri[k] = nt;
+}
+
+// exclusive scan of two counter arrays in place (single CTA), totals[0..1] = their sums
+__global__ void scan2_kernel(uint32_t* __restrict__ a, uint32_t* __restrict__ b, int total, uint32_t* __restrict__ totals) {
+    __shared__ uint32_t wsum[2][32];
+    __shared__ uint32_t carry[2];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if (threadIdx.x < 2) carry[threadIdx.x] = 0;
+    __syncthreads();
+    for (int base = 0; base < total; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const uint32_t va = i < total ? a[i] : 0u, vb = i < total ? b[i] : 0u;
+        uint32_t xa = va, xb = vb;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t ya = __shfl_up_sync(0xffffffffu, xa, o), yb = __shfl_up_sync(0xffffffffu, xb, o);
+            if (lane >= o) { xa += ya; xb += yb; }
+        }
+        if (lane == 31) { wsum[0][wid] = xa; wsum[1][wid] = xb; }
+        __syncthreads();
+        uint32_t oa = 0, ob = 0;
+        for (int w = 0; w < wid; ++w) { oa += wsum[0][w]; ob += wsum[1][w]; }
+        const uint32_t ca = carry[0], cb2 = carry[1];
+        if (i < total) { a[i] = ca + oa + xa - va; b[i] = cb2 + ob + xb - vb; }
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) { carry[0] = ca + oa + xa; carry[1] = cb2 + ob + xb; }
+        __syncthreads();
+    }
+    (void)nw;
+    if (threadIdx.x == 0) { totals[0] = carry[0]; totals[1] = carry[1]; }
+}
+
+struct RawTris {
+    const double *v0, *v1, *v2;
+    const int32_t* mat;
+    const uint8_t* light;
+};
+
+LT_DEVINL void write_wtri(const RawTris& r, int prim, WTri* __restrict__ out) {
+    WTri t;
+    double cx[3], e1[3], e2[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const double a = r.v0[3 * (size_t)prim + c], b = r.v1[3 * (size_t)prim + c], cc = r.v2[3 * (size_t)prim + c];
+        t.v0[c] = (float)a;
+        e1[c] = b - a; e2[c] = cc - a;
+        t.ab[c] = (float)e1[c];                  // float64 differences rounded afterwards, like TriRec<float>
+        t.ac[c] = (float)e2[c];
+    }
+    cx[0] = e1[1] * e2[2] - e1[2] * e2[1]; cx[1] = e1[2] * e2[0] - e1[0] * e2[2]; cx[2] = e1[0] * e2[1] - e1[1] * e2[0];
+    t.area2 = (float)sqrt(cx[0] * cx[0] + cx[1] * cx[1] + cx[2] * cx[2]);
+    t.prim = prim;
+    t.mat_light = r.mat[prim] | ((r.light && r.light[prim]) ? (int)0x80000000 : 0);
+    *out = t;
+}
+
+// One thread per wide node of the current level: octant slot assignment, quantisation, node + triangle records,
+// and the binary nodes of the next level's wide nodes.
+__global__ void emit_wide_kernel(TreeView t, RawTris raw, int* __restrict__ wb, int level_start, int level_n, int next_start, int tri_start,
+                                 const int* __restrict__ slots, const uint32_t* __restrict__ off_int, const uint32_t* __restrict__ off_tri,
+                                 WNode* __restrict__ out, WTri* __restrict__ wtris, int32_t* __restrict__ leaf_prims, double* __restrict__ sah) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    double cost = 0.0;
+    if (k < level_n) {
+        const int w = level_start + k, b = wb[w];
+        const Box nb = t.node_boxes[b];
+        int c[8];
+        Box bx[8];
+        int n = 0;
+        for (int i = 0; i < 8; ++i) {
+            c[i] = slots[8 * (size_t)w + i];
+            if (c[i] != WB_EMPTY) { bx[i] = ref_box(t, c[i]); n = i + 1; }
+        }
+        // ---- slot assignment: child i goes to the free slot s whose diagonal (+-1, +-1, +-1) it lies furthest along, greedily
+        // (a ray of octant `oct` then visits slots in descending s ^ (7 ^ oct): near children first)
+        float ctr[3];
+        for (int a = 0; a < 3; ++a) ctr[a] = 0.5f * (nb.lo[a] + nb.hi[a]);
+        int child_at[8];
+        for (int s2 = 0; s2 < 8; ++s2) child_at[s2] = -1;
+        unsigned done_c = 0, used_s = 0;
+        for (int r = 0; r < n; ++r) {
+            float bestv = -FLT_MAX;
+            int bi = 0, bs = 0;
+            for (int i = 0; i < n; ++i) {
+                if (done_c & (1u << i)) continue;
+                const float dx = 0.5f * (bx[i].lo[0] + bx[i].hi[0]) - ctr[0], dy = 0.5f * (bx[i].lo[1] + bx[i].hi[1]) - ctr[1],
+                            dz = 0.5f * (bx[i].lo[2] + bx[i].hi[2]) - ctr[2];
+                for (int s2 = 0; s2 < 8; ++s2) {
+                    if (used_s & (1u << s2)) continue;
+                    const float v = ((s2 & 1) ? dx : -dx) + ((s2 & 2) ? dy : -dy) + ((s2 & 4) ? dz : -dz);
+                    if (v > bestv) { bestv = v; bi = i; bs = s2; }
+                }
+            }
+            child_at[bs] = bi;
+            done_c |= 1u << bi;
+            used_s |= 1u << bs;
+        }
+        // ---- quantisation grid: plane = p + q * 2^e, q in 0..255, boxes only ever grow (see lt_scene.cuh)
+        float pf[3], scale[3];
+        uint32_t eb[3];
+        for (int a = 0; a < 3; ++a) {
+            const float ext = nb.hi[a] - nb.lo[a];
+            const float mag = fmaxf(fabsf(nb.lo[a]), fabsf(nb.hi[a]));
+            const float ext_eff = fmaxf(fmaxf(ext, mag * (1.0f / 8192.0f)), 1e-30f);
+            int ex;
+            frexpf(ext_eff / 253.0f, &ex);                       // 2^ex >= ext_eff / 253
+            int biased = min(max(ex + 127, 17), 250);
+            for (;;) {
+                scale[a] = __uint_as_float((uint32_t)biased << 23);
+                pf[a] = __fsub_rd(nb.lo[a], scale[a]);
+                const double top = ((double)nb.hi[a] - (double)pf[a]) / (double)scale[a] + 0.02;
+                if (top <= 255.0 || biased >= 250) break;
+                ++biased;
+            }
+            eb[a] = (uint32_t)biased;
+        }
+        uint32_t imask = 0, meta[8], q[3][2][8];
+        const uint32_t child_base = (uint32_t)next_start + off_int[k], tri_base = (uint32_t)tri_start + off_tri[k];
+        uint32_t n_int = 0, n_tri = 0;
+        for (int s2 = 0; s2 < 8; ++s2) {
+            meta[s2] = 0;
+            for (int a = 0; a < 3; ++a) { q[a][0][s2] = 255; q[a][1][s2] = 0; }
+            const int i = child_at[s2];
+            if (i < 0) continue;
+            for (int a = 0; a < 3; ++a) {
+                const double xl = ((double)bx[i].lo[a] - (double)pf[a]) / (double)scale[a] - 0.02;
+                const double xh = ((double)bx[i].hi[a] - (double)pf[a]) / (double)scale[a] + 0.02;
+                q[a][0][s2] = (uint32_t)min(max((int)floor(xl), 0), 255);
+                q[a][1][s2] = (uint32_t)min(max((int)ceil(xh), 0), 255);
+            }
+            const int ref = c[i];
+            const int cnt = ref_count(t, ref);
+            if (cnt <= LT_WBVH_LEAF_MAX) {
+                meta[s2] = (((1u << cnt) - 1u) << 5) | n_tri;
+                const int first = ref >= 0 ? t.rng_lo[ref] : ~ref;
+                for (int j = 0; j < cnt; ++j) {
+                    const int prim = (int)t.sorted_prim[first + j];
+                    write_wtri(raw, prim, wtris + tri_base + n_tri + j);
+                    leaf_prims[tri_base + n_tri + j] = prim;
+                }
+                n_tri += (uint32_t)cnt;
+                cost += (double)box_area(bx[i]) * cnt;
+            } else {
+                meta[s2] = 0x20u | (24u + (uint32_t)s2);
+                imask |= 1u << s2;
+                wb[child_base + n_int] = ref;
+                n_int += 1;
+            }
+        }
+        cost += (double)box_area(nb);
+        WNode nd;
+        nd.w0 = make_uint4(__float_as_uint(pf[0]), __float_as_uint(pf[1]), __float_as_uint(pf[2]), eb[0] | (eb[1] << 8) | (eb[2] << 16) | (imask << 24));
+        auto pack4 = [](const uint32_t* v) { return v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24); };
+        nd.w1 = make_uint4(child_base, tri_base, pack4(meta), pack4(meta + 4));
+        nd.w2 = make_uint4(pack4(q[0][0]), pack4(q[0][0] + 4), pack4(q[0][1]), pack4(q[0][1] + 4));
+        nd.w3 = make_uint4(pack4(q[1][0]), pack4(q[1][0] + 4), pack4(q[1][1]), pack4(q[1][1] + 4));
+        nd.w4 = make_uint4(pack4(q[2][0]), pack4(q[2][0] + 4), pack4(q[2][1]), pack4(q[2][1] + 4));
+        out[w] = nd;
+    }
+    // surface-area cost of the level: sum over nodes of area(node) + sum over leaf slots of area(slot) * triangles
+    for (int o = 16; o > 0; o >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, o);
+    if ((threadIdx.x & 31) == 0 && cost != 0.0) atomicAdd(sah, cost);
+}
+
+__global__ void single_tri_kernel(RawTris raw, WTri* __restrict__ wtris, int32_t* __restrict__ leaf_prims) {
+    write_wtri(raw, 0, wtris);
+    leaf_prims[0] = 0;
+}
+
 template <typename T>
 struct Tmp {
     T* p = nullptr;
     cudaError_t alloc(size_t n) { return lt_dev_malloc(&p, std::max<size_t>(n, 1) * sizeof(T)); }
     ~Tmp() { if (p) lt_dev_free(p); }
 };
+struct Events {                       // RAII: every early return of lt_bvh_build releases them
+    cudaEvent_t e[5] = {};
+    cudaError_t create() {
+        for (auto& x : e) { cudaError_t r = cudaEventCreate(&x); if (r != cudaSuccess) return r; }
+        return cudaSuccess;
+    }
+    ~Events() { for (auto x : e) if (x) cudaEventDestroy(x); }
+};
 
 }  // namespace lt
 
 using namespace lt;
 
+static void free_hierarchy(lt_scene* s) {
+    if (s->lbvh_nodes) lt_dev_free(s->lbvh_nodes);
+    if (s->wnodes) lt_dev_free(s->wnodes);
+    if (s->wtris) lt_dev_free(s->wtris);
+    if (s->wleaf_prims) lt_dev_free(s->wleaf_prims);
+    s->lbvh_nodes = nullptr; s->wnodes = nullptr; s->wtris = nullptr; s->wleaf_prims = nullptr;
+    s->n_lbvh_nodes = 0; s->n_wnodes = 0; s->wbvh_depth = 0;
+}
+
 extern "C" int lt_bvh_build(lt_scene* s, int flags, lt_bvh_stats* out) {
-    (void)flags;
     if (!s) { set_error("lt_bvh_build: null scene"); return LT_E_INVALID; }
     lt_ctx* ctx = s->ctx;
     LT_CUDA_OK(cudaSetDevice(ctx->device));
@@ -304,8 +550,14 @@ extern "C" int lt_bvh_build(lt_scene* s, int flags, lt_bvh_stats* out) {
     lt_bvh_stats stats;
     memset(&stats, 0, sizeof stats);
     stats.n_prims = n;
-    if (s->lbvh_nodes) { lt_dev_free(s->lbvh_nodes); s->lbvh_nodes = nullptr; s->n_lbvh_nodes = 0; }
+    free_hierarchy(s);
+    const RawTris raw{s->d_v0, s->d_v1, s->d_v2, s->d_mat, s->d_light};
+    LT_CUDA_OK(lt_dev_malloc(&s->wtris, (size_t)n * sizeof(WTri)));
+    LT_CUDA_OK(lt_dev_malloc(&s->wleaf_prims, (size_t)n * sizeof(int32_t)));
     if (n < 2) {   // a single primitive needs no hierarchy; the traversal tests it directly
+        single_tri_kernel<<<1, 1, 0, st>>>(raw, s->wtris, s->wleaf_prims);
+        LT_CUDA_OK(cudaGetLastError());
+        LT_CUDA_OK(cudaStreamSynchronize(st));
         if (out) *out = stats;
         return LT_OK;
     }
@@ -314,26 +566,33 @@ extern "C" int lt_bvh_build(lt_scene* s, int flags, lt_bvh_stats* out) {
     Tmp<Box> prim_boxes, node_boxes;
     Tmp<float> block_cb, cb;
     Tmp<uint64_t> keys_a, keys_b;
-    Tmp<uint32_t> vals_a, vals_b, hist;
-    Tmp<int> left, right, par_i, par_l, arrive, maxd;
+    Tmp<uint32_t> vals_a, vals_b, hist, cnt_int, cnt_tri, totals;
+    Tmp<int> left, right, par_i, par_l, arrive, maxd, rng_lo, rng_hi, wb, slots;
+    Tmp<WNode> wtmp;
+    Tmp<double> sah;
     LT_CUDA_OK(prim_boxes.alloc(n)); LT_CUDA_OK(node_boxes.alloc(n));
     LT_CUDA_OK(block_cb.alloc(6 * (size_t)blocks)); LT_CUDA_OK(cb.alloc(6));
     LT_CUDA_OK(keys_a.alloc(n)); LT_CUDA_OK(keys_b.alloc(n)); LT_CUDA_OK(vals_a.alloc(n)); LT_CUDA_OK(vals_b.alloc(n));
     LT_CUDA_OK(hist.alloc(256 * (size_t)tiles));
     LT_CUDA_OK(left.alloc(n)); LT_CUDA_OK(right.alloc(n)); LT_CUDA_OK(par_i.alloc(n)); LT_CUDA_OK(par_l.alloc(n));
+    LT_CUDA_OK(rng_lo.alloc(n)); LT_CUDA_OK(rng_hi.alloc(n));
     LT_CUDA_OK(arrive.alloc(n)); LT_CUDA_OK(maxd.alloc(1));
+    LT_CUDA_OK(wb.alloc(n)); LT_CUDA_OK(slots.alloc(8 * (size_t)n)); LT_CUDA_OK(cnt_int.alloc(n)); LT_CUDA_OK(cnt_tri.alloc(n));
+    LT_CUDA_OK(totals.alloc(2)); LT_CUDA_OK(wtmp.alloc(n)); LT_CUDA_OK(sah.alloc(1));
     LT_CUDA_OK(cudaMemsetAsync(arrive.p, 0, (size_t)n * sizeof(int), st));
     LT_CUDA_OK(cudaMemsetAsync(maxd.p, 0, sizeof(int), st));
-    cudaEvent_t e0, e1, e2, e3;
-    cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventCreate(&e3);
-    cudaEventRecord(e0, st);
+    LT_CUDA_OK(cudaMemsetAsync(sah.p, 0, sizeof(double), st));
+    LT_CUDA_OK(cudaMemsetAsync(wb.p, 0, sizeof(int), st));              // wide node 0 collapses binary node 0
+    Events ev;
+    LT_CUDA_OK(ev.create());
+    cudaEventRecord(ev.e[0], st);
     prim_boxes_kernel<<<blocks, LB_THREADS, 0, st>>>(s->d_v0, s->d_v1, s->d_v2, n, prim_boxes.p, block_cb.p);
     reduce_cb_kernel<<<1, LB_THREADS, 0, st>>>(block_cb.p, blocks, cb.p);
     morton_kernel<<<blocks, LB_THREADS, 0, st>>>(prim_boxes.p, n, cb.p, keys_a.p, vals_a.p);
-    cudaEventRecord(e1, st);
+    cudaEventRecord(ev.e[1], st);
     uint64_t *ki = keys_a.p, *ko = keys_b.p;
     uint32_t *vi = vals_a.p, *vo = vals_b.p;
-    for (int pass = 0; pass < 8; ++pass) {           // 63-bit codes: 8 digits of 8 bits
+    for (int pass = 0; pass < 8; ++pass) {           // 63-bit codes + the size-class bit: 8 digits of 8 bits
         int shift = pass * 8;
         rs_hist_kernel<<<tiles, LB_THREADS, 0, st>>>(ki, n, shift, hist.p);
         rs_scan_kernel<<<1, LB_THREADS, 0, st>>>(hist.p, 256 * tiles);
@@ -341,34 +600,69 @@ extern "C" int lt_bvh_build(lt_scene* s, int flags, lt_bvh_stats* out) {
         std::swap(ki, ko);
         std::swap(vi, vo);
     }
-    cudaEventRecord(e2, st);
+    cudaEventRecord(ev.e[2], st);
     const int iblocks = (n - 1 + LB_THREADS - 1) / LB_THREADS;
-    karras_kernel<<<iblocks, LB_THREADS, 0, st>>>(ki, n, left.p, right.p, par_i.p, par_l.p);
-    refit_kernel<<<blocks, LB_THREADS, 0, st>>>(prim_boxes.p, vi, n, left.p, right.p, par_i.p, par_l.p, node_boxes.p, arrive.p, maxd.p);
+    karras_kernel<<<iblocks, LB_THREADS, 0, st>>>(ki, n, left.p, right.p, par_i.p, par_l.p, rng_lo.p, rng_hi.p);
+    refit_kernel<<<blocks, LB_THREADS, 0, st>>>(prim_boxes.p, vi, n, left.p, right.p, par_i.p, par_l.p, node_boxes.p, arrive.p);
     depth_kernel<<<blocks, LB_THREADS, 0, st>>>(n, par_i.p, par_l.p, maxd.p);
-    LT_CUDA_OK(lt_dev_malloc(&s->lbvh_nodes, (size_t)(n - 1) * sizeof(LbvhNode)));
-    emit_kernel<<<iblocks, LB_THREADS, 0, st>>>(prim_boxes.p, vi, n, left.p, right.p, node_boxes.p, s->lbvh_nodes);
-    cudaEventRecord(e3, st);
+    if (flags & LT_BVH_KEEP_BINARY) {
+        LT_CUDA_OK(lt_dev_malloc(&s->lbvh_nodes, (size_t)(n - 1) * sizeof(LbvhNode)));
+        emit_kernel<<<iblocks, LB_THREADS, 0, st>>>(prim_boxes.p, vi, n, left.p, right.p, node_boxes.p, s->lbvh_nodes);
+        s->n_lbvh_nodes = n - 1;
+    }
+    cudaEventRecord(ev.e[3], st);
+    LT_CUDA_OK(cudaGetLastError());
+    // ---- collapse, breadth first: the wide nodes of a level are contiguous, children in slot order
+    const TreeView tv{left.p, right.p, rng_lo.p, rng_hi.p, node_boxes.p, prim_boxes.p, vi};
+    int level_start = 0, level_n = 1, tri_cursor = 0, levels = 0;
+    while (level_n > 0) {
+        const int lb = (level_n + LB_THREADS - 1) / LB_THREADS;
+        collapse_kernel<<<lb, LB_THREADS, 0, st>>>(tv, wb.p, level_start, level_n, slots.p, cnt_int.p, cnt_tri.p);
+        scan2_kernel<<<1, 1024, 0, st>>>(cnt_int.p, cnt_tri.p, level_n, totals.p);
+        emit_wide_kernel<<<lb, LB_THREADS, 0, st>>>(tv, raw, wb.p, level_start, level_n, level_start + level_n, tri_cursor, slots.p, cnt_int.p,
+                                                    cnt_tri.p, wtmp.p, s->wtris, s->wleaf_prims, sah.p);
+        uint32_t tot[2];
+        LT_CUDA_OK(cudaMemcpyAsync(tot, totals.p, sizeof tot, cudaMemcpyDeviceToHost, st));
+        LT_CUDA_OK(cudaStreamSynchronize(st));
+        level_start += level_n;
+        level_n = (int)tot[0];
+        tri_cursor += (int)tot[1];
+        ++levels;
+        if (levels > 4 * LT_LBVH_STACK) { free_hierarchy(s); set_error("wide-BVH collapse did not terminate"); return LT_E_OVERFLOW; }
+    }
+    const int n_wide = level_start;
+    if (tri_cursor != n) { free_hierarchy(s); set_error("wide-BVH collapse placed %d of %d triangles", tri_cursor, n); return LT_E_OVERFLOW; }
+    LT_CUDA_OK(lt_dev_malloc(&s->wnodes, (size_t)n_wide * sizeof(WNode)));
+    LT_CUDA_OK(cudaMemcpyAsync(s->wnodes, wtmp.p, (size_t)n_wide * sizeof(WNode), cudaMemcpyDeviceToDevice, st));
+    cudaEventRecord(ev.e[4], st);
     LT_CUDA_OK(cudaGetLastError());
     LT_CUDA_OK(cudaStreamSynchronize(st));
-    float ms_all = 0, ms_sort = 0;
-    cudaEventElapsedTime(&ms_all, e0, e3);
-    cudaEventElapsedTime(&ms_sort, e1, e2);
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
+    float ms_all = 0, ms_sort = 0, ms_collapse = 0;
+    cudaEventElapsedTime(&ms_all, ev.e[0], ev.e[4]);
+    cudaEventElapsedTime(&ms_sort, ev.e[1], ev.e[2]);
+    cudaEventElapsedTime(&ms_collapse, ev.e[3], ev.e[4]);
     int depth = 0;
     Box root;
+    double cost = 0.0;
     LT_CUDA_OK(cudaMemcpy(&depth, maxd.p, sizeof(int), cudaMemcpyDeviceToHost));
     LT_CUDA_OK(cudaMemcpy(&root, node_boxes.p, sizeof(Box), cudaMemcpyDeviceToHost));
-    s->n_lbvh_nodes = n - 1;
-    stats.n_nodes = n - 1;
-    stats.max_depth = depth;
+    LT_CUDA_OK(cudaMemcpy(&cost, sah.p, sizeof(double), cudaMemcpyDeviceToHost));
+    s->n_wnodes = n_wide;
+    s->wbvh_depth = levels;
+    stats.n_nodes = n_wide;
+    stats.max_depth = levels;
+    stats.binary_depth = depth;
     stats.build_ms = ms_all;
     stats.sort_ms = ms_sort;
+    stats.collapse_ms = ms_collapse;
+    stats.bytes = (int64_t)n_wide * (int64_t)sizeof(WNode) + (int64_t)n * (int64_t)sizeof(WTri);
     for (int k = 0; k < 3; ++k) { stats.root_bmin[k] = root.lo[k]; stats.root_bmax[k] = root.hi[k]; }
+    const double ra = (double)box_area(root);
+    stats.sah_cost = ra > 0 ? cost / ra : 0.0;
     if (out) *out = stats;
-    if (depth > LT_LBVH_STACK) {
-        lt_dev_free(s->lbvh_nodes); s->lbvh_nodes = nullptr; s->n_lbvh_nodes = 0;
-        set_error("LBVH depth %d exceeds the traversal stack (%d)", depth, LT_LBVH_STACK);
+    if (levels > LT_WBVH_MAX_DEPTH || ((flags & LT_BVH_KEEP_BINARY) && depth > LT_LBVH_STACK)) {
+        free_hierarchy(s);
+        set_error("hierarchy depth %d (binary %d) exceeds the traversal stack (%d / %d)", levels, depth, LT_WBVH_MAX_DEPTH, LT_LBVH_STACK);
         return LT_E_OVERFLOW;
     }
     return LT_OK;

@@ -60,7 +60,11 @@ LT_DEVINL void flush_film_warp(double* film, int32_t pix, double acc[3]) {
 #define LT_MIN_BLOCKS_F32 5
 #endif
 #ifndef LT_MIN_BLOCKS_F32_LBVH
-#define LT_MIN_BLOCKS_F32_LBVH 8          // memory-latency bound: C3 probe 5: 2.29, 6: 2.53, 7: 2.64, 8: 2.74, 10: 2.73, 12: 2.72 Grays/s
+#if LT_WIDE
+#define LT_MIN_BLOCKS_F32_LBVH 5
+#else
+#define LT_MIN_BLOCKS_F32_LBVH 8          // binary tree, memory-latency bound: C3 probe 5: 2.29, 6: 2.53, 7: 2.64, 8: 2.74, 10: 2.73, 12: 2.72 Grays/s
+#endif
 #endif
 #ifndef LT_MIN_BLOCKS_F64
 #define LT_MIN_BLOCKS_F64 3
@@ -146,9 +150,16 @@ walk_megakernel(const WalkParams<R> P) {
     // spread 10..80 steps; whole-query iterations kept ~10 of 32 lanes busy).  Measured on that scene:
     // whole query 1.76, chunk 8: 2.21, 16: 2.48, 24: 2.51, 64: 2.18 Grays/s; letting finished lanes pile up
     // before shading (4..16 lanes) changed nothing (+-1 %).
+#if LT_WIDE
+    // stack of postponed groups in dynamic shared memory: [wide level][thread], 8 bytes each
+    uint2* const wstack = reinterpret_cast<uint2*>(smem) + threadIdx.x;
+    WState<R> ts;
+    ts.G = make_uint2(0u, 0u); ts.T = make_uint2(0u, 0u); ts.sp = -1; ts.prim = -1; ts.leaf = -1; ts.best = (R)0;
+#else
     int tstack[TRAV == LT_TRAV_LBVH ? LT_LBVH_STACK : 1];
     LbvhState<R> ts;
     ts.cur = LT_LBVH_DONE; ts.sp = 0; ts.prim = -1; ts.best = (R)0;
+#endif
     V3<R> tinv = mk<R>((R)0, (R)0, (R)0);
     bool tracing = false;
     Stats st;
@@ -232,13 +243,24 @@ walk_megakernel(const WalkParams<R> P) {
             }
             uint32_t it_memo = 0, it_lidx = 0, it_fovf = 0, it_maxf = 0, it_early = 0;    // this iteration's per-lane events, reduced below
             if (TRAV == LT_TRAV_LBVH) {
+#if LT_WIDE
                 if (active && !tracing) {
-                    lbvh_begin<R>(ts, P.S.n_tris, ln.tlimit, true);
+                    wbvh_begin<R>(ts, P.S.n_tris, ln.tlimit, true);
                     tinv = mk<R>((R)1 / ln.d.x, (R)1 / ln.d.y, (R)1 / ln.d.z);
                     tracing = true;
                 }
-                lbvh_run<R>(full, ts, tstack, P.S.lbvh, tris, ln.o, ln.d, tinv, eps, ln.qtype == 2, ln.skip, st, P.lbvh_chunk);
+                wbvh_run<R>(full, ts, wstack, LT_BLOCK, P.S.wnodes, P.S.wtris, P.S.wleaf_prims, tris, ln.o, ln.d, tinv, eps, ln.qtype == 2, ln.skip, st,
+                            P.lbvh_chunk);
+                active = tracing && ts.sp < 0;                    // only lanes whose query just completed go on to shade
+#else
+                if (active && !tracing) {
+                    lbvh2_begin<R>(ts, P.S.n_tris, ln.tlimit, true);
+                    tinv = mk<R>((R)1 / ln.d.x, (R)1 / ln.d.y, (R)1 / ln.d.z);
+                    tracing = true;
+                }
+                lbvh2_run<R>(full, ts, tstack, P.S.lbvh, tris, ln.o, ln.d, tinv, eps, ln.qtype == 2, ln.skip, st, P.lbvh_chunk);
                 active = tracing && ts.cur == LT_LBVH_DONE;       // only lanes whose query just completed go on to shade
+#endif
                 if (active) tracing = false;
             }
             {
@@ -276,7 +298,21 @@ walk_megakernel(const WalkParams<R> P) {
                 int stt;
                 R adv_rand0 = (R)0;
                 if (want == 1) {            // warp-uniform when phases are aligned
-                    stt = shade_extension<R, SEM>(P, ln, prim, t, tris, mats, it_lidx, adv_rand0);
+                    HitRec<R> hit_rec;
+#if LT_WIDE
+                    if constexpr (TRAV == LT_TRAV_LBVH && sizeof(R) == 4) {
+                        // the float32 wide-BVH walk shades from the compact leaf-order record it has just tested: the
+                        // normal is rebuilt from ab x ac (R/src/primitives.py:108-111), material and is_light ride in c.w
+                        if (prim >= 0) {
+                            const float4* wp = reinterpret_cast<const float4*>(P.S.wtris + ts.leaf);
+                            const float4 wb = __ldg(wp + 1), wc = __ldg(wp + 2);
+                            hit_rec.n = normalize_fast(cross(mk<float>(wb.x, wb.y, wb.z), mk<float>(wc.x, wc.y, wc.z)));
+                            const int ml = __float_as_int(wc.w);
+                            hit_rec.mat = ml & 0x7fffffff; hit_rec.is_light = (ml >> 31) & 1; hit_rec.valid = true;
+                        }
+                    }
+#endif
+                    stt = shade_extension<R, SEM>(P, ln, prim, t, tris, mats, it_lidx, adv_rand0, hit_rec);
                 } else {
                     stt = shade_shadow<R, SEM, LT_LOCAL_FRAMES>(P, ln, frames, gtid, prim >= 0, it_fovf, it_maxf, adv_rand0);
                 }
@@ -408,7 +444,7 @@ __global__ void __launch_bounds__(LT_BLOCK) intersect_kernel(const IntersectPara
             else if (TRAV == LT_TRAV_NEAREST)
                 nearest_query<R>(P.S.tris, P.S.n_tris, o, d, (R)P.eps, Lim<R>::inf(), false, -1, prim, t, st);
             else
-                lbvh_query<R>(am, P.S.lbvh, P.S.tris, P.S.n_tris, o, d, (R)P.eps, Lim<R>::inf(), false, -1, prim, t, st);
+                lbvh_query<R>(am, P.S, P.S.tris, o, d, (R)P.eps, Lim<R>::inf(), false, -1, prim, t, st);
             P.prim[r] = prim;
             P.t[r] = prim >= 0 ? (double)t : (double)Lim<double>::inf();
         }

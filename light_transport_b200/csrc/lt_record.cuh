@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(LT_BLOCK) record_kernel(const WalkParams<R> P,
             else if (TRAV == LT_TRAV_NEAREST)
                 nearest_query<R>(P.S.tris, P.S.n_tris, ln.o, ln.d, eps, ln.tlimit, anyhit, ln.skip, prim, t, st);
             else
-                lbvh_query<R>(am, P.S.lbvh, P.S.tris, P.S.n_tris, ln.o, ln.d, eps, ln.tlimit, anyhit, ln.skip, prim, t, st);
+                lbvh_query<R>(am, P.S, P.S.tris, ln.o, ln.d, eps, ln.tlimit, anyhit, ln.skip, prim, t, st);
             int stt;
             R adv_rand0 = (R)0;
             if (ln.qtype == 1) {

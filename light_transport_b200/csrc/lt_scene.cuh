@@ -56,6 +56,33 @@ struct alignas(16) LbvhNode {
 #define LT_LBVH_STACK 96
 static_assert(sizeof(LbvhNode) == 64, "LbvhNode must be four 128-bit words");
 
+// 8-wide compressed node of the traversal hierarchy (collapsed from the Karras tree by lt_bvh_build), 80 B = five
+// 128-bit words.  Child boxes are quantised to 8 bits per plane on a per-node grid: plane = p + q * 2^e with p the node's
+// grid origin and e a per-axis power of two (after Ylitie, Karras, Laine 2017).  Quantisation only ever GROWS a child box
+// (lo rounded down, hi rounded up, plus a 2 % of a quantum safety margin that covers the float32 decode, see wnode_step).
+//   w0: p.x p.y p.z | e_x, e_y, e_z (biased IEEE exponents), imask (bit s: slot s holds an interior child)
+//   w1: child_base | tri_base | meta[0..3] | meta[4..7]
+//       meta of slot s: 0 = empty; interior child: 001|11sss (bit index 24 + s of the hit word);
+//       leaf: unary triangle count (001, 011, 111) << 5 | offset of its first triangle in the node's block (< 24)
+//   w2: qlo_x[0..7] | qhi_x[0..7]     w3: the same for y     w4: for z
+// Interior children of a node are stored contiguously from child_base in slot order; the triangles of its leaf slots are
+// stored contiguously from tri_base in the leaf-ordered triangle array (WTri / wleaf_prims).
+struct alignas(16) WNode {
+    uint4 w0, w1, w2, w3, w4;
+};
+static_assert(sizeof(WNode) == 80, "WNode must be five 128-bit words");
+// float32 triangle record of the wide hierarchy, in LEAF order (the triangles a node step exposes sit next to each other):
+// 48 B = three 128-bit words.  area2 = |ab x ac| replaces the stored unit normal in the reference's grazing test
+// (|d.n| <= 1e-7  <=>  |det| <= 1e-7 * |ab x ac|, because det = -(d . (ab x ac))); the shading normal is rebuilt from ab x ac.
+struct alignas(16) WTri {
+    float v0[3]; int32_t prim;
+    float ab[3]; float area2;
+    float ac[3]; int32_t mat_light;      // material index | is_light << 31
+};
+static_assert(sizeof(WTri) == 48, "WTri must be three 128-bit words");
+#define LT_WBVH_LEAF_MAX 3        // triangles per leaf slot (unary count in 3 bits)
+#define LT_WBVH_MAX_DEPTH 28      // wide levels the traversal stack (shared memory, 8 B per level and lane) can hold
+
 template <typename R>
 struct SceneView {
     const TriRec<R>* tris;
@@ -64,7 +91,11 @@ struct SceneView {
     const CompatNode<R>* cnodes;
     const CompatLeaf<R>* cleaves;
     const CompatLeaf<R>* nleaves;  // NEAREST, small scenes: per-triangle bounds in primitive order (kill = 0), else null
-    const LbvhNode* lbvh;         // root = node 0
+    const LbvhNode* lbvh;         // root = node 0 (binary tree: kept for A/B runs, flag LT_BVH_KEEP_BINARY)
+    const WNode* wnodes;          // 8-wide compressed hierarchy, root = node 0
+    const WTri* wtris;            // float32 triangle records in leaf order
+    const int32_t* wleaf_prims;   // leaf order -> primitive index (float64 traversal tests TriRec<double>[prim])
+    int32_t wbvh_depth;           // wide levels (stack entries a traversal may need)
     int32_t n_tris, n_mats, n_lights, n_cnodes, n_cleaves, n_lbvh_nodes;
     int32_t n_cflat;              // primitives referenced by the COMPAT leaves (flattened sequence length)
     int32_t n_nleaves;

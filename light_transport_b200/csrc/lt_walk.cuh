@@ -40,6 +40,19 @@ struct WalkParams {
     int32_t arena_frames;
 };
 
+// what shading needs to know about the primitive that was hit
+template <typename R>
+struct HitRec {
+    V3<R> n;                      // geometric unit normal (unflipped)
+    int32_t mat, is_light;
+    bool valid = false;
+};
+template <typename R> LT_DEVINL HitRec<R> hit_record(const TriRec<R>& t) {
+    HitRec<R> h;
+    h.n = mk<R>(t.n[0], t.n[1], t.n[2]); h.mat = t.mat; h.is_light = t.is_light; h.valid = true;
+    return h;
+}
+
 template <typename R>
 struct Frame {
     R T[3], W[3];
@@ -251,7 +264,7 @@ enum { ST_QUERY = 0, ST_ADVANCE = 1, ST_ADVANCE_ENDED = 2 };
 // Shading after an EXTENSION query, given the bounce's two random numbers.
 template <typename R, int SEM>
 LT_DEVINL int shade_extension_with(const WalkParams<R>& P, Lane<R>& ln, int prim, R t, const TriRec<R>* tris, const MatRec<R>* mats,
-                                   uint32_t& lidx_overflow, R& adv_rand0, R rand_0, R rand_1) {
+                                   uint32_t& lidx_overflow, R& adv_rand0, R rand_0, R rand_1, HitRec<R> hit_rec = HitRec<R>()) {
     const R eps = (R)P.eps;
     const R inv_pi = (R)(1 / 3.141592653589793);
     if (sizeof(R) == 4 && prim >= 0) ln.skip = prim;   // every continuation ray below starts on `prim`;
@@ -259,10 +272,11 @@ LT_DEVINL int shade_extension_with(const WalkParams<R>& P, Lane<R>& ln, int prim
     if (prim < 0) { ln.memo |= 1; return ST_ADVANCE_ENDED; }           // miss: frame ends (:48-53)
     ln.memo &= ~1;
     ln.pdf_zero = 0;
-    const TriRec<R>& tr = tris[prim];
+    if (!hit_rec.valid) hit_rec = hit_record(tris[prim]);          // else: the record already in hand (wide-BVH float32 walk)
+    const HitRec<R>& tr = hit_rec;
     const MatRec<R>& m = mats[tr.mat];
     V3<R> p = mk<R>(ln.o.x + t * ln.d.x, ln.o.y + t * ln.d.y, ln.o.z + t * ln.d.z);    // utils.py:65
-    V3<R> n = mk<R>(tr.n[0], tr.n[1], tr.n[2]);
+    V3<R> n = tr.n;
     if (tr.is_light && (SEM == LT_SEM_ITERATIVE || ln.bounce == 0)) {   // :59-60 (Q4) / fix1:45-46
         V3<R> w = SEM == LT_SEM_REFERENCE ? ln.W * ln.T : ln.T;
         ln.L = ln.L + w * m.emission;
@@ -342,10 +356,10 @@ LT_DEVINL int shade_extension_with(const WalkParams<R>& P, Lane<R>& ln, int prim
 // Shading after an EXTENSION query; draws rand(path, bounce) only when something was hit.
 template <typename R, int SEM>
 LT_DEVINL int shade_extension(const WalkParams<R>& P, Lane<R>& ln, int prim, R t, const TriRec<R>* tris, const MatRec<R>* mats,
-                              uint32_t& lidx_overflow, R& adv_rand0) {
+                              uint32_t& lidx_overflow, R& adv_rand0, HitRec<R> hit_rec = HitRec<R>()) {
     R rand_0 = (R)0, rand_1 = (R)0;
     if (prim >= 0) get_rand<R>(P, path_id_of(P, ln), ln.bounce, rand_0, rand_1);
-    return shade_extension_with<R, SEM>(P, ln, prim, t, tris, mats, lidx_overflow, adv_rand0, rand_0, rand_1);
+    return shade_extension_with<R, SEM>(P, ln, prim, t, tris, mats, lidx_overflow, adv_rand0, rand_0, rand_1, hit_rec);
 }
 
 // After the SHADOW query.  occluded = a hit was found in (eps, r - eps).

@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(WfCfg<R>::NT, WfCfg<R>::MINB) walk_wavefront(c
             else if (TRAV == LT_TRAV_NEAREST)
                 nearest_query<R>(tris, P.S.n_tris, ln.o, ln.d, eps, ln.tlimit, anyhit, ln.skip, prim, t, st);
             else
-                lbvh_query<R>(am, P.S.lbvh, tris, P.S.n_tris, ln.o, ln.d, eps, ln.tlimit, anyhit, ln.skip, prim, t, st);
+                lbvh_query<R>(am, P.S, tris, ln.o, ln.d, eps, ln.tlimit, anyhit, ln.skip, prim, t, st);
             ln.hit_prim = prim;
             ln.hit_pad = 0;
             ln.hit_t = t;

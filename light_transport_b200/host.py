@@ -18,7 +18,7 @@ import numpy as np
 from . import _pack, compat_bvh
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("LT_B200_LIB", os.path.join(_HERE, "liblt_b200.so"))   # env override: A/B builds only
+LIB_PATH = os.path.join(_HERE, "liblt_b200.so")     # (A/B tools under tools/ point this at a variant build before first use)
 
 TRAVERSAL = {"compat": 0, "nearest": 1, "lbvh": 2}
 SEMANTICS = {"reference": 0, "iterative": 1}
@@ -63,9 +63,10 @@ class LtCounters(C.Structure):
 
 
 class LtBvhStats(C.Structure):
-    _fields_ = [("n_prims", C.c_int32), ("n_nodes", C.c_int32), ("max_depth", C.c_int32), ("reserved", C.c_int32),
+    _fields_ = [("n_prims", C.c_int32), ("n_nodes", C.c_int32), ("max_depth", C.c_int32), ("binary_depth", C.c_int32),
                 ("build_ms", C.c_float), ("sort_ms", C.c_float), ("root_bmin", C.c_double * 3),
-                ("root_bmax", C.c_double * 3), ("sah_cost", C.c_double)]
+                ("root_bmax", C.c_double * 3), ("sah_cost", C.c_double), ("collapse_ms", C.c_float), ("reserved", C.c_float),
+                ("bytes", C.c_int64)]
 
 
 class LtError(RuntimeError):
@@ -88,7 +89,8 @@ def lib():
         L.lt_last_error.restype = C.c_char_p
         L.lt_version.restype = C.c_char_p
         for name in ("lt_init", "lt_set_stream", "lt_device_info", "lt_scene_create", "lt_scene_set_compat_bvh", "lt_bvh_build",
-                     "lt_intersect", "lt_render", "lt_render_image", "lt_render_records", "lt_film_finalize", "lt_measure_fp32_peak"):
+                     "lt_intersect", "lt_render", "lt_render_image", "lt_render_records", "lt_film_finalize", "lt_measure_fp32_peak",
+                     "lt_measure_fp64_peak", "lt_measure_l2_bandwidth"):
             getattr(L, name).restype = C.c_int
         L.lt_destroy.restype = None
         L.lt_scene_destroy.restype = None
@@ -180,11 +182,13 @@ class Renderer:
         _check(lib().lt_scene_set_compat_bvh(self._scene, C.byref(d)))
         self.has_compat = True
 
-    def build_lbvh(self):
+    def build_lbvh(self, keep_binary=False):
+        """GPU LBVH build (Morton, radix sort, Karras, refit) + collapse into the 8-wide compressed hierarchy."""
         st = LtBvhStats()
-        _check(lib().lt_bvh_build(self._scene, C.c_int(0), C.byref(st)))
-        self.lbvh_stats = dict(n_prims=st.n_prims, n_nodes=st.n_nodes, max_depth=st.max_depth, build_ms=st.build_ms,
-                               sort_ms=st.sort_ms, root_bmin=list(st.root_bmin), root_bmax=list(st.root_bmax))
+        _check(lib().lt_bvh_build(self._scene, C.c_int(1 if keep_binary else 0), C.byref(st)))
+        self.lbvh_stats = dict(n_prims=st.n_prims, n_nodes=st.n_nodes, max_depth=st.max_depth, binary_depth=st.binary_depth,
+                               build_ms=st.build_ms, sort_ms=st.sort_ms, collapse_ms=st.collapse_ms, sah_cost=st.sah_cost,
+                               bytes=st.bytes, root_bmin=list(st.root_bmin), root_bmax=list(st.root_bmax))
         return self.lbvh_stats
 
     # -- queries -----------------------------------------------------------------------------------
@@ -205,7 +209,7 @@ class Renderer:
     def render(self, *, width, height, spp, max_depth, camera, f_distance, s0=0, s1=None, semantics="reference",
                traversal="compat", real="f32", rand0=None, rand1=None, light_idx=None, seed=0, rr_start=None,
                film=None, return_samples=False, pixel_range=None, paths_per_warp=0, image=None, scheduler="megakernel", lbvh_chunk=0,
-               phased=None):
+               phased=None, ctas_per_sm=0):
         """One pass of the walk over samples ``[s0,s1)`` of every pixel.  Returns
         ``(film_sum, samples|None, counters)``; ``film`` may be a preallocated float64 buffer (numpy or a
         CUDA tensor / device address of H*W*3 doubles) that is accumulated into."""
@@ -219,6 +223,7 @@ class Renderer:
         p.rr_floor, p.eps, p.f_distance, p.seed = 0.05, _pack_eps(), float(f_distance), int(seed)
         p.paths_per_warp = int(paths_per_warp)
         p.flags = (int(lbvh_chunk) & 0xff) << 8          # LBVH traversal steps per megakernel iteration (0 = default)
+        p.flags |= (int(ctas_per_sm) & 0xf) << 20        # A/B: cap on resident CTAs per SM (0 = what the kernel was built for)
         if phased is not None:                           # phase-aligned iterations: None = chosen from the scene, True / False = forced (A/B)
             p.flags |= (1 << 17) if phased else (1 << 16)
         cam = np.asarray(camera, dtype=np.float64)
@@ -326,6 +331,17 @@ class Renderer:
     def measure_fp32_peak(self):
         v = C.c_double()
         _check(lib().lt_measure_fp32_peak(self._ctx, C.byref(v)))
+        return v.value
+
+    def measure_fp64_peak(self):
+        v = C.c_double()
+        _check(lib().lt_measure_fp64_peak(self._ctx, C.byref(v)))
+        return v.value
+
+    def measure_l2_bandwidth(self, buffer_bytes=48 << 20, granule_bytes=80, mode=1):
+        """GB/s of 128-bit L2 gathers (mode 1: one random granule per lane, the pattern of an incoherent traversal)."""
+        v = C.c_double()
+        _check(lib().lt_measure_l2_bandwidth(self._ctx, C.c_int64(buffer_bytes), C.c_int(granule_bytes), C.c_int(mode), C.byref(v)))
         return v.value
 
     def close(self):

@@ -105,7 +105,8 @@ def test_lbvh_mesh_vs_oracle(oracle):
     ps = _pack.from_arrays(scenes.heightfield(nx=240, ny=120), base=base)
     R = host.Renderer(ps, None, build_lbvh=True)
     st = R.lbvh_stats
-    assert st["n_prims"] == ps.n_tris and st["n_nodes"] == ps.n_tris - 1 and 10 < st["max_depth"] <= 96
+    assert st["n_prims"] == ps.n_tris and 0 < st["n_nodes"] < ps.n_tris // 2 and 3 <= st["max_depth"] <= 28
+    assert 10 < st["binary_depth"] <= 96 and st["sah_cost"] > 0
     rng = np.random.default_rng(5)
     n = 60000
     o = np.concatenate([np.tile(cam, (n // 2, 1)), rng.uniform(-7, 7, (n // 2, 3))])
@@ -153,3 +154,89 @@ def test_compat_beyond_the_small_scene_paths(oracle):
         assert (rel_err(samples, o_samples) > 1e-9).sum() == 0
         assert cnt["rays_ext"] == o_cnt["rays_ext"] and cnt["rays_shadow"] == o_cnt["rays_shadow"]
     R.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# C3 at its BASELINE size: 1,000,028 triangles
+
+@pytest.fixture(scope="module")
+def c3_scene():
+    from light_transport_b200 import host, scenes, _pack
+    base, _, cam, f = load_scene("lts_scene.npz")
+    ps = _pack.from_arrays(scenes.heightfield(nx=1000, ny=500), base=base)
+    R = host.Renderer(ps, None, build_lbvh=True)
+    yield R, ps, cam, f
+    R.close()
+
+
+def _c3_rays(ps, cam, n, seed):
+    """camera rays, rays from random interior points, rays aimed at Light samples"""
+    rng = np.random.default_rng(seed)
+    k = n // 3
+    o = np.concatenate([np.tile(cam, (k, 1)), rng.uniform(-7, 7, (n - k, 3))])
+    d = rng.normal(size=(n, 3))
+    d[:k, 2] = -np.abs(d[:k, 2]) - 0.5
+    tgt = ps.light_pos[rng.integers(0, len(ps.light_pos), n - 2 * k)]
+    d[2 * k:] = tgt - o[2 * k:]
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    return o, d
+
+
+def test_c3_full_size_hierarchy(c3_scene):
+    R, ps, cam, f = c3_scene
+    st = R.lbvh_stats
+    print("C3 hierarchy:", st)
+    assert st["n_prims"] == ps.n_tris == 1_000_028
+    assert st["max_depth"] <= 28 and st["binary_depth"] <= 96
+    assert st["bytes"] <= 64 << 20                      # nodes + float32 triangle records stay well inside the L2
+    assert st["sah_cost"] > 0
+
+
+def test_c3_full_size_f64_equals_oracle_brute_force(c3_scene, oracle):
+    """lt_intersect through the 8-wide hierarchy, float64: primitive ids AND t bit-exact against the oracle's brute force
+    over all 1,000,028 triangles (R/src/intersects.py:45-104 on every primitive, EPSILON < t, lowest index wins ties)."""
+    R, ps, cam, f = c3_scene
+    o, d = _c3_rays(ps, cam, 3000, seed=21)
+    p_l, t_l, c_l = R.intersect(o, d, "lbvh", "f64")
+    p_o, t_o, _ = oracle.intersect(oracle.OracleScene(ps, None), o, d, "nearest")
+    assert np.array_equal(p_l, p_o), f"{(p_l != p_o).sum()} ids differ"
+    assert np.array_equal(t_l[p_o >= 0], t_o[p_o >= 0])
+    assert (p_o >= 28).mean() > 0.2 and (p_o < 0).mean() < 0.5
+    assert c_l["tri_tests"] < 64 * len(o)               # the hierarchy culls: a handful of triangles per ray, not a million
+
+
+def test_c3_full_size_f64_equals_gpu_scan_and_f32_counted(c3_scene, record_property):
+    """100k rays: the hierarchy == the GPU's own all-primitive scan (float64, ids and t); float32 disagreements with the
+    float64 result are COUNTED, classified and bounded (north_star: 'grazing-edge disagreements are counted and reported')."""
+    R, ps, cam, f = c3_scene
+    o, d = _c3_rays(ps, cam, 100_000, seed=22)
+    p_l, t_l, _ = R.intersect(o, d, "lbvh", "f64")
+    p_n, t_n, _ = R.intersect(o, d, "nearest", "f64")
+    assert np.array_equal(p_l, p_n) and np.array_equal(t_l, t_n)
+    p_f, t_f, _ = R.intersect(o, d, "lbvh", "f32")
+    bad = p_f != p_l
+    both = bad & (p_f >= 0) & (p_l >= 0)
+    same_t = np.isclose(t_f[both], t_l[both], rtol=1e-4, atol=1e-4)          # a neighbouring triangle at the same distance: an edge
+    n_edge, n_other = int(same_t.sum()), int(bad.sum() - same_t.sum())
+    record_property("c3_f32_disagreements", int(bad.sum()))
+    print(f"C3 1M triangles, f32 vs f64 over {len(o)} rays: {bad.sum()} ids differ ({n_edge} shared-edge neighbours at the same t, "
+          f"{n_other} hit/miss or occluder flips)")
+    assert bad.mean() < 5e-3 and n_other <= max(20, n_edge)
+    ok = ~bad & (p_l >= 0)
+    assert np.allclose(t_f[ok], t_l[ok], rtol=2e-4, atol=1e-4)
+
+
+def test_c3_walk_f64_replays_oracle(c3_scene, oracle):
+    """ITERATIVE semantics (R/src/path_tracing_fix1.py:17-136) on the 1 M-triangle scene through the GPU hierarchy,
+    float64, Philox: every path equals the oracle's (which intersects by brute force) and so do the ray counts."""
+    R, ps, cam, f = c3_scene
+    kw = dict(width=64, height=36, spp=1, max_depth=8, camera=cam, f_distance=f, semantics="iterative", seed=3)
+    film, samples, cnt = R.render(traversal="lbvh", real="f64", return_samples=True, **kw)
+    _, o_samples, o_cnt = oracle.render(oracle.OracleScene(ps, None), traversal="nearest", return_samples=True, **kw)
+    assert (rel_err(samples, o_samples) > 1e-5).sum() == 0
+    assert cnt["rays_ext"] == o_cnt["rays_ext"] and cnt["rays_shadow"] == o_cnt["rays_shadow"]
+    # float32 walk of the same streams: a few paths branch differently at edges; counted and bounded
+    _, s32, _ = R.render(traversal="lbvh", real="f32", return_samples=True, **kw)
+    differ = (rel_err(s32, o_samples) > 1e-3).any(axis=-1).mean()
+    print(f"C3 walk: {100 * differ:.2f} % of float32 paths differ from the float64 oracle by more than 1e-3")
+    assert differ < 0.05

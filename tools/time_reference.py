@@ -173,7 +173,7 @@ def main():
 
     out = {
         "what": "the unmodified reference (numba) timed in the BUILD container; BASELINE.md section 3",
-        "host": {"cpu": platform.processor() or open("/proc/cpuinfo").read().split("model name")[1].split("\n")[0].strip(": \t"),
+        "host": {"cpu": open("/proc/cpuinfo").read().split("model name")[1].split("\n")[0].strip(": \t"),
                  "cores": cores, "numba_threads": thr, "numba": numba.__version__, "numpy": np.__version__, "python": platform.python_version()},
         "config": {"workload": f"C1: LTS scene {W}x{H}, {a.spp} spp, max depth {a.depth}", "paths": paths, "rays": rays,
                    "rays_per_path": rays / paths, "ray_count_source": "oracle replay of the same rand_0/rand_1 (REFERENCE semantics, COMPAT)"},

@@ -637,22 +637,35 @@ LT_DEVINL uint32_t whit_bits(uint32_t meta4, uint32_t octinv4, uint32_t hit4 /* 
     return m;
 }
 
-// float32 node step.  A quantised plane q of axis k decodes, and turns into a ray distance, in ONE byte-permute and ONE
-// fused multiply-add: prmt drops the byte into bits 16..23 of the float 0x4B000000 (= 2^23 + q * 2^16), so
-//     t = f * A + B,   A = 2^(e-16) / d,   B = (p - 128 * 2^e - o) / d
-// (the constant 2^23 of the pattern is folded into B).  Rounding: |error(t)| <= ~2e-7 * (|t| + 2.5 * node extent / |d_k|);
-// the relative part is covered by the reference's (1 + 2 gamma_3) widening of the far distance, the absolute part by the
-// 2 % of a quantum (= 8e-5 node extents) the builder adds to every quantised plane.  A zero direction component gives
-// NaN distances, which fminf / fmaxf drop: the axis does not constrain the ray (conservative).
+// float32 node step.  A quantised plane q of axis k turns into a ray distance with one conversion and one fused multiply-add.
+// LT_WDECODE 0 (default): the conversion is a byte-permute that drops the byte into bits 8..15 of the float pattern
+// 0x47000000 (= 2^15 + q exactly), so
+//     t = f * A + B,   A = 2^e / d,   B = (p - 2^15 * 2^e - o) / d
+// with the pattern's 2^15 folded into B.  That shifts the node's grid origin by 128 node extents, so the rounding of B costs
+// |error(t)| <= ~3e-5 node extents / |d_k| (about 0.008 of a quantum) on top of the usual 2e-7 * |t|: the relative part is
+// covered by the reference's (1 + 2 gamma_3) widening of the far distance, the absolute part by the 5 % of a quantum the
+// builder adds to every quantised plane.  LT_WDECODE 1: I2F.U8 with a byte selector, exact, B = (p - o) / d.
+// A zero direction component gives NaN distances, which fminf / fmaxf drop: the axis does not constrain the ray (conservative).
+#ifndef LT_WDECODE
+#define LT_WDECODE 0
+#endif
+LT_DEVINL float wplane(uint32_t word, int c) {
+#if LT_WDECODE == 0
+    return __uint_as_float(__byte_perm(word, 0x47000000u, 0x7404u | ((uint32_t)c << 4)));
+#else
+    return (float)((word >> (8 * c)) & 0xffu);
+#endif
+}
 LT_DEVINL void wnode_step(const WNode* __restrict__ nodes, uint32_t idx, V3<float> o, V3<float> inv, float best, uint32_t octinv, uint2& G, uint2& T) {
     const uint4* p = reinterpret_cast<const uint4*>(nodes + idx);
     const uint4 w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2), w3 = __ldg(p + 3), w4 = __ldg(p + 4);
     const float widen = 1.0f + 2.0f * ((3.0f * 5.9604644775390625e-08f) / (1.0f - 3.0f * 5.9604644775390625e-08f));
-    const float sx = __uint_as_float(((w0.w & 0xffu) - 16u) << 23), sy = __uint_as_float((((w0.w >> 8) & 0xffu) - 16u) << 23),
-                sz = __uint_as_float((((w0.w >> 16) & 0xffu) - 16u) << 23);
+    const float sx = __uint_as_float((w0.w & 0xffu) << 23), sy = __uint_as_float(((w0.w >> 8) & 0xffu) << 23),
+                sz = __uint_as_float(((w0.w >> 16) & 0xffu) << 23);
     const float Ax = sx * inv.x, Ay = sy * inv.y, Az = sz * inv.z;
-    const float Bx = (__uint_as_float(w0.x) - sx * 8388608.0f - o.x) * inv.x, By = (__uint_as_float(w0.y) - sy * 8388608.0f - o.y) * inv.y,
-                Bz = (__uint_as_float(w0.z) - sz * 8388608.0f - o.z) * inv.z;
+    const float bias = LT_WDECODE == 0 ? 32768.0f : 0.0f;
+    const float Bx = (__uint_as_float(w0.x) - sx * bias - o.x) * inv.x, By = (__uint_as_float(w0.y) - sy * bias - o.y) * inv.y,
+                Bz = (__uint_as_float(w0.z) - sz * bias - o.z) * inv.z;
     const bool ngx = inv.x < 0.0f, ngy = inv.y < 0.0f, ngz = inv.z < 0.0f;
     const float bw = best * widen;
     uint32_t hitmask = 0;
@@ -665,10 +678,9 @@ LT_DEVINL void wnode_step(const WNode* __restrict__ nodes, uint32_t idx, V3<floa
         uint32_t hit4 = 0;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            const uint32_t sel = 0x7044u | ((uint32_t)c << 8);
-            const float tnx = fmaf(__uint_as_float(__byte_perm(nx, 0x4B000000u, sel)), Ax, Bx), tfx = fmaf(__uint_as_float(__byte_perm(fx, 0x4B000000u, sel)), Ax, Bx);
-            const float tny = fmaf(__uint_as_float(__byte_perm(ny, 0x4B000000u, sel)), Ay, By), tfy = fmaf(__uint_as_float(__byte_perm(fy, 0x4B000000u, sel)), Ay, By);
-            const float tnz = fmaf(__uint_as_float(__byte_perm(nz, 0x4B000000u, sel)), Az, Bz), tfz = fmaf(__uint_as_float(__byte_perm(fz, 0x4B000000u, sel)), Az, Bz);
+            const float tnx = fmaf(wplane(nx, c), Ax, Bx), tfx = fmaf(wplane(fx, c), Ax, Bx);
+            const float tny = fmaf(wplane(ny, c), Ay, By), tfy = fmaf(wplane(fy, c), Ay, By);
+            const float tnz = fmaf(wplane(nz, c), Az, Bz), tfz = fmaf(wplane(fz, c), Az, Bz);
             const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));
             const float tf = fminf(fminf(fminf(tfx, tfy), tfz) * widen, bw);
             if (tn <= tf) hit4 |= 1u << (8 * c);

@@ -303,6 +303,7 @@ struct TreeView {
     const uint32_t* sorted_prim;
 };
 #define WB_EMPTY ((int)0x80000000)
+#define LB_QUANT_SLACK 0.05      // quanta added to every quantised plane: covers the float32 decode of the traversal (wnode_step)
 LT_DEVINL Box ref_box(const TreeView& t, int c) { return c >= 0 ? t.node_boxes[c] : t.prim_boxes[t.sorted_prim[~c]]; }
 LT_DEVINL int ref_count(const TreeView& t, int c) { return c >= 0 ? t.rng_hi[c] - t.rng_lo[c] + 1 : 1; }
 LT_DEVINL bool ref_is_leaf(const TreeView& t, int c) { return ref_count(t, c) <= LT_WBVH_LEAF_MAX; }
@@ -450,11 +451,11 @@ __global__ void emit_wide_kernel(TreeView t, RawTris raw, int* __restrict__ wb, 
             const float ext_eff = fmaxf(fmaxf(ext, mag * (1.0f / 8192.0f)), 1e-30f);
             int ex;
             frexpf(ext_eff / 253.0f, &ex);                       // 2^ex >= ext_eff / 253
-            int biased = min(max(ex + 127, 17), 250);
+            int biased = min(max(ex + 127, 2), 250);
             for (;;) {
                 scale[a] = __uint_as_float((uint32_t)biased << 23);
                 pf[a] = __fsub_rd(nb.lo[a], scale[a]);
-                const double top = ((double)nb.hi[a] - (double)pf[a]) / (double)scale[a] + 0.02;
+                const double top = ((double)nb.hi[a] - (double)pf[a]) / (double)scale[a] + LB_QUANT_SLACK;
                 if (top <= 255.0 || biased >= 250) break;
                 ++biased;
             }
@@ -469,8 +470,8 @@ __global__ void emit_wide_kernel(TreeView t, RawTris raw, int* __restrict__ wb, 
             const int i = child_at[s2];
             if (i < 0) continue;
             for (int a = 0; a < 3; ++a) {
-                const double xl = ((double)bx[i].lo[a] - (double)pf[a]) / (double)scale[a] - 0.02;
-                const double xh = ((double)bx[i].hi[a] - (double)pf[a]) / (double)scale[a] + 0.02;
+                const double xl = ((double)bx[i].lo[a] - (double)pf[a]) / (double)scale[a] - LB_QUANT_SLACK;
+                const double xh = ((double)bx[i].hi[a] - (double)pf[a]) / (double)scale[a] + LB_QUANT_SLACK;
                 q[a][0][s2] = (uint32_t)min(max((int)floor(xl), 0), 255);
                 q[a][1][s2] = (uint32_t)min(max((int)ceil(xh), 0), 255);
             }

@@ -183,11 +183,12 @@ __global__ void __launch_bounds__(LT_BLOCK) record_kernel(const WalkParams<R> P,
                 rec_rand<R>(P, RP, ln, rl, ln.bounce, r0, r1);
                 stt = shade_extension_with<R, LT_SEM_REFERENCE>(P, ln, prim, t, P.S.tris, P.S.mats, lidx_overflow, adv_rand0, r0, r1);
                 if (prim < 0 && !RP.grad) rl.min_zero = min(rl.min_zero, ln.bounce);                  // :50-52
-                if (prim >= 0 && ln.pdf_zero && !RP.grad) rl.min_zero = min(rl.min_zero, ln.bounce + 1);   // :77-79
+                if (prim >= 0 && (ln.pdf_zero & 1) && !RP.grad) rl.min_zero = min(rl.min_zero, ln.bounce + 1);   // :77-79
             } else {
                 n_shadow++;
-                const bool occluded = prim >= 0;
-                if (ln.pdf_zero) {
+                const bool occluded = prim >= 0 || (ln.pdf_zero & 2);
+                if (ln.pdf_zero & 1) {
+                    ln.o = ln.new_o; ln.d = ln.new_d; ln.skip = (ln.pdf_zero >> 2) - 1;               // the untouched incoming ray
                     if (!RP.grad) rl.min_zero = min(rl.min_zero, ln.bounce + 1);                      // :77-79
                     stt = ST_ADVANCE_ENDED;
                 } else {

@@ -59,7 +59,7 @@ static_assert(sizeof(LbvhNode) == 64, "LbvhNode must be four 128-bit words");
 // 8-wide compressed node of the traversal hierarchy (collapsed from the Karras tree by lt_bvh_build), 80 B = five
 // 128-bit words.  Child boxes are quantised to 8 bits per plane on a per-node grid: plane = p + q * 2^e with p the node's
 // grid origin and e a per-axis power of two (after Ylitie, Karras, Laine 2017).  Quantisation only ever GROWS a child box
-// (lo rounded down, hi rounded up, plus a 2 % of a quantum safety margin that covers the float32 decode, see wnode_step).
+// (lo rounded down, hi rounded up, plus a 5 % of a quantum safety margin that covers the float32 decode, see wnode_step).
 //   w0: p.x p.y p.z | e_x, e_y, e_z (biased IEEE exponents), imask (bit s: slot s holds an interior child)
 //   w1: child_base | tri_base | meta[0..3] | meta[4..7]
 //       meta of slot s: 0 = empty; interior child: 001|11sss (bit index 24 + s of the hit word);

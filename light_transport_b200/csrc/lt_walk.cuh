@@ -74,7 +74,8 @@ struct Lane {
     int32_t pix, s_rel;           // pixel (row-major) and s - s0
     uint64_t path_id;             // (pixel * spp + s): Philox counter / replay row
     int32_t bounce, nframes, nee;
-    int32_t pdf_zero;
+    int32_t pdf_zero;             // bit 0: the pending hemisphere sample has pdf == 0; bit 1: float32 self-occluded shadow query;
+                                  // bits 2..: with bit 0, 1 + the skip primitive of the incoming ray
     int32_t memo;                 // bit 0: the current extension ray is known to miss (it already did): Q1 re-traces need no
                                   // traversal.  bits 1..: how many suspended frames would re-trace it (see resume_retraces)
     V3<R> T, W, L;
@@ -267,6 +268,7 @@ LT_DEVINL int shade_extension_with(const WalkParams<R>& P, Lane<R>& ln, int prim
                                    uint32_t& lidx_overflow, R& adv_rand0, R rand_0, R rand_1, HitRec<R> hit_rec = HitRec<R>()) {
     const R eps = (R)P.eps;
     const R inv_pi = (R)(1 / 3.141592653589793);
+    const int32_t skip_in = ln.skip;
     if (sizeof(R) == 4 && prim >= 0) ln.skip = prim;   // every continuation ray below starts on `prim`;
                                                        // on a miss the (unchanged) ray keeps its own skip
     if (prim < 0) { ln.memo |= 1; return ST_ADVANCE_ENDED; }           // miss: frame ends (:48-53)
@@ -300,22 +302,34 @@ LT_DEVINL int shade_extension_with(const WalkParams<R>& P, Lane<R>& ln, int prim
         // thing left between here and the recursion point
         V3<R> dir;
         R pdf = cosine_sample<R>(n, ln.d, rand_0, rand_1, dir);
-        // pdf == 0 (u0 == 0 exactly, or a direction with zero z): the reference breaks BEFORE touching the ray
-        // (:76-80) and drops the direct light it has just computed — nothing to trace, the frame ends on the
-        // incoming ray (the light pick above was still consumed, as in cast_one_shadow_ray)
-        if (pdf == 0) { ln.pdf_zero = 1; adv_rand0 = rand_0; return ST_ADVANCE_ENDED; }
+        // pdf == 0 (u0 == 0 exactly, or a direction with zero z): the reference has ALREADY cast the shadow ray
+        // (cast_one_shadow_ray runs before the sampling, :70-75 / fix1:56-59) and then breaks without touching the ray
+        // (:76-80, dropping the direct light; fix1:59-67 has already added it).  So the shadow query is still issued and
+        // counted; shade_shadow ends the frame.
+        ln.pdf_zero = pdf == 0 ? 1 : 0;
         ln.rand0_pending = rand_0;
         ln.pdf_pending = pdf;
         R ct = dot(dir, n);
         ln.tfac = mk<R>((m.kd[0] * inv_pi) * ct / pdf, (m.kd[1] * inv_pi) * ct / pdf, (m.kd[2] * inv_pi) * ct / pdf);
         ln.new_o = mk<R>(p.x + eps * dir.x, p.y + eps * dir.y, p.z + eps * dir.z);
         ln.new_d = dir;
+        if (pdf == 0) {        // the frame ends on the INCOMING ray, which its caller re-traces (Q1): keep it across the shadow query
+            ln.new_o = ln.o; ln.new_d = ln.d;
+            ln.pdf_zero |= (skip_in + 1) << 2;
+        }
         ln.o = so;
         ln.d = sd;
         // light_samples.py:53: visible iff nearest t >= r - EPSILON.  The target point lies ON a lamp
         // triangle that is itself in the primitive list, so the nearest t is r up to rounding; float32
         // cannot resolve 1e-6 at r ~ 10 and needs a margin relative to r.
         ln.tlimit = sizeof(R) == 4 ? mag - fmax(eps, mag * (R)4e-6) : mag - eps;
+        // float32 skips the primitive a ray starts on instead of offsetting its origin by 1e-6 (below float32 resolution).
+        // That is equivalent EXCEPT for a shadow ray whose light lies behind the surface (cos_theta < 0 on the flipped
+        // normal): the reference's origin sits 1e-6 in FRONT of the surface (light_samples.py:41 gets x + EPSILON*n), so the
+        // ray crosses the very triangle it left at t = 1e-6/|cos_theta| > EPSILON and is occluded by it — the back side of a
+        // surface is dark.  (|cos_theta| <= 1e-7 is the triangle test's own grazing rejection, intersects.py:72.)  The query is
+        // still issued and counted, with an empty interval; shade_shadow takes it as occluded.
+        if (sizeof(R) == 4 && cos_theta < (R)-1e-7) { ln.pdf_zero |= 2; ln.tlimit = (R)-1; }
         ln.qtype = 2;
         return ST_QUERY;
     }
@@ -366,16 +380,18 @@ LT_DEVINL int shade_extension(const WalkParams<R>& P, Lane<R>& ln, int prim, R t
 template <typename R, int SEM, int LF>
 LT_DEVINL int shade_shadow(const WalkParams<R>& P, Lane<R>& ln, Frame<R>* frames, int64_t gtid, bool occluded,
                            uint32_t& frame_overflow, uint32_t& max_frames, R& adv_rand0) {
+    if (ln.pdf_zero & 2) occluded = true;                               // float32: the surface shadows its own back side (see shade_extension_with)
+    if (ln.pdf_zero & 1) { ln.o = ln.new_o; ln.d = ln.new_d; ln.skip = (ln.pdf_zero >> 2) - 1; }   // the untouched incoming ray
     if (SEM == LT_SEM_ITERATIVE) {
         if (!occluded) ln.L = ln.L + ln.T * ln.contrib;                 // fix1:59
-        if (ln.pdf_zero) return ST_ADVANCE_ENDED;                       // fix1:64-67
+        if (ln.pdf_zero & 1) return ST_ADVANCE_ENDED;                   // fix1:64-67
         ln.T = ln.T * ln.tfac;
         ln.o = ln.new_o;
         ln.d = ln.new_d;
         adv_rand0 = ln.rand0_pending;
         return ST_ADVANCE;
     }
-    if (ln.pdf_zero) return ST_ADVANCE_ENDED;                           // :76-80 — direct light is dropped
+    if (ln.pdf_zero & 1) return ST_ADVANCE_ENDED;                       // :76-80 — direct light is dropped
     ln.T = ln.T * ln.tfac;                                              // :92
     if (!occluded) ln.L = ln.L + ln.W * ln.contrib;                     // direct enters un-weighted by T (Q2)
     // recursion (:93): suspend this frame, open the child at bounce+1 on the new ray

@@ -239,4 +239,4 @@ def test_c3_walk_f64_replays_oracle(c3_scene, oracle):
     _, s32, _ = R.render(traversal="lbvh", real="f32", return_samples=True, **kw)
     differ = (rel_err(s32, o_samples) > 1e-3).any(axis=-1).mean()
     print(f"C3 walk: {100 * differ:.2f} % of float32 paths differ from the float64 oracle by more than 1e-3")
-    assert differ < 0.05
+    assert differ < 0.02

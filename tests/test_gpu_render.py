@@ -331,3 +331,25 @@ def test_scheduling_policies_do_not_change_paths(R_lts, R_mirror, scene_file, tr
     assert np.array_equal(s_on, s_off) and np.array_equal(s_on, s_small)
     for k in ("paths", "rays_ext", "rays_shadow", "rays_memo", "max_frames"):
         assert c_on[k] == c_off[k] == c_small[k], k
+
+
+@pytest.mark.parametrize("semantics", ["reference", "iterative"])
+def test_zero_pdf_sample_still_casts_its_shadow_ray(R_lts, oracle, semantics):
+    """rand_0 == 0 puts the hemisphere sample on the disk's rim: pdf == 0.  The reference has already cast the shadow ray by
+    then (R/src/path_tracing.py:70-80; path_tracing_fix1.py:56-67 has even added the direct light), so the query counts and,
+    for ITERATIVE, its light is kept.  Replayed against the oracle in float64; float32 keeps the same ray counts."""
+    ps, nodes, cam, f = load_scene("lts_scene.npz")
+    W, H, spp, D = 12, 10, 2, 8
+    rng = np.random.default_rng(17)
+    r0, r1 = rng.random((H, W, spp, D)), rng.random((H, W, spp, D))
+    r0[:, :, 0, 1] = 0.0; r1[:, :, 0, 1] = 0.5            # sample 0: zero pdf at bounce 1
+    r0[:, :, 1, 0] = 0.0; r1[:, :, 1, 0] = 0.5            # sample 1: at bounce 0 (jitter 0 as well)
+    kw = dict(width=W, height=H, spp=spp, max_depth=D, camera=cam, f_distance=f, semantics=semantics, traversal="compat",
+              rand0=r0, rand1=r1, seed=9, return_samples=True)
+    _, s_gpu, c_gpu = R_lts.render(real="f64", **kw)
+    _, s_cpu, c_cpu = oracle.render(oracle.OracleScene(ps, nodes), **kw)
+    assert (rel_err(s_gpu, s_cpu) > 1e-9).sum() == 0
+    for k in ("rays_ext", "rays_shadow"):
+        assert c_gpu[k] == c_cpu[k], k
+    _, _, c32 = R_lts.render(real="f32", **kw)
+    assert abs(c32["rays_shadow"] - c_cpu["rays_shadow"]) <= 2 and abs(c32["rays_ext"] - c_cpu["rays_ext"]) <= 4

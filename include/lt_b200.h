@@ -29,11 +29,14 @@ extern "C" {
 #define LT_E_COMPAT_UNDEFINED (-3) /* COMPAT traversal on a node list where the reference raises IndexError (Q9b) */
 #define LT_E_NO_BVH (-4)       /* traversal needs a structure that was not set/built */
 #define LT_E_OVERFLOW (-5)     /* a capacity was exceeded (details in message) */
+#define LT_E_NCCL (-6)         /* NCCL unavailable, or a collective failed (synchronously or asynchronously); the communicator is aborted */
 
 /* traversal semantics */
 #define LT_TRAV_COMPAT 0       /* emulate R/src/bvh_new.py:413-482 over the reference's node list, defects included */
 #define LT_TRAV_NEAREST 1      /* true closest hit, EPSILON < t, ties -> lowest primitive index; all-primitive scan */
-#define LT_TRAV_LBVH 2         /* same semantics as NEAREST through the GPU-built LBVH */
+#define LT_TRAV_LBVH 2         /* same semantics as NEAREST through the GPU-built hierarchy: 8-wide, compressed (lt_bvh_build) */
+#define LT_TRAV_LBVH2 3        /* the same through the binary Karras tree it is collapsed from (needs LT_BVH_KEEP_BINARY);
+                                  lt_intersect and the megakernel walk only */
 /* integrator semantics */
 #define LT_SEM_REFERENCE 0     /* R/src/path_tracing.py:23-159 (recurse-and-continue) */
 #define LT_SEM_ITERATIVE 1     /* R/src/path_tracing_fix1.py:17-136 */
@@ -46,6 +49,7 @@ extern "C" {
 
 typedef struct lt_ctx lt_ctx;
 typedef struct lt_scene lt_scene;
+typedef struct lt_comm lt_comm;
 
 /* Scene as structure-of-arrays, float64 like the reference's jitclass fields (a11):
  * PreComputedTriangle R/src/primitives.py:85-113, Material R/src/material.py:18-37,
@@ -116,7 +120,8 @@ typedef struct {
     int64_t bytes;               /* nodes (80 B) + float32 triangle records (48 B): what a float32 traversal touches */
 } lt_bvh_stats;
 /* lt_bvh_build flags */
-#define LT_BVH_KEEP_BINARY 1     /* also keep the binary (Karras) nodes: A/B arm of the traversal, build variant LT_WIDE=0 */
+/* bits 8-9: triangles per leaf slot of the wide hierarchy, 1..3 (0 = default 3) */
+#define LT_BVH_KEEP_BINARY 1     /* also keep the binary (Karras) nodes for LT_TRAV_LBVH2 */
 
 int lt_init(int device, lt_ctx **out);
 void lt_destroy(lt_ctx *);
@@ -166,6 +171,20 @@ int lt_render_records(lt_scene *, const lt_render_params *, const double *rand0,
 
 /* image = clip(film_sum / spp_total, 0, 1)   (R/src/path_tracing.py:304-305) */
 int lt_film_finalize(lt_ctx *, const double *film_sum, int64_t n_values, int64_t spp_total, double *image_out);
+
+/* ---- multi-GPU: photons shard across ranks by sample range (disjoint Philox counters); the ONLY exchange of a pass is one
+ * sum-reduction of the per-rank films over NCCL (NVLink / NVSwitch).  The reference is single-process (numba.prange threads,
+ * R/src/path_tracing_old.py:142-149) and has no counterpart.  One process per GPU: rank 0 calls lt_comm_unique_id, the host
+ * hands the 128 bytes to every rank (torch.distributed / MPI / a file), every rank calls lt_comm_init.
+ * lt_film_reduce: film_sum (DEVICE, [n] float64) <- sum over ranks, on rank `root` (root < 0: on every rank), on the context's
+ * stream; with spp_total > 0 the receiving rank(s) also finalize in place: film_sum <- clip(film_sum / spp_total, 0, 1)
+ * (R/src/path_tracing.py:304-305).  NCCL errors, including asynchronous ones (ncclCommGetAsyncError), abort the communicator and
+ * return LT_E_NCCL instead of hanging. */
+int lt_comm_unique_id(void *id128);
+int lt_comm_init(lt_ctx *, int n_ranks, int rank, const void *id128, lt_comm **out);
+void lt_comm_destroy(lt_comm *);
+int lt_film_reduce(lt_ctx *, lt_comm *, double *film_sum, int64_t n_values, int root, int64_t spp_total);
+int lt_nccl_version(int *version);
 
 /* ---- C4b: many-bounce photon walk in a homogeneous scattering medium (BASELINE.json config 4).  The
  * reference only has the Henyey-Greenstein evaluation (R/src/medium_samples.py:14-16, lt_henyey_greenstein);

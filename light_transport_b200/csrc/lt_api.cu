@@ -118,7 +118,7 @@ static void fill_view(const lt_scene* s, SceneView<R>& v) {
     v.nleaves = a.nleaves;
     v.n_nleaves = a.nleaves ? s->n_nleaves : 0;
     v.lbvh = s->lbvh_nodes;
-    v.wnodes = s->wnodes; v.wtris = s->wtris; v.wleaf_prims = s->wleaf_prims; v.wbvh_depth = s->wbvh_depth;
+    v.wnodes = s->wnodes; v.wtris = s->wtris; v.wleaf_prims = s->wleaf_prims; v.wbvh_depth = s->wbvh_depth; v.wmagic = 0x47000000u;
     v.n_tris = s->n_tris; v.n_mats = s->n_mats; v.n_lights = s->n_lights;
     v.n_cnodes = s->n_cnodes; v.n_cleaves = s->n_cleaves; v.n_lbvh_nodes = s->n_lbvh_nodes;
     v.n_cflat = s->n_cflat;
@@ -265,7 +265,8 @@ static size_t staged_bytes(const lt_scene* s, int trav, int real) {
     size_t mat = r == 8 ? sizeof(MatRec<double>) : sizeof(MatRec<float>);
     size_t nod = r == 8 ? sizeof(CompatNode<double>) : sizeof(CompatNode<float>);
     size_t lef = r == 8 ? sizeof(CompatLeaf<double>) : sizeof(CompatLeaf<float>);
-    if (trav == LT_TRAV_LBVH) return LT_WIDE ? (size_t)std::max(s->wbvh_depth, 1) * LT_BLOCK * sizeof(uint2) : 0;   // traversal stacks
+    if (trav == LT_TRAV_LBVH) return (size_t)std::max(s->wbvh_depth, 1) * LT_BLOCK * sizeof(uint2);   // traversal stacks
+    if (trav == LT_TRAV_LBVH2) return 0;
     size_t b = al(tri * s->n_tris) + al(mat * s->n_mats);
     if (trav == LT_TRAV_COMPAT) b += al(nod * s->n_cnodes) + al(lef * s->n_cleaves);
     if (trav == LT_TRAV_COMPAT && r == 4) b += al((size_t)((s->n_cleaves + 1) / 2) * 96) + (8 * 4 * 12 * 4 + 32);   // slab_pairs_bytes + LT_CHAIN_BYTES
@@ -280,6 +281,8 @@ static int check_traversal(const lt_scene* s, int trav) {
         if (s->n_cnodes == 0) { set_error("COMPAT traversal needs lt_scene_set_compat_bvh"); return LT_E_NO_BVH; }
     } else if (trav == LT_TRAV_LBVH) {
         if (!s->wtris) { set_error("LBVH traversal needs lt_bvh_build"); return LT_E_NO_BVH; }
+    } else if (trav == LT_TRAV_LBVH2) {
+        if (!s->lbvh_nodes && s->n_tris > 1) { set_error("LBVH2 traversal needs lt_bvh_build with LT_BVH_KEEP_BINARY"); return LT_E_NO_BVH; }
     } else if (trav != LT_TRAV_NEAREST) {
         set_error("unknown traversal %d", trav);
         return LT_E_INVALID;
@@ -361,15 +364,18 @@ static int do_render(lt_scene* s, const lt_render_params* p, const double* rand0
     P.counters = reinterpret_cast<unsigned long long*>(ctx->d_counters);
 
     const bool wavefront = p->scheduler == LT_SCHED_WAVEFRONT;
+    if (p->traversal == LT_TRAV_LBVH2 && wavefront) { set_error("LT_TRAV_LBVH2 runs on the megakernel scheduler only"); return LT_E_INVALID; }
     const size_t staged = (wavefront && p->traversal == LT_TRAV_LBVH) ? 0 : staged_bytes(s, p->traversal, p->real);
     const size_t smem = wavefront ? wavefront_smem_bytes<R>(staged) : staged;
     if (smem > (size_t)ctx->prop.sharedMemPerBlockOptin) {
         set_error("scene needs %zu B of shared memory for traversal %d; use LT_TRAV_LBVH for large scenes", smem, p->traversal);
         return LT_E_OVERFLOW;
     }
+    // phase-aligned iterations pay where most extension hits spawn a shadow query (flags bit 16 / 17 force off / on: A/B runs)
+    P.phased = (p->flags & (1 << 17)) ? 1 : (p->flags & (1 << 16)) ? 0 : (s->diffuse_area_share >= 0.5 ? 1 : 0);
     int regs = 0, local_bytes = 0, bps = 0;
     if (wavefront) { if ((rc = wavefront_kernel_attrs<R>(p->traversal, p->semantics, &regs, &bps, smem))) return rc; }
-    else if ((rc = walk_kernel_attrs<R>(p->traversal, p->semantics, &regs, &local_bytes, &bps, smem))) return rc;
+    else if ((rc = walk_kernel_attrs<R>(p->traversal, p->semantics, P.phased, &regs, &local_bytes, &bps, smem))) return rc;
     if (bps < 1) bps = 1;
     if (((p->flags >> 20) & 0xf) && !wavefront) bps = std::min(bps, (p->flags >> 20) & 0xf);     // A/B: fewer resident CTAs per SM
     const int block = wavefront ? WfCfg<R>::NT : LT_BLOCK;
@@ -394,9 +400,7 @@ static int do_render(lt_scene* s, const lt_render_params* p, const double* rand0
         if (granules < nwarps) grid = (int)std::max<int64_t>(1, (granules * 32 + block - 1) / block);
     }
     P.paths_per_warp = (int32_t)ppw;
-    P.lbvh_chunk = ((p->flags >> 8) & 0xff) ? ((p->flags >> 8) & 0xff) : (LT_WIDE ? 8 : 24);
-    // phase-aligned iterations pay where most extension hits spawn a shadow query (flags bit 16 / 17 force off / on: A/B runs)
-    P.phased = (p->flags & (1 << 17)) ? 1 : (p->flags & (1 << 16)) ? 0 : (s->diffuse_area_share >= 0.5 ? 1 : 0);
+    P.lbvh_chunk = ((p->flags >> 8) & 0xff) ? ((p->flags >> 8) & 0xff) : (p->traversal == LT_TRAV_LBVH ? 16 : 24);
     // suspended-frame storage for REFERENCE walks: a frame at stack depth k has bounce >= k and can still
     // recurse at bounce D-1, so up to D suspended frames; the megakernel keeps the first LT_LOCAL_FRAMES locally
     P.arena = nullptr; P.arena_frames = 0; P.arena_threads = (int64_t)grid * block;

@@ -605,6 +605,9 @@ struct WState {
 #ifndef LT_WBVH_TRI_WEIGHT
 #define LT_WBVH_TRI_WEIGHT 2  // a triangle step runs when (lanes waiting for one) * weight >= lanes waiting for a node step
 #endif
+#ifndef LT_WBVH_TRI_PER_STEP
+#define LT_WBVH_TRI_PER_STEP 1  // triangles a lane tests per triangle step
+#endif
 
 template <typename R>
 LT_DEVINL void wbvh_begin(WState<R>& s, int n_tris, R tlimit, bool live) {
@@ -649,14 +652,17 @@ LT_DEVINL uint32_t whit_bits(uint32_t meta4, uint32_t octinv4, uint32_t hit4 /* 
 #ifndef LT_WDECODE
 #define LT_WDECODE 0
 #endif
-LT_DEVINL float wplane(uint32_t word, int c) {
+LT_DEVINL float wplane(uint32_t word, int c, uint32_t magic) {
 #if LT_WDECODE == 0
-    return __uint_as_float(__byte_perm(word, 0x47000000u, 0x7404u | ((uint32_t)c << 4)));
+    // `magic` = 0x47000000 arrives as a kernel parameter: PRMT has ONE immediate slot, and with the pattern a compile-time
+    // constant too ptxas spent it on the pattern and re-materialised the selector in a register before every PRMT
+    return __uint_as_float(__byte_perm(word, magic, 0x7404u | ((uint32_t)c << 4)));
 #else
     return (float)((word >> (8 * c)) & 0xffu);
 #endif
 }
-LT_DEVINL void wnode_step(const WNode* __restrict__ nodes, uint32_t idx, V3<float> o, V3<float> inv, float best, uint32_t octinv, uint2& G, uint2& T) {
+LT_DEVINL void wnode_step(const WNode* __restrict__ nodes, uint32_t idx, V3<float> o, V3<float> inv, float best, uint32_t octinv, uint32_t magic,
+                          uint2& G, uint2& T) {
     const uint4* p = reinterpret_cast<const uint4*>(nodes + idx);
     const uint4 w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2), w3 = __ldg(p + 3), w4 = __ldg(p + 4);
     const float widen = 1.0f + 2.0f * ((3.0f * 5.9604644775390625e-08f) / (1.0f - 3.0f * 5.9604644775390625e-08f));
@@ -678,9 +684,9 @@ LT_DEVINL void wnode_step(const WNode* __restrict__ nodes, uint32_t idx, V3<floa
         uint32_t hit4 = 0;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            const float tnx = fmaf(wplane(nx, c), Ax, Bx), tfx = fmaf(wplane(fx, c), Ax, Bx);
-            const float tny = fmaf(wplane(ny, c), Ay, By), tfy = fmaf(wplane(fy, c), Ay, By);
-            const float tnz = fmaf(wplane(nz, c), Az, Bz), tfz = fmaf(wplane(fz, c), Az, Bz);
+            const float tnx = fmaf(wplane(nx, c, magic), Ax, Bx), tfx = fmaf(wplane(fx, c, magic), Ax, Bx);
+            const float tny = fmaf(wplane(ny, c, magic), Ay, By), tfy = fmaf(wplane(fy, c, magic), Ay, By);
+            const float tnz = fmaf(wplane(nz, c, magic), Az, Bz), tfz = fmaf(wplane(fz, c, magic), Az, Bz);
             const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));
             const float tf = fminf(fminf(fminf(tfx, tfy), tfz) * widen, bw);
             if (tn <= tf) hit4 |= 1u << (8 * c);
@@ -692,7 +698,8 @@ LT_DEVINL void wnode_step(const WNode* __restrict__ nodes, uint32_t idx, V3<floa
 }
 
 // float64 node step (parity path): planes decoded exactly (p + q * 2^e is exact in double), slab test as in the binary tree
-LT_DEVINL void wnode_step(const WNode* __restrict__ nodes, uint32_t idx, V3<double> o, V3<double> inv, double best, uint32_t octinv, uint2& G, uint2& T) {
+LT_DEVINL void wnode_step(const WNode* __restrict__ nodes, uint32_t idx, V3<double> o, V3<double> inv, double best, uint32_t octinv, uint32_t,
+                          uint2& G, uint2& T) {
     const uint4* p = reinterpret_cast<const uint4*>(nodes + idx);
     const uint4 w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2), w3 = __ldg(p + 3), w4 = __ldg(p + 4);
     const double px = (double)__uint_as_float(w0.x), py = (double)__uint_as_float(w0.y), pz = (double)__uint_as_float(w0.z);
@@ -749,7 +756,7 @@ LT_DEVINL bool wtri_test(const WTri* __restrict__, const int32_t* __restrict__ l
 template <typename R>
 LT_DEVINL void wbvh_run(unsigned amask, WState<R>& s, uint2* stack, int stride, const WNode* __restrict__ nodes, const WTri* __restrict__ wtris,
                         const int32_t* __restrict__ leaf_prims, const TriRec<R>* __restrict__ tris, V3<R> o, V3<R> d, V3<R> inv, R eps, bool anyhit,
-                        int skip, Stats& st, int max_steps) {
+                        int skip, Stats& st, int max_steps, uint32_t magic) {
     const uint32_t octinv = octinv_of(inv);
     for (int step = 0; step < max_steps; ++step) {
         const bool live = s.sp >= 0;
@@ -759,17 +766,21 @@ LT_DEVINL void wbvh_run(unsigned amask, WState<R>& s, uint2* stack, int stride, 
         if (!(nm | tm)) break;
         if (__popc(tm) * LT_WBVH_TRI_WEIGHT >= __popc(nm)) {
             if (want_tri) {
-                const uint32_t j = (uint32_t)__ffs((int)s.T.y) - 1u;
-                s.T.y &= s.T.y - 1u;
-                const uint32_t ti = s.T.x + j;
-                R t;
-                int k;
-                st.tri_tests++;
-                const bool h = wtri_test(wtris, leaf_prims, tris, ti, o, d, t, k);
-                if (h & (k != skip) & (eps < t) & ((t < s.best) | ((t == s.best) & (k < s.prim)))) {
-                    s.best = t;
-                    s.prim = k;
-                    s.leaf = (int)ti;
+#pragma unroll
+                for (int rep = 0; rep < LT_WBVH_TRI_PER_STEP; ++rep) {
+                    if (rep > 0 && s.T.y == 0u) break;
+                    const uint32_t j = (uint32_t)__ffs((int)s.T.y) - 1u;
+                    s.T.y &= s.T.y - 1u;
+                    const uint32_t ti = s.T.x + j;
+                    R t;
+                    int k;
+                    st.tri_tests++;
+                    const bool h = wtri_test(wtris, leaf_prims, tris, ti, o, d, t, k);
+                    if (h & (k != skip) & (eps < t) & ((t < s.best) | ((t == s.best) & (k < s.prim)))) {
+                        s.best = t;
+                        s.prim = k;
+                        s.leaf = (int)ti;
+                    }
                 }
                 if (anyhit && s.prim >= 0) { s.sp = -1; s.G.y = 0u; s.T.y = 0u; }
             }
@@ -781,7 +792,7 @@ LT_DEVINL void wbvh_run(unsigned amask, WState<R>& s, uint2* stack, int stride, 
             const uint32_t idx = s.G.x + (uint32_t)__popc(hits & 0xffu & ~(0xffffffffu << slot));
             if (rest & 0xff000000u) { stack[s.sp * stride] = make_uint2(s.G.x, rest); s.sp++; }
             st.box_tests += 8;
-            wnode_step(nodes, idx, o, inv, s.best, octinv, s.G, s.T);
+            wnode_step(nodes, idx, o, inv, s.best, octinv, magic, s.G, s.T);
         }
         // a lane that has nothing left in hand takes the next postponed group, or is done
         if (s.sp >= 0 && s.T.y == 0u && !(s.G.y & 0xff000000u)) {
@@ -799,33 +810,28 @@ LT_DEVINL void wbvh_run(unsigned amask, WState<R>& s, uint2* stack, int stride, 
 template <typename R>
 LT_DEVINL void wbvh_query(unsigned amask, uint2* stack, int stride, const WNode* __restrict__ nodes, const WTri* __restrict__ wtris,
                           const int32_t* __restrict__ leaf_prims, const TriRec<R>* __restrict__ tris, int n_tris, V3<R> o, V3<R> d, R eps, R tlimit,
-                          bool anyhit, int skip, int& prim, R& best, int& leaf, Stats& st) {
+                          bool anyhit, int skip, int& prim, R& best, int& leaf, Stats& st, uint32_t magic) {
     WState<R> s;
     wbvh_begin<R>(s, n_tris, tlimit, true);
     V3<R> inv = mk<R>((R)1 / d.x, (R)1 / d.y, (R)1 / d.z);
-    wbvh_run<R>(amask, s, stack, stride, nodes, wtris, leaf_prims, tris, o, d, inv, eps, anyhit, skip, st, 0x7fffffff);
+    wbvh_run<R>(amask, s, stack, stride, nodes, wtris, leaf_prims, tris, o, d, inv, eps, anyhit, skip, st, 0x7fffffff, magic);
     prim = s.prim;
     best = s.best;
     leaf = s.leaf;
 }
 
-// LT_WIDE: 1 = the 8-wide compressed hierarchy (shipped), 0 = the binary Karras tree (A/B build variant; needs
-// lt_bvh_build(..., LT_BVH_KEEP_BINARY, ...))
-#ifndef LT_WIDE
-#define LT_WIDE 1
-#endif
-
-// whole-query form with a thread-local stack (record / wavefront / explicit-ray kernels)
+// whole-query form with a thread-local stack (record / wavefront / explicit-ray kernels); `binary` picks the Karras tree
+// (kept by lt_bvh_build(..., LT_BVH_KEEP_BINARY, ...)) instead of the 8-wide hierarchy
 template <typename R>
 LT_DEVINL void lbvh_query(unsigned amask, const SceneView<R>& S, const TriRec<R>* __restrict__ tris, V3<R> o, V3<R> d, R eps, R tlimit, bool anyhit,
-                          int skip, int& prim, R& best, Stats& st) {
-#if LT_WIDE
-    uint2 stack[LT_WBVH_MAX_DEPTH];
-    int leaf;
-    wbvh_query<R>(amask, stack, 1, S.wnodes, S.wtris, S.wleaf_prims, tris, S.n_tris, o, d, eps, tlimit, anyhit, skip, prim, best, leaf, st);
-#else
-    lbvh2_query<R>(amask, S.lbvh, tris, S.n_tris, o, d, eps, tlimit, anyhit, skip, prim, best, st);
-#endif
+                          int skip, int& prim, R& best, Stats& st, bool binary = false) {
+    if (binary) {
+        lbvh2_query<R>(amask, S.lbvh, tris, S.n_tris, o, d, eps, tlimit, anyhit, skip, prim, best, st);
+    } else {
+        uint2 stack[LT_WBVH_MAX_DEPTH];
+        int leaf;
+        wbvh_query<R>(amask, stack, 1, S.wnodes, S.wtris, S.wleaf_prims, tris, S.n_tris, o, d, eps, tlimit, anyhit, skip, prim, best, leaf, st, S.wmagic);
+    }
 }
 
 }  // namespace lt

@@ -301,12 +301,13 @@ struct TreeView {
     const int *left, *right, *rng_lo, *rng_hi;
     const Box *node_boxes, *prim_boxes;
     const uint32_t* sorted_prim;
+    int leaf_max;              // triangles per leaf slot (1..LT_WBVH_LEAF_MAX)
 };
 #define WB_EMPTY ((int)0x80000000)
 #define LB_QUANT_SLACK 0.05      // quanta added to every quantised plane: covers the float32 decode of the traversal (wnode_step)
 LT_DEVINL Box ref_box(const TreeView& t, int c) { return c >= 0 ? t.node_boxes[c] : t.prim_boxes[t.sorted_prim[~c]]; }
 LT_DEVINL int ref_count(const TreeView& t, int c) { return c >= 0 ? t.rng_hi[c] - t.rng_lo[c] + 1 : 1; }
-LT_DEVINL bool ref_is_leaf(const TreeView& t, int c) { return ref_count(t, c) <= LT_WBVH_LEAF_MAX; }
+LT_DEVINL bool ref_is_leaf(const TreeView& t, int c) { return ref_count(t, c) <= t.leaf_max; }
 __host__ __device__ inline float box_area(const Box& b) {
     const float x = b.hi[0] - b.lo[0], y = b.hi[1] - b.lo[1], z = b.hi[2] - b.lo[2];
     return 2.0f * (x * y + y * z + z * x);
@@ -477,7 +478,7 @@ __global__ void emit_wide_kernel(TreeView t, RawTris raw, int* __restrict__ wb, 
             }
             const int ref = c[i];
             const int cnt = ref_count(t, ref);
-            if (cnt <= LT_WBVH_LEAF_MAX) {
+            if (cnt <= t.leaf_max) {
                 meta[s2] = (((1u << cnt) - 1u) << 5) | n_tri;
                 const int first = ref >= 0 ? t.rng_lo[ref] : ~ref;
                 for (int j = 0; j < cnt; ++j) {
@@ -614,7 +615,8 @@ extern "C" int lt_bvh_build(lt_scene* s, int flags, lt_bvh_stats* out) {
     cudaEventRecord(ev.e[3], st);
     LT_CUDA_OK(cudaGetLastError());
     // ---- collapse, breadth first: the wide nodes of a level are contiguous, children in slot order
-    const TreeView tv{left.p, right.p, rng_lo.p, rng_hi.p, node_boxes.p, prim_boxes.p, vi};
+    const int leaf_max = ((flags >> 8) & 3) ? ((flags >> 8) & 3) : LT_WBVH_LEAF_MAX;
+    const TreeView tv{left.p, right.p, rng_lo.p, rng_hi.p, node_boxes.p, prim_boxes.p, vi, leaf_max};
     int level_start = 0, level_n = 1, tri_cursor = 0, levels = 0;
     while (level_n > 0) {
         const int lb = (level_n + LB_THREADS - 1) / LB_THREADS;

@@ -60,11 +60,10 @@ LT_DEVINL void flush_film_warp(double* film, int32_t pix, double acc[3]) {
 #define LT_MIN_BLOCKS_F32 5
 #endif
 #ifndef LT_MIN_BLOCKS_F32_LBVH
-#if LT_WIDE
-#define LT_MIN_BLOCKS_F32_LBVH 5
-#else
-#define LT_MIN_BLOCKS_F32_LBVH 8          // binary tree, memory-latency bound: C3 probe 5: 2.29, 6: 2.53, 7: 2.64, 8: 2.74, 10: 2.73, 12: 2.72 Grays/s
+#define LT_MIN_BLOCKS_F32_LBVH 5          // 8-wide hierarchy: instruction-bound (96 registers); 4 or 5 resident CTAs: 2.06 vs 2.11 Grays/s on C3
 #endif
+#ifndef LT_MIN_BLOCKS_F32_LBVH2
+#define LT_MIN_BLOCKS_F32_LBVH2 8         // binary tree, memory-latency bound: C3 probe 5: 2.29, 6: 2.53, 7: 2.64, 8: 2.74, 10: 2.73, 12: 2.72 Grays/s
 #endif
 #ifndef LT_MIN_BLOCKS_F64
 #define LT_MIN_BLOCKS_F64 3
@@ -83,7 +82,8 @@ LT_DEVINL void flush_film_warp(double* film, int32_t pix, double acc[3]) {
 #endif
 
 template <typename R, int TRAV, int SEM, int PH = 1>
-__global__ void __launch_bounds__(LT_BLOCK, sizeof(R) == 4 ? (TRAV == LT_TRAV_LBVH ? LT_MIN_BLOCKS_F32_LBVH : LT_MIN_BLOCKS_F32) : LT_MIN_BLOCKS_F64)
+__global__ void __launch_bounds__(LT_BLOCK, sizeof(R) == 4 ? (TRAV == LT_TRAV_LBVH ? LT_MIN_BLOCKS_F32_LBVH : TRAV == LT_TRAV_LBVH2 ? LT_MIN_BLOCKS_F32_LBVH2 : LT_MIN_BLOCKS_F32)
+                                                           : LT_MIN_BLOCKS_F64)
 walk_megakernel(const WalkParams<R> P) {
     extern __shared__ __align__(16) char smem[];
     const TriRec<R>* tris = P.S.tris;
@@ -93,7 +93,8 @@ walk_megakernel(const WalkParams<R> P) {
     const float* slabtab = nullptr;
     const uint8_t* flatprim = nullptr;
     ChainTab chain;
-    if (TRAV != LT_TRAV_LBVH) {
+    constexpr bool HIER = TRAV == LT_TRAV_LBVH || TRAV == LT_TRAV_LBVH2;      // a GPU-built hierarchy in global memory
+    if (!HIER) {
         char* cur = smem;
         tris = stage_array(cur, P.S.tris, P.S.n_tris);
         mats = stage_array(cur, P.S.mats, P.S.n_mats);
@@ -150,16 +151,14 @@ walk_megakernel(const WalkParams<R> P) {
     // spread 10..80 steps; whole-query iterations kept ~10 of 32 lanes busy).  Measured on that scene:
     // whole query 1.76, chunk 8: 2.21, 16: 2.48, 24: 2.51, 64: 2.18 Grays/s; letting finished lanes pile up
     // before shading (4..16 lanes) changed nothing (+-1 %).
-#if LT_WIDE
-    // stack of postponed groups in dynamic shared memory: [wide level][thread], 8 bytes each
+    // 8-wide hierarchy: stack of postponed groups in dynamic shared memory, [wide level][thread], 8 bytes each
     uint2* const wstack = reinterpret_cast<uint2*>(smem) + threadIdx.x;
-    WState<R> ts;
-    ts.G = make_uint2(0u, 0u); ts.T = make_uint2(0u, 0u); ts.sp = -1; ts.prim = -1; ts.leaf = -1; ts.best = (R)0;
-#else
-    int tstack[TRAV == LT_TRAV_LBVH ? LT_LBVH_STACK : 1];
+    WState<R> ws8;
+    ws8.G = make_uint2(0u, 0u); ws8.T = make_uint2(0u, 0u); ws8.sp = -1; ws8.prim = -1; ws8.leaf = -1; ws8.best = (R)0;
+    // binary tree: stack in local memory
+    int tstack[TRAV == LT_TRAV_LBVH2 ? LT_LBVH_STACK : 1];
     LbvhState<R> ts;
     ts.cur = LT_LBVH_DONE; ts.sp = 0; ts.prim = -1; ts.best = (R)0;
-#endif
     V3<R> tinv = mk<R>((R)0, (R)0, (R)0);
     bool tracing = false;
     Stats st;
@@ -200,7 +199,7 @@ walk_megakernel(const WalkParams<R> P) {
         for (;;) {
             // ---- regeneration: idle lanes take the next indices of the granule (not ahead of a shadow phase, which
             // they could not join: they are refilled together before the next extension phase)
-            const bool phased = PH && TRAV != LT_TRAV_LBVH && LT_PHASED > 0;
+            const bool phased = PH && !HIER && LT_PHASED > 0;
             const bool shadow_phase = phased && __popc(__ballot_sync(full, ln.qtype == 2)) >= LT_PHASED;
             bool need = ln.qtype == 0;
             unsigned m = shadow_phase ? 0u : __ballot_sync(full, need);
@@ -242,17 +241,18 @@ walk_megakernel(const WalkParams<R> P) {
                 am = __ballot_sync(full, active);
             }
             uint32_t it_memo = 0, it_lidx = 0, it_fovf = 0, it_maxf = 0, it_early = 0;    // this iteration's per-lane events, reduced below
-            if (TRAV == LT_TRAV_LBVH) {
-#if LT_WIDE
+            if constexpr (TRAV == LT_TRAV_LBVH) {
                 if (active && !tracing) {
-                    wbvh_begin<R>(ts, P.S.n_tris, ln.tlimit, true);
+                    wbvh_begin<R>(ws8, P.S.n_tris, ln.tlimit, true);
                     tinv = mk<R>((R)1 / ln.d.x, (R)1 / ln.d.y, (R)1 / ln.d.z);
                     tracing = true;
                 }
-                wbvh_run<R>(full, ts, wstack, LT_BLOCK, P.S.wnodes, P.S.wtris, P.S.wleaf_prims, tris, ln.o, ln.d, tinv, eps, ln.qtype == 2, ln.skip, st,
-                            P.lbvh_chunk);
-                active = tracing && ts.sp < 0;                    // only lanes whose query just completed go on to shade
-#else
+                wbvh_run<R>(full, ws8, wstack, LT_BLOCK, P.S.wnodes, P.S.wtris, P.S.wleaf_prims, tris, ln.o, ln.d, tinv, eps, ln.qtype == 2, ln.skip, st,
+                            P.lbvh_chunk, P.S.wmagic);
+                active = tracing && ws8.sp < 0;                   // only lanes whose query just completed go on to shade
+                if (active) { tracing = false; ts.prim = ws8.prim; ts.best = ws8.best; }
+            }
+            if constexpr (TRAV == LT_TRAV_LBVH2) {
                 if (active && !tracing) {
                     lbvh2_begin<R>(ts, P.S.n_tris, ln.tlimit, true);
                     tinv = mk<R>((R)1 / ln.d.x, (R)1 / ln.d.y, (R)1 / ln.d.z);
@@ -260,7 +260,6 @@ walk_megakernel(const WalkParams<R> P) {
                 }
                 lbvh2_run<R>(full, ts, tstack, P.S.lbvh, tris, ln.o, ln.d, tinv, eps, ln.qtype == 2, ln.skip, st, P.lbvh_chunk);
                 active = tracing && ts.cur == LT_LBVH_DONE;       // only lanes whose query just completed go on to shade
-#endif
                 if (active) tracing = false;
             }
             {
@@ -299,19 +298,17 @@ walk_megakernel(const WalkParams<R> P) {
                 R adv_rand0 = (R)0;
                 if (want == 1) {            // warp-uniform when phases are aligned
                     HitRec<R> hit_rec;
-#if LT_WIDE
                     if constexpr (TRAV == LT_TRAV_LBVH && sizeof(R) == 4) {
                         // the float32 wide-BVH walk shades from the compact leaf-order record it has just tested: the
                         // normal is rebuilt from ab x ac (R/src/primitives.py:108-111), material and is_light ride in c.w
                         if (prim >= 0) {
-                            const float4* wp = reinterpret_cast<const float4*>(P.S.wtris + ts.leaf);
+                            const float4* wp = reinterpret_cast<const float4*>(P.S.wtris + ws8.leaf);
                             const float4 wb = __ldg(wp + 1), wc = __ldg(wp + 2);
                             hit_rec.n = normalize_fast(cross(mk<float>(wb.x, wb.y, wb.z), mk<float>(wc.x, wc.y, wc.z)));
                             const int ml = __float_as_int(wc.w);
                             hit_rec.mat = ml & 0x7fffffff; hit_rec.is_light = (ml >> 31) & 1; hit_rec.valid = true;
                         }
                     }
-#endif
                     stt = shade_extension<R, SEM>(P, ln, prim, t, tris, mats, it_lidx, adv_rand0, hit_rec);
                 } else {
                     stt = shade_shadow<R, SEM, LT_LOCAL_FRAMES>(P, ln, frames, gtid, prim >= 0, it_fovf, it_maxf, adv_rand0);
@@ -444,7 +441,7 @@ __global__ void __launch_bounds__(LT_BLOCK) intersect_kernel(const IntersectPara
             else if (TRAV == LT_TRAV_NEAREST)
                 nearest_query<R>(P.S.tris, P.S.n_tris, o, d, (R)P.eps, Lim<R>::inf(), false, -1, prim, t, st);
             else
-                lbvh_query<R>(am, P.S, P.S.tris, o, d, (R)P.eps, Lim<R>::inf(), false, -1, prim, t, st);
+                lbvh_query<R>(am, P.S, P.S.tris, o, d, (R)P.eps, Lim<R>::inf(), false, -1, prim, t, st, TRAV == LT_TRAV_LBVH2);
             P.prim[r] = prim;
             P.t[r] = prim >= 0 ? (double)t : (double)Lim<double>::inf();
         }
@@ -459,6 +456,6 @@ __global__ void __launch_bounds__(LT_BLOCK) intersect_kernel(const IntersectPara
 // host-side dispatch, instantiated per R in lt_walk_f32.cu / lt_walk_f64.cu
 template <typename R> int launch_walk(const WalkParams<R>& P, int grid, size_t smem, cudaStream_t stream);
 template <typename R> int launch_intersect(const IntersectParams<R>& P, int grid, cudaStream_t stream);
-template <typename R> int walk_kernel_attrs(int trav, int sem, int* regs, int* local_bytes, int* max_blocks_per_sm, size_t smem);
+template <typename R> int walk_kernel_attrs(int trav, int sem, int phased, int* regs, int* local_bytes, int* max_blocks_per_sm, size_t smem);
 
 }  // namespace lt

@@ -96,6 +96,7 @@ struct SceneView {
     const WTri* wtris;            // float32 triangle records in leaf order
     const int32_t* wleaf_prims;   // leaf order -> primitive index (float64 traversal tests TriRec<double>[prim])
     int32_t wbvh_depth;           // wide levels (stack entries a traversal may need)
+    uint32_t wmagic;              // 0x47000000, see wplane() in lt_intersect.cuh
     int32_t n_tris, n_mats, n_lights, n_cnodes, n_cleaves, n_lbvh_nodes;
     int32_t n_cflat;              // primitives referenced by the COMPAT leaves (flattened sequence length)
     int32_t n_nleaves;

@@ -3,7 +3,7 @@
 namespace lt {
 template int launch_walk<double>(const WalkParams<double>&, int, size_t, cudaStream_t);
 template int launch_intersect<double>(const IntersectParams<double>&, int, cudaStream_t);
-template int walk_kernel_attrs<double>(int, int, int*, int*, int*, size_t);
+template int walk_kernel_attrs<double>(int, int, int, int*, int*, int*, size_t);
 template int launch_wavefront<double>(const WalkParams<double>&, unsigned long long*, int, size_t, cudaStream_t);
 template int wavefront_kernel_attrs<double>(int, int, int*, int*, size_t);
 template size_t wavefront_smem_bytes<double>(size_t);

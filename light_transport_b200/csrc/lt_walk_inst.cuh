@@ -21,7 +21,7 @@ static int launch_ph(const WalkParams<R>& P, int grid, size_t smem, cudaStream_t
 // query kind being warp-uniform.  The LBVH walk is never aligned.
 template <typename R, int TRAV, int SEM>
 static int launch_one(const WalkParams<R>& P, int grid, size_t smem, cudaStream_t stream) {
-    if (TRAV != LT_TRAV_LBVH && !P.phased) return launch_ph<R, TRAV, SEM, 0>(P, grid, smem, stream);
+    if (TRAV != LT_TRAV_LBVH && TRAV != LT_TRAV_LBVH2 && !P.phased) return launch_ph<R, TRAV, SEM, 0>(P, grid, smem, stream);
     return launch_ph<R, TRAV, SEM, 1>(P, grid, smem, stream);
 }
 
@@ -37,14 +37,15 @@ int launch_walk(const WalkParams<R>& P, int grid, size_t smem, cudaStream_t stre
         case LT_TRAV_COMPAT: return launch_sem<R, LT_TRAV_COMPAT>(P, grid, smem, stream);
         case LT_TRAV_NEAREST: return launch_sem<R, LT_TRAV_NEAREST>(P, grid, smem, stream);
         case LT_TRAV_LBVH: return launch_sem<R, LT_TRAV_LBVH>(P, grid, smem, stream);
+        case LT_TRAV_LBVH2: return launch_sem<R, LT_TRAV_LBVH2>(P, grid, smem, stream);
     }
     set_error("unknown traversal %d", P.traversal);
     return LT_E_INVALID;
 }
 
-template <typename R, int TRAV, int SEM>
-static int attrs_one(int* regs, int* local_bytes, int* max_blocks, size_t smem) {
-    auto k = walk_megakernel<R, TRAV, SEM>;
+template <typename R, int TRAV, int SEM, int PH>
+static int attrs_ph(int* regs, int* local_bytes, int* max_blocks, size_t smem) {
+    auto k = walk_megakernel<R, TRAV, SEM, PH>;
     cudaFuncAttributes a;
     LT_CUDA_OK(cudaFuncGetAttributes(&a, k));
     if (smem > 48 * 1024) LT_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -56,16 +57,25 @@ static int attrs_one(int* regs, int* local_bytes, int* max_blocks, size_t smem) 
     return LT_OK;
 }
 
+// the variant launch_one() will launch: PH = 0 only exists for the shared-memory scenes
+template <typename R, int TRAV, int SEM>
+static int attrs_one(int phased, int* regs, int* local_bytes, int* max_blocks, size_t smem) {
+    if (TRAV != LT_TRAV_LBVH && TRAV != LT_TRAV_LBVH2 && !phased) return attrs_ph<R, TRAV, SEM, 0>(regs, local_bytes, max_blocks, smem);
+    return attrs_ph<R, TRAV, SEM, 1>(regs, local_bytes, max_blocks, smem);
+}
+
 template <typename R>
-int walk_kernel_attrs(int trav, int sem, int* regs, int* local_bytes, int* max_blocks, size_t smem) {
+int walk_kernel_attrs(int trav, int sem, int phased, int* regs, int* local_bytes, int* max_blocks, size_t smem) {
 #define LT_ATTR(T, S) \
-    if (trav == T && sem == S) return attrs_one<R, T, S>(regs, local_bytes, max_blocks, smem);
+    if (trav == T && sem == S) return attrs_one<R, T, S>(phased, regs, local_bytes, max_blocks, smem);
     LT_ATTR(LT_TRAV_COMPAT, LT_SEM_REFERENCE)
     LT_ATTR(LT_TRAV_COMPAT, LT_SEM_ITERATIVE)
     LT_ATTR(LT_TRAV_NEAREST, LT_SEM_REFERENCE)
     LT_ATTR(LT_TRAV_NEAREST, LT_SEM_ITERATIVE)
     LT_ATTR(LT_TRAV_LBVH, LT_SEM_REFERENCE)
     LT_ATTR(LT_TRAV_LBVH, LT_SEM_ITERATIVE)
+    LT_ATTR(LT_TRAV_LBVH2, LT_SEM_REFERENCE)
+    LT_ATTR(LT_TRAV_LBVH2, LT_SEM_ITERATIVE)
 #undef LT_ATTR
     set_error("unknown kernel variant");
     return LT_E_INVALID;
@@ -135,6 +145,7 @@ int launch_intersect(const IntersectParams<R>& P, int grid, cudaStream_t stream)
         case LT_TRAV_COMPAT: intersect_kernel<R, LT_TRAV_COMPAT><<<grid, LT_BLOCK, 32 + (sizeof(R) == 4 ? (size_t)((((P.S.n_cleaves + 1) >> 1) * LT_SLAB_PAIR_FLOATS * 4 + 15) / 16 * 16 + LT_CHAIN_BYTES) : 0), stream>>>(P); break;
         case LT_TRAV_NEAREST: intersect_kernel<R, LT_TRAV_NEAREST><<<grid, LT_BLOCK, 0, stream>>>(P); break;
         case LT_TRAV_LBVH: intersect_kernel<R, LT_TRAV_LBVH><<<grid, LT_BLOCK, 0, stream>>>(P); break;
+        case LT_TRAV_LBVH2: intersect_kernel<R, LT_TRAV_LBVH2><<<grid, LT_BLOCK, 0, stream>>>(P); break;
         default: set_error("unknown traversal %d", P.traversal); return LT_E_INVALID;
     }
     LT_CUDA_OK(cudaGetLastError());

@@ -12,6 +12,7 @@ from __future__ import annotations
 import atexit
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 
@@ -20,7 +21,7 @@ from . import _pack, compat_bvh
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liblt_b200.so")     # (A/B tools under tools/ point this at a variant build before first use)
 
-TRAVERSAL = {"compat": 0, "nearest": 1, "lbvh": 2}
+TRAVERSAL = {"compat": 0, "nearest": 1, "lbvh": 2, "lbvh2": 3}      # lbvh: 8-wide compressed hierarchy; lbvh2: the binary tree under it
 SEMANTICS = {"reference": 0, "iterative": 1}
 REAL = {"f32": 0, "f64": 1}
 SCHEDULER = {"megakernel": 0, "wavefront": 1}
@@ -115,6 +116,7 @@ def _ptr(a, typ):
 
 
 _ctx_cache: dict[int, C.c_void_p] = {}
+_live_renderers: "weakref.WeakSet[Renderer]" = None     # created below (needs the class)
 
 
 def _get_ctx(device: int) -> C.c_void_p:
@@ -130,6 +132,19 @@ def _get_ctx(device: int) -> C.c_void_p:
 
 @atexit.register
 def _destroy_contexts():
+    """Scenes first, then their contexts: a Renderer that is still alive at exit (module-level objects, scripts that never
+    call close()) must not outlive the lt_ctx its scene points into."""
+    try:
+        from . import parallel
+        parallel.close_comms()
+    except Exception:
+        pass
+    if _live_renderers is not None:
+        for r in list(_live_renderers):
+            try:
+                r.close()
+            except Exception:
+                pass
     for ctx in _ctx_cache.values():
         try:
             lib().lt_destroy(ctx)
@@ -143,9 +158,15 @@ class Renderer:
 
     def __init__(self, packed: _pack.PackedScene, nodes: compat_bvh.CompatNodes | None = None, device: int = 0,
                  build_lbvh: bool = False):
+        global _live_renderers
         L = lib()
         self._ctx = _get_ctx(device)
+        self._device = device
+        self._stream = None           # cudaStream_t this renderer's work runs on (None: the context's own stream)
         self._scene = C.c_void_p()
+        if _live_renderers is None:
+            _live_renderers = weakref.WeakSet()
+        _live_renderers.add(self)
         f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
         i = lambda a: np.ascontiguousarray(a, dtype=np.int32)
         self._keep = dict(tri_v0=f(packed.tri_v0), tri_v1=f(packed.tri_v1), tri_v2=f(packed.tri_v2), tri_n=f(packed.tri_n),
@@ -167,10 +188,11 @@ class Renderer:
         if nodes is not None:
             self.set_compat_bvh(nodes)
         if build_lbvh:
-            self.build_lbvh()
+            self.build_lbvh(keep_binary=(build_lbvh == "binary"))
 
     # -- structures --------------------------------------------------------------------------------
     def set_compat_bvh(self, nodes: compat_bvh.CompatNodes):
+        self._bind()
         d = LtNodeDesc()
         keep = dict(bmin=np.ascontiguousarray(nodes.bmin, np.float64), bmax=np.ascontiguousarray(nodes.bmax, np.float64),
                     prim_off=np.ascontiguousarray(nodes.prim_off, np.int32), second=np.ascontiguousarray(nodes.second, np.int32),
@@ -182,10 +204,11 @@ class Renderer:
         _check(lib().lt_scene_set_compat_bvh(self._scene, C.byref(d)))
         self.has_compat = True
 
-    def build_lbvh(self, keep_binary=False):
+    def build_lbvh(self, keep_binary=False, leaf_max=0):
         """GPU LBVH build (Morton, radix sort, Karras, refit) + collapse into the 8-wide compressed hierarchy."""
+        self._bind()
         st = LtBvhStats()
-        _check(lib().lt_bvh_build(self._scene, C.c_int(1 if keep_binary else 0), C.byref(st)))
+        _check(lib().lt_bvh_build(self._scene, C.c_int((1 if keep_binary else 0) | ((int(leaf_max) & 3) << 8)), C.byref(st)))
         self.lbvh_stats = dict(n_prims=st.n_prims, n_nodes=st.n_nodes, max_depth=st.max_depth, binary_depth=st.binary_depth,
                                build_ms=st.build_ms, sort_ms=st.sort_ms, collapse_ms=st.collapse_ms, sah_cost=st.sah_cost,
                                bytes=st.bytes, root_bmin=list(st.root_bmin), root_bmax=list(st.root_bmax))
@@ -202,6 +225,7 @@ class Renderer:
         prim = np.empty(n, np.int32)
         t = np.empty(n, np.float64)
         cnt = LtCounters()
+        self._bind()
         _check(lib().lt_intersect(self._scene, C.c_int(TRAVERSAL[traversal]), C.c_int(REAL[real]), _ptr(o, PD), _ptr(d, PD),
                                   C.c_int64(n), _ptr(prim, PI32), _ptr(t, PD), C.byref(cnt)))
         return prim, t, cnt.as_dict()
@@ -249,6 +273,7 @@ class Renderer:
             raise ValueError("light_idx must be a numpy array")
         samples = np.zeros((height, width, s1 - s0, 3), np.float64) if return_samples else None
         cnt = LtCounters()
+        self._bind()
         if image is not None:
             # film stays on the device; one D2H of the finished image (lt_render_image)
             _check(lib().lt_render_image(self._scene, C.byref(p), _ptr(rand0, PD), _ptr(rand1, PD), _ptr(light_idx, PI32),
@@ -297,6 +322,7 @@ class Renderer:
             out["rlp_plus"] = np.zeros((height, width, spp, 2 * D, D))
             out["record_s"] = np.full((height, width, spp, 2 * D), 0.01)      # _s of :210,230
         cnt = LtCounters()
+        self._bind()
         _check(lib().lt_render_records(self._scene, C.byref(p), _ptr(rand0, PD), _ptr(rand1, PD), _ptr(l0, PD), _ptr(l1, PD),
                                        _ptr(light_idx, PI32), _ptr(out["samples"], PD), _ptr(out["record_log_pdf"], PD),
                                        _ptr(out["scene_record_log_pdf"], PD), _ptr(out["bounce_record"], C.POINTER(C.c_int8)),
@@ -314,13 +340,25 @@ class Renderer:
             n = int(film_sum.numel())
             if out is None:
                 raise ValueError("pass out= for device buffers")
+        self._bind()
         _check(lib().lt_film_finalize(self._ctx, _ptr(film_sum, PD), C.c_int64(n), C.c_int64(spp_total), _ptr(out, PD)))
         return out
 
     def set_stream(self, cuda_stream):
         """Run this renderer's kernels on ``cuda_stream`` (int handle, e.g.
-        ``torch.cuda.current_stream().cuda_stream``); ``None`` restores its own stream."""
-        _check(lib().lt_set_stream(self._ctx, C.c_void_p(cuda_stream) if cuda_stream else None))
+        ``torch.cuda.current_stream().cuda_stream``); ``None`` = the context's own stream.  The stream belongs to the
+        Renderer: it is bound to the (per-device, shared) context at the start of each of its calls, so renderers on one
+        device do not disturb one another."""
+        self._stream = int(cuda_stream) if cuda_stream else None
+        self._bind()
+
+    def _bind(self):
+        if self._ctx_gone():
+            raise LtError(-1, "the library context of this Renderer was destroyed (interpreter exit)")
+        _check(lib().lt_set_stream(self._ctx, C.c_void_p(self._stream) if self._stream else None))
+
+    def _ctx_gone(self):
+        return _ctx_cache.get(self._device) is not self._ctx
 
     def device_info(self):
         sm, khz, cc0, cc1 = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
@@ -329,6 +367,7 @@ class Renderer:
         return dict(sm_count=sm.value, clock_khz=khz.value, global_mem=mem.value, cc=(cc0.value, cc1.value))
 
     def measure_fp32_peak(self):
+        self._bind()
         v = C.c_double()
         _check(lib().lt_measure_fp32_peak(self._ctx, C.byref(v)))
         return v.value
@@ -345,9 +384,10 @@ class Renderer:
         return v.value
 
     def close(self):
+        """Free the device scene.  Safe to call twice, and a no-op once the context is gone (interpreter exit)."""
         if getattr(self, "_scene", None) and self._scene:
-            self.set_stream(None)
-            lib().lt_scene_destroy(self._scene)
+            if not self._ctx_gone():
+                lib().lt_scene_destroy(self._scene)
             self._scene = C.c_void_p()
 
     def __del__(self):
@@ -383,7 +423,7 @@ def intersect(primitives, bvh, o, d, *, lights=(), traversal="compat", real="f64
 
 def render_scene(scene, primitives, bvh=None, *, spp=None, rng=None, seed=0, semantics="reference", traversal="compat",
                  light_idx=None, real=None, return_samples=False, world=None, device=None, return_info=False,
-                 scheduler="auto"):
+                 scheduler="auto", all_ranks=False):
     """Drop-in for ``render_scene(scene, primitives, bvh)``.
 
     ``scene``/``primitives``/``bvh`` are the reference's objects (or the ``api`` mirrors / a
@@ -395,7 +435,9 @@ def render_scene(scene, primitives, bvh=None, *, spp=None, rng=None, seed=0, sem
     numbers keyed by ``seed`` (needed for configs whose ``Scene`` arrays cannot exist, Q15).
     ``real`` defaults to "f64" for replay and "f32" for philox.
     ``world=(rank, world_size)`` or an initialised ``torch.distributed`` group shards the samples
-    ``[r*spp/R, (r+1)*spp/R)`` across ranks and sums the film with ONE reduce (NCCL on GPUs).
+    ``[r*spp/R, (r+1)*spp/R)`` across ranks and sums the film with ONE reduce to rank 0 (NCCL on GPUs): rank 0
+    finalizes, copies the image to the host and returns it, the other ranks return ``None`` for the image
+    (``all_ranks=True``: all-reduce, every rank gets the image).
     """
     H, W, D = int(scene.height), int(scene.width), int(scene.max_depth)
     n_spp = int(scene.number_of_samples) if spp is None else int(spp)
@@ -443,13 +485,13 @@ def render_scene(scene, primitives, bvh=None, *, spp=None, rng=None, seed=0, sem
                                            real=real, rand0=rand0, rand1=rand1, light_idx=light_idx, seed=seed, film=film,
                                            return_samples=return_samples, image=image, scheduler=scheduler)
         if use_dist:
-            parallel.reduce_film(film, group)                    # the single collective of a pass (NCCL)
-            image_t = torch.empty_like(film)
-            r.finalize(film, n_spp, out=image_t)
-            image = image_t.cpu().numpy().reshape(H, W, 3)
+            # the single collective of a pass: lt_film_reduce (ncclReduce on the library's communicator + finalize on the root)
+            parallel.reduce_film(film, group, root=None if all_ranks else 0, device=device, spp_total=n_spp)
+            if all_ranks or rank == 0:
+                image = film.cpu().numpy().reshape(H, W, 3)
     finally:
         r.close()
-    if getattr(scene, "image", None) is not None and (size == 1 or use_dist):
+    if image is not None and getattr(scene, "image", None) is not None and (size == 1 or use_dist):
         try:
             scene.image[...] = image
         except Exception:

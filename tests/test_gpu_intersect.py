@@ -18,7 +18,7 @@ def renderers():
     out = {}
     for sf, _ in RAY_SETS:
         ps, nodes, cam, f = load_scene(sf)
-        out[sf] = host.Renderer(ps, nodes, build_lbvh=True)
+        out[sf] = host.Renderer(ps, nodes, build_lbvh="binary")
     yield out
     for r in out.values():
         r.close()
@@ -35,7 +35,7 @@ def test_compat_f64_bit_exact(renderers, scene_file, ray_file):
     assert cnt["tri_tests"] > 0 and cnt["box_tests"] > 0
 
 
-@pytest.mark.parametrize("trav", ["nearest", "lbvh"])
+@pytest.mark.parametrize("trav", ["nearest", "lbvh", "lbvh2"])
 @pytest.mark.parametrize("scene_file,ray_file", RAY_SETS)
 def test_nearest_f64_bit_exact(renderers, scene_file, ray_file, trav):
     r = np.load(os.path.join(GOLDEN, ray_file))
@@ -45,7 +45,7 @@ def test_nearest_f64_bit_exact(renderers, scene_file, ray_file, trav):
     assert np.array_equal(t[hit], r["nearest_t"][hit])
 
 
-@pytest.mark.parametrize("trav,key", [("compat", "compat"), ("nearest", "nearest"), ("lbvh", "nearest")])
+@pytest.mark.parametrize("trav,key", [("compat", "compat"), ("nearest", "nearest"), ("lbvh", "nearest"), ("lbvh2", "nearest")])
 @pytest.mark.parametrize("scene_file,ray_file", RAY_SETS)
 def test_f32_disagreements_counted(renderers, scene_file, ray_file, trav, key, record_property):
     r = np.load(os.path.join(GOLDEN, ray_file))
@@ -58,7 +58,7 @@ def test_f32_disagreements_counted(renderers, scene_file, ray_file, trav, key, r
     ok = ~bad & (prim >= 0)
     assert np.allclose(t[ok], ref_t[ok], rtol=2e-4, atol=1e-4)
     # f32 LBVH and f32 all-primitive scan implement the same semantics in the same arithmetic
-    if trav == "lbvh":
+    if trav in ("lbvh", "lbvh2"):
         p2, t2, _ = renderers[scene_file].intersect(r["o"], r["d"], "nearest", "f32")
         assert (p2 != prim).mean() < 2e-3
 
@@ -71,7 +71,7 @@ def test_edge_cases(renderers):
     # rays that leave through the open front of the box miss; axis-parallel rays (inf in 1/d) work
     o = np.array([[5, 5, 0.0], [5, 5, 0], [5, 5, 0], [0, 0, 8.0]])
     d = np.array([[0, 0, 1.0], [0, -1, 0], [1, 0, 0], [0, 0, 1.0]])
-    for trav in ("compat", "nearest", "lbvh"):
+    for trav in ("compat", "nearest", "lbvh", "lbvh2"):
         p, t, _ = R.intersect(o, d, trav, "f64")
         assert p[0] == -1 and np.isinf(t[0]) and p[3] == -1
         assert p[1] in (6, 7) and abs(t[1] - 12.5) < 1e-12          # floor
@@ -164,7 +164,7 @@ def c3_scene():
     from light_transport_b200 import host, scenes, _pack
     base, _, cam, f = load_scene("lts_scene.npz")
     ps = _pack.from_arrays(scenes.heightfield(nx=1000, ny=500), base=base)
-    R = host.Renderer(ps, None, build_lbvh=True)
+    R = host.Renderer(ps, None, build_lbvh="binary")
     yield R, ps, cam, f
     R.close()
 
@@ -213,6 +213,8 @@ def test_c3_full_size_f64_equals_gpu_scan_and_f32_counted(c3_scene, record_prope
     p_l, t_l, _ = R.intersect(o, d, "lbvh", "f64")
     p_n, t_n, _ = R.intersect(o, d, "nearest", "f64")
     assert np.array_equal(p_l, p_n) and np.array_equal(t_l, t_n)
+    p_2, t_2, _ = R.intersect(o, d, "lbvh2", "f64")                          # the binary tree the hierarchy is collapsed from
+    assert np.array_equal(p_2, p_n) and np.array_equal(t_2, t_n)
     p_f, t_f, _ = R.intersect(o, d, "lbvh", "f32")
     bad = p_f != p_l
     both = bad & (p_f >= 0) & (p_l >= 0)
@@ -236,7 +238,8 @@ def test_c3_walk_f64_replays_oracle(c3_scene, oracle):
     assert (rel_err(samples, o_samples) > 1e-5).sum() == 0
     assert cnt["rays_ext"] == o_cnt["rays_ext"] and cnt["rays_shadow"] == o_cnt["rays_shadow"]
     # float32 walk of the same streams: a few paths branch differently at edges; counted and bounded
-    _, s32, _ = R.render(traversal="lbvh", real="f32", return_samples=True, **kw)
-    differ = (rel_err(s32, o_samples) > 1e-3).any(axis=-1).mean()
-    print(f"C3 walk: {100 * differ:.2f} % of float32 paths differ from the float64 oracle by more than 1e-3")
-    assert differ < 0.02
+    for trav in ("lbvh", "lbvh2"):
+        _, s32, _ = R.render(traversal=trav, real="f32", return_samples=True, **kw)
+        differ = (rel_err(s32, o_samples) > 1e-3).any(axis=-1).mean()
+        print(f"C3 walk, {trav}: {100 * differ:.2f} % of float32 paths differ from the float64 oracle by more than 1e-3")
+        assert differ < 0.02

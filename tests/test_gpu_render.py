@@ -18,7 +18,7 @@ REL_TOL = 1e-5          # BASELINE.json north_star: "per-path radiance must agre
 def R_lts():
     from light_transport_b200 import host
     ps, nodes, cam, f = load_scene("lts_scene.npz")
-    r = host.Renderer(ps, nodes, build_lbvh=True)
+    r = host.Renderer(ps, nodes, build_lbvh="binary")
     yield r
     r.close()
 
@@ -69,7 +69,7 @@ def test_replay_control_flow_equals_oracle(R_lts, R_mirror, oracle, scene_file, 
 
 
 @pytest.mark.parametrize("semantics", ["reference", "iterative"])
-@pytest.mark.parametrize("trav", ["compat", "nearest", "lbvh"])
+@pytest.mark.parametrize("trav", ["compat", "nearest", "lbvh", "lbvh2"])
 def test_philox_f64_replays_oracle(R_lts, oracle, trav, semantics):
     ps, nodes, cam, f = load_scene("lts_scene.npz")
     kw = dict(width=40, height=24, spp=6, max_depth=8, camera=cam, f_distance=f, semantics=semantics, seed=11)

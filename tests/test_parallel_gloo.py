@@ -29,6 +29,9 @@ def _worker(rank, world, port, out_dir):
     t = torch.from_numpy(film.reshape(-1).copy())
     parallel.reduce_film(t)                      # all-reduce: every rank ends with the full film
     np.save(os.path.join(out_dir, f"film_{rank}.npy"), t.numpy())
+    t2 = torch.from_numpy(film.reshape(-1).copy())
+    parallel.reduce_film(t2, root=0, spp_total=spp)     # reduce to rank 0 + fused finalize there (the GPU path: lt_film_reduce)
+    np.save(os.path.join(out_dir, f"image_{rank}.npy"), t2.numpy())
     np.save(os.path.join(out_dir, f"paths_{rank}.npy"), np.array([cnt["paths"]]))
     dist.destroy_process_group()
 
@@ -43,4 +46,6 @@ def test_two_rank_film_reduce(tmp_path, oracle):
     f1 = np.load(tmp_path / "film_1.npy")
     assert np.array_equal(f0, f1)
     assert np.allclose(f0.reshape(full.shape), full, rtol=1e-12, atol=1e-12)
+    img0 = np.load(tmp_path / "image_0.npy")
+    assert np.allclose(img0.reshape(full.shape), np.clip(full / 6, 0, 1), rtol=1e-12, atol=1e-12)     # R/src/path_tracing.py:304-305
     assert int(np.load(tmp_path / "paths_0.npy")[0] + np.load(tmp_path / "paths_1.npy")[0]) == cnt["paths"]

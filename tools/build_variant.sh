@@ -10,5 +10,5 @@ nvcc $C --use_fast_math "$@" -c lt_walk_f32.cu -o ../../variants/walk_f32_$name.
 nvcc $C -fmad=false "$@" -c lt_walk_f64.cu -o ../../variants/walk_f64_$name.o &
 nvcc $C "$@" -c lt_api.cu -o ../../variants/api_$name.o &
 wait
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../../variants/liblt_$name.so ../../variants/api_$name.o lt_lbvh.o lt_medium.o ../../variants/walk_f32_$name.o ../../variants/walk_f64_$name.o -lcudart
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../../variants/liblt_$name.so ../../variants/api_$name.o lt_lbvh.o lt_medium.o lt_comm.o ../../variants/walk_f32_$name.o ../../variants/walk_f64_$name.o -lcudart -ldl
 echo built variants/liblt_$name.so

@@ -13,6 +13,7 @@ ap.add_argument("--nx", type=int, default=1000)
 ap.add_argument("--ny", type=int, default=500)
 ap.add_argument("--l2", action="store_true", help="also run the L2 / FP peaks micro-benchmarks")
 ap.add_argument("--reps", type=int, default=2)
+ap.add_argument("--leaf", type=int, default=0)
 a = ap.parse_args()
 import torch
 from light_transport_b200 import api, host, pack_scene, scenes, from_arrays
@@ -21,7 +22,7 @@ if a.lib:
 objs, lights, cam, depth = scenes.lts_scene(api)
 ps = from_arrays(scenes.heightfield(nx=a.nx, ny=a.ny), base=pack_scene(objs, lights))
 R = host.Renderer(ps, None)
-print("lbvh:", R.build_lbvh(keep_binary=a.binary))
+print("lbvh:", R.build_lbvh(keep_binary=a.binary, leaf_max=a.leaf))
 film = torch.zeros(1080 * 1920 * 3, dtype=torch.float64, device="cuda")
 kw = dict(width=1920, height=1080, spp=a.spp, max_depth=8, camera=cam, f_distance=depth, seed=3, semantics="iterative", traversal="lbvh",
           real="f32", film=film)

@@ -91,7 +91,8 @@ class Scene:
     """R/src/scene.py:53-73.
 
     Like the reference, the constructor pre-draws ``rand_0``/``rand_1`` of shape
-    ``[H, W, spp, max_depth]`` from NumPy's global generator (Q15) unless
+    ``[H, W, spp, max_depth]`` from NumPy's global generator (Q15), their logits and the
+    ``bounce_record`` / ``record_log_pdf`` side-effect arrays (``:70-73``) unless
     ``allocate=False`` is given; configs whose arrays would not fit (C2: 704 GB) pass
     ``allocate=False`` and render with ``rng="philox"``.
     """
@@ -115,9 +116,15 @@ class Scene:
             shape = (height, width, number_of_samples, max_depth)
             self.rand_0 = np.random.rand(*shape)
             self.rand_1 = np.random.rand(*shape)
+            with np.errstate(divide="ignore"):
+                self.rand_0_logit = np.log(self.rand_0 / (1 - self.rand_0))          # R/src/scene.py:70-71
+                self.rand_1_logit = np.log(self.rand_1 / (1 - self.rand_1))
+            self.bounce_record = np.ones(shape, dtype=np.int8)                       # :72
+            self.record_log_pdf = np.zeros(shape, dtype=np.float64)                  # :73
         else:
-            self.rand_0 = None
-            self.rand_1 = None
+            self.rand_0 = self.rand_1 = None
+            self.rand_0_logit = self.rand_1_logit = None
+            self.bounce_record = self.record_log_pdf = None
 
 
 def generate_area_light_samples(tri_1, tri_2, source_mat, number_of_samples, total_area):

@@ -52,7 +52,7 @@ LT_DEVINL bool tri_intersect(const TriRec<R>& T, V3<R> o, V3<R> d, R& t_out) {
 // returns False as soon as t0 > t1; t0 only grows and t1 only shrinks (a NaN candidate never
 // replaces them), so one comparison after the third axis gives the same answer.
 template <typename R>
-LT_DEVINL bool slab(const R* bmin, const R* bmax, V3<R> o, V3<R> inv) {
+LT_DEVINL bool slab(const R* bmin, const R* bmax, V3<R> o, V3<R> inv, V3<R> = V3<R>{(R)0, (R)0, (R)0}) {
     const R eps32 = (R)5.9604644775390625e-08;
     const R widen = (R)1 + (R)2 * (((R)3 * eps32) / ((R)1 - (R)3 * eps32));
     R t0 = 0, t1 = Lim<R>::inf();
@@ -73,11 +73,20 @@ LT_DEVINL bool slab(const R* bmin, const R* bmax, V3<R> o, V3<R> inv) {
 // float32 overload: min/max instructions instead of compare+select (6 FMNMX fewer per axis).  Differs
 // from the form above only when a slab distance is NaN (origin exactly on a box plane AND a direction
 // component exactly zero): fminf/fmaxf drop the NaN operand, the reference keeps its swap order.
-LT_DEVINL bool slab(const float* bmin, const float* bmax, V3<float> o, V3<float> inv) {
+//
+// `sh` (float32 walk): the reference offsets every secondary ray's origin by EPSILON = 1e-6 (along the new direction, or
+// along the surface normal: path_tracing.py:69,82,104,134,139), which float32 cannot represent at |x| ~ 7.5 — the origin
+// stays ON the surface.  For the triangle tests that is handled by skipping the origin primitive; for BOUNDS it matters
+// too: a wall's leaf box is flat, a ray that starts on it sees slab distances 0 <= 0 and "hits" the box, while the
+// reference's ray, 1e-6 off the wall, misses it — and in COMPAT a bounds hit feeds the visited marks (kill masks), i.e.
+// it changes which OTHER leaves are skipped (measured on C2: floor pixels 4 % too dark).  An origin offset delta shifts
+// the slab distances of axis k by delta_k / d_k, so the walk carries sh_k = delta_k / d_k (= EPSILON on every axis for an
+// offset along the ray itself) and the slab distances are formed as (b - o) * inv - sh, one FMA instead of the multiply.
+LT_DEVINL bool slab(const float* bmin, const float* bmax, V3<float> o, V3<float> inv, V3<float> sh = V3<float>{0.0f, 0.0f, 0.0f}) {
     const float widen = 1.0f + 2.0f * ((3.0f * 5.9604644775390625e-08f) / (1.0f - 3.0f * 5.9604644775390625e-08f));
-    float ax = (bmin[0] - o.x) * inv.x, bx = (bmax[0] - o.x) * inv.x;
-    float ay = (bmin[1] - o.y) * inv.y, by = (bmax[1] - o.y) * inv.y;
-    float az = (bmin[2] - o.z) * inv.z, bz = (bmax[2] - o.z) * inv.z;
+    float ax = fmaf(bmin[0] - o.x, inv.x, -sh.x), bx = fmaf(bmax[0] - o.x, inv.x, -sh.x);
+    float ay = fmaf(bmin[1] - o.y, inv.y, -sh.y), by = fmaf(bmax[1] - o.y, inv.y, -sh.y);
+    float az = fmaf(bmin[2] - o.z, inv.z, -sh.z), bz = fmaf(bmax[2] - o.z, inv.z, -sh.z);
     float t0 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
     float t1 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)) * widen;
     return !(t0 > t1);
@@ -124,7 +133,7 @@ LT_DEVINL void build_flat_prims(uint8_t* tab, const CompatLeaf<R>* leaves, int n
 // the small-scene path needs positions and primitive indices that fit 32-bit masks / bytes
 LT_DEVINL bool compat_small(int n_leaves, int n_cflat, int n_tris) { return n_leaves <= 32 && n_cflat <= 32 && n_tris <= 256; }
 
-LT_DEVINL uint64_t slab_pairs_mask(const float* tab, int n_leaves, V3<float> o, V3<float> inv) {
+LT_DEVINL uint64_t slab_pairs_mask(const float* tab, int n_leaves, V3<float> o, V3<float> inv, V3<float> sh) {
     const float widen = 1.0f + 2.0f * ((3.0f * 5.9604644775390625e-08f) / (1.0f - 3.0f * 5.9604644775390625e-08f));
     const float4* tx = reinterpret_cast<const float4*>(tab) + (__float_as_uint(inv.x) >> 31);
     const float4* ty = reinterpret_cast<const float4*>(tab) + 2 + (__float_as_uint(inv.y) >> 31);
@@ -132,6 +141,7 @@ LT_DEVINL uint64_t slab_pairs_mask(const float* tab, int n_leaves, V3<float> o, 
     const float2 nox = make_float2(-o.x, -o.x), noy = make_float2(-o.y, -o.y), noz = make_float2(-o.z, -o.z);
     const float2 ivx = make_float2(inv.x, inv.x), ivy = make_float2(inv.y, inv.y), ivz = make_float2(inv.z, inv.z);
     const float2 w2 = make_float2(widen, widen);
+    const float2 nsx = make_float2(-sh.x, -sh.x), nsy = make_float2(-sh.y, -sh.y), nsz = make_float2(-sh.z, -sh.z);
     const int n_pairs = (n_leaves + 1) >> 1;
     uint64_t hm = 0;
     for (int p0 = 0; p0 < n_pairs; p0 += 16) {          // 32 leaves per 32-bit word
@@ -141,12 +151,12 @@ LT_PRAGMA_UNROLL(LT_SLAB_UNROLL)
         for (int q = 0; q < pe; ++q) {
             const int p = p0 + q;
             const float4 X = tx[6 * p], Y = ty[6 * p], Z = tz[6 * p];
-            const float2 nx = __fmul2_rn(__fadd2_rn(make_float2(X.x, X.y), nox), ivx);
-            const float2 fx = __fmul2_rn(__fadd2_rn(make_float2(X.z, X.w), nox), ivx);
-            const float2 ny = __fmul2_rn(__fadd2_rn(make_float2(Y.x, Y.y), noy), ivy);
-            const float2 fy = __fmul2_rn(__fadd2_rn(make_float2(Y.z, Y.w), noy), ivy);
-            const float2 nz = __fmul2_rn(__fadd2_rn(make_float2(Z.x, Z.y), noz), ivz);
-            const float2 fz = __fmul2_rn(__fadd2_rn(make_float2(Z.z, Z.w), noz), ivz);
+            const float2 nx = __ffma2_rn(__fadd2_rn(make_float2(X.x, X.y), nox), ivx, nsx);
+            const float2 fx = __ffma2_rn(__fadd2_rn(make_float2(X.z, X.w), nox), ivx, nsx);
+            const float2 ny = __ffma2_rn(__fadd2_rn(make_float2(Y.x, Y.y), noy), ivy, nsy);
+            const float2 fy = __ffma2_rn(__fadd2_rn(make_float2(Y.z, Y.w), noy), ivy, nsy);
+            const float2 nz = __ffma2_rn(__fadd2_rn(make_float2(Z.x, Z.y), noz), ivz, nsz);
+            const float2 fz = __ffma2_rn(__fadd2_rn(make_float2(Z.z, Z.w), noz), ivz, nsz);
             const float t0a = fmaxf(fmaxf(nx.x, ny.x), fmaxf(nz.x, 0.0f));
             const float t0b = fmaxf(fmaxf(nx.y, ny.y), fmaxf(nz.y, 0.0f));
             const float2 t1 = __fmul2_rn(make_float2(fminf(fminf(fx.x, fy.x), fz.x), fminf(fminf(fx.y, fy.y), fz.y)), w2);
@@ -205,21 +215,22 @@ LT_DEVINL void build_chains(float* tab, uint16_t* meta, const CompatNode<float>*
     }
 }
 
-LT_DEVINL uint32_t chain_mask(const float* tab_oct, int n_pairs, V3<float> o, V3<float> inv) {
+LT_DEVINL uint32_t chain_mask(const float* tab_oct, int n_pairs, V3<float> o, V3<float> inv, V3<float> sh) {
     const float widen = 1.0f + 2.0f * ((3.0f * 5.9604644775390625e-08f) / (1.0f - 3.0f * 5.9604644775390625e-08f));
     const float4* t4 = reinterpret_cast<const float4*>(tab_oct);
     const float2 nox = make_float2(-o.x, -o.x), noy = make_float2(-o.y, -o.y), noz = make_float2(-o.z, -o.z);
     const float2 ivx = make_float2(inv.x, inv.x), ivy = make_float2(inv.y, inv.y), ivz = make_float2(inv.z, inv.z);
     const float2 w2 = make_float2(widen, widen);
+    const float2 nsx = make_float2(-sh.x, -sh.x), nsy = make_float2(-sh.y, -sh.y), nsz = make_float2(-sh.z, -sh.z);
     uint32_t m = 0;
     for (int p = 0; p < n_pairs; ++p) {
         const float4 X = t4[3 * p], Y = t4[3 * p + 1], Z = t4[3 * p + 2];
-        const float2 nx = __fmul2_rn(__fadd2_rn(make_float2(X.x, X.y), nox), ivx);
-        const float2 fx = __fmul2_rn(__fadd2_rn(make_float2(X.z, X.w), nox), ivx);
-        const float2 ny = __fmul2_rn(__fadd2_rn(make_float2(Y.x, Y.y), noy), ivy);
-        const float2 fy = __fmul2_rn(__fadd2_rn(make_float2(Y.z, Y.w), noy), ivy);
-        const float2 nz = __fmul2_rn(__fadd2_rn(make_float2(Z.x, Z.y), noz), ivz);
-        const float2 fz = __fmul2_rn(__fadd2_rn(make_float2(Z.z, Z.w), noz), ivz);
+        const float2 nx = __ffma2_rn(__fadd2_rn(make_float2(X.x, X.y), nox), ivx, nsx);
+        const float2 fx = __ffma2_rn(__fadd2_rn(make_float2(X.z, X.w), nox), ivx, nsx);
+        const float2 ny = __ffma2_rn(__fadd2_rn(make_float2(Y.x, Y.y), noy), ivy, nsy);
+        const float2 fy = __ffma2_rn(__fadd2_rn(make_float2(Y.z, Y.w), noy), ivy, nsy);
+        const float2 nz = __ffma2_rn(__fadd2_rn(make_float2(Z.x, Z.y), noz), ivz, nsz);
+        const float2 fz = __ffma2_rn(__fadd2_rn(make_float2(Z.z, Z.w), noz), ivz, nsz);
         const float t0a = fmaxf(fmaxf(nx.x, ny.x), fmaxf(nz.x, 0.0f));
         const float t0b = fmaxf(fmaxf(nx.y, ny.y), fmaxf(nz.y, 0.0f));
         const float2 t1 = __fmul2_rn(make_float2(fminf(fminf(fx.x, fy.x), fz.x), fminf(fminf(fx.y, fy.y), fz.y)), w2);
@@ -260,7 +271,8 @@ LT_DEVINL double shfl_real(double v, int src) { return __shfl_sync(0xffffffffu, 
 template <typename R>
 LT_DEVINL void compat_query(unsigned amask, const CompatNode<R>* nodes, const CompatLeaf<R>* leaves, int n_leaves, const float* slabtab,
                             const uint8_t* flatprim, const TriRec<R>* tris, V3<R> o, V3<R> d, R eps, R tlimit, bool anyhit, int skip, int& prim, R& best,
-                            Stats& st, bool live = true, WarpScratch<R> ws = WarpScratch<R>(), ChainTab chain = ChainTab(), bool descent = true) {
+                            Stats& st, bool live = true, WarpScratch<R> ws = WarpScratch<R>(), ChainTab chain = ChainTab(), bool descent = true,
+                            V3<R> sh = V3<R>{(R)0, (R)0, (R)0}) {
     V3<R> inv = mk<R>((R)1 / d.x, (R)1 / d.y, (R)1 / d.z);
     prim = -1;
     best = tlimit;
@@ -278,7 +290,7 @@ LT_DEVINL void compat_query(unsigned amask, const CompatNode<R>* nodes, const Co
         if (meta != 0xffffu) {
             const int n_int = (int)(meta & 255u);
             const uint32_t allm = (1u << n_int) - 1u;
-            const uint32_t cm = chain_mask(chain.tab + oct * LT_CHAIN_PAIRS * 12, (int)chain.meta[8], of, invf) & allm;
+            const uint32_t cm = chain_mask(chain.tab + oct * LT_CHAIN_PAIRS * 12, (int)chain.meta[8], of, invf, mk<float>((float)sh.x, (float)sh.y, (float)sh.z)) & allm;
             const bool all = cm == allm;
             st.box_tests += all ? n_int + 1 : __ffs((int)~cm);
             done = !(cm & 1u);
@@ -290,7 +302,7 @@ LT_DEVINL void compat_query(unsigned amask, const CompatNode<R>* nodes, const Co
         if (descending) {
             const CompatNode<R>& nd = nodes[cur];
             st.box_tests++;
-            bool hit = slab(nd.bmin, nd.bmax, o, inv);
+            bool hit = slab(nd.bmin, nd.bmax, o, inv, sh);
             bool leaf = nd.n_prims > 0;
             if (leaf) lvis |= 1ull << nd.axis;
             if (!hit || leaf) {
@@ -306,19 +318,20 @@ LT_DEVINL void compat_query(unsigned amask, const CompatNode<R>* nodes, const Co
     uint64_t hm = 0;
     if (!done) {
         if (sizeof(R) == 4 && slabtab) {            // float32: paired, sign-selected table (see slab_pairs_mask)
-            hm = slab_pairs_mask(slabtab, n_leaves, mk<float>((float)o.x, (float)o.y, (float)o.z), mk<float>((float)inv.x, (float)inv.y, (float)inv.z));
+            hm = slab_pairs_mask(slabtab, n_leaves, mk<float>((float)o.x, (float)o.y, (float)o.z), mk<float>((float)inv.x, (float)inv.y, (float)inv.z),
+                                 mk<float>((float)sh.x, (float)sh.y, (float)sh.z));
         } else if (n_leaves <= 32) {                // 32-bit mask arithmetic
             uint32_t m = 0;
 #pragma unroll 4
             for (int li = 0; li < n_leaves; ++li) {
                 const CompatLeaf<R>& lf = leaves[li];
-                m |= (uint32_t)slab(lf.bmin, lf.bmax, o, inv) << li;
+                m |= (uint32_t)slab(lf.bmin, lf.bmax, o, inv, sh) << li;
             }
             hm = m;
         } else {
             for (int li = 0; li < n_leaves; ++li) {
                 const CompatLeaf<R>& lf = leaves[li];
-                hm |= (uint64_t)slab(lf.bmin, lf.bmax, o, inv) << li;
+                hm |= (uint64_t)slab(lf.bmin, lf.bmax, o, inv, sh) << li;
             }
         }
         st.box_tests += n_leaves;

@@ -278,10 +278,10 @@ walk_megakernel(const WalkParams<R> P) {
                 if (LT_POOLED) {
                     // the whole warp enters: lanes without a query of their own help with the pooled triangle tests
                     compat_query<R>(full, cnodes, cleaves, P.S.n_cleaves, slabtab, flatprim, tris, ln.o, ln.d, eps, ln.tlimit, ln.qtype == 2, ln.skip,
-                                    prim, t, st, active, ws, chain);
+                                    prim, t, st, active, ws, chain, true, ln.qshift);
                 } else if (active) {
                     compat_query<R>(am, cnodes, cleaves, P.S.n_cleaves, slabtab, flatprim, tris, ln.o, ln.d, eps, ln.tlimit, ln.qtype == 2, ln.skip, prim, t, st,
-                                    true, ws, chain);
+                                    true, ws, chain, true, ln.qshift);
                 }
             }
             if (active) {
@@ -332,7 +332,7 @@ walk_megakernel(const WalkParams<R> P) {
                         bmin[c] = TRAV == LT_TRAV_COMPAT ? cnodes[0].bmin[c] : (R)P.S.bbox_min[c];
                         bmax[c] = TRAV == LT_TRAV_COMPAT ? cnodes[0].bmax[c] : (R)P.S.bbox_max[c];
                     }
-                    if (!slab(bmin, bmax, ln.o, inv)) {
+                    if (!slab(bmin, bmax, ln.o, inv, TRAV == LT_TRAV_COMPAT ? ln.qshift : mk<R>((R)0, (R)0, (R)0))) {
                         if (TRAV == LT_TRAV_COMPAT) st.box_tests++;
                         it_early++;
                         ln.memo |= 1;

@@ -168,7 +168,8 @@ __global__ void __launch_bounds__(LT_BLOCK) record_kernel(const WalkParams<R> P,
             R t;
             const bool anyhit = ln.qtype == 2;
             if (TRAV == LT_TRAV_COMPAT)
-                compat_query<R>(am, P.S.cnodes, P.S.cleaves, P.S.n_cleaves, nullptr, nullptr, P.S.tris, ln.o, ln.d, eps, ln.tlimit, anyhit, ln.skip, prim, t, st);
+                compat_query<R>(am, P.S.cnodes, P.S.cleaves, P.S.n_cleaves, nullptr, nullptr, P.S.tris, ln.o, ln.d, eps, ln.tlimit, anyhit, ln.skip, prim, t, st, true,
+                                WarpScratch<R>(), ChainTab(), true, ln.qshift);
             else if (TRAV == LT_TRAV_NEAREST)
                 nearest_query<R>(P.S.tris, P.S.n_tris, ln.o, ln.d, eps, ln.tlimit, anyhit, ln.skip, prim, t, st);
             else

@@ -64,6 +64,7 @@ template <typename R>
 struct Lane {
     // query (the wavefront scheduler loads only this head for its trace stage)
     V3<R> o, d;
+    V3<R> qshift;                 // float32: slab-distance shift of the query ray = (reference's 1e-6 origin offset)_k / d_k, see slab()
     R tlimit;
     int32_t skip;                 // primitive the query ray starts on (float32 walk only), else -1
     int32_t qtype;                // 0 idle, 1 extension, 2 shadow
@@ -319,6 +320,7 @@ LT_DEVINL int shade_extension_with(const WalkParams<R>& P, Lane<R>& ln, int prim
         }
         ln.o = so;
         ln.d = sd;
+        if (sizeof(R) == 4) ln.qshift = mk<R>(eps * n.x / sd.x, eps * n.y / sd.y, eps * n.z / sd.z);      // origin x + EPSILON*n
         // light_samples.py:53: visible iff nearest t >= r - EPSILON.  The target point lies ON a lamp
         // triangle that is itself in the primitive list, so the nearest t is r up to rounding; float32
         // cannot resolve 1e-6 at r ~ 10 and needs a margin relative to r.
@@ -338,6 +340,7 @@ LT_DEVINL int shade_extension_with(const WalkParams<R>& P, Lane<R>& ln, int prim
         V3<R> r = reflect_dir<R>(ln.d, n);
         ln.o = mk<R>(p.x + eps * n.x, p.y + eps * n.y, p.z + eps * n.z);
         ln.d = r;
+        if (sizeof(R) == 4) ln.qshift = mk<R>(eps * n.x / r.x, eps * n.y / r.y, eps * n.z / r.z);
     } else if (m.transmission > (R)0) {                                 // :108-141 (Q5)
         R n1 = inside ? m.ior : (R)1, n2 = inside ? (R)1 : m.ior;
         R qq = (n1 - n2) / (n1 + n2), R0 = qq * qq;
@@ -355,10 +358,12 @@ LT_DEVINL int shade_extension_with(const WalkParams<R>& P, Lane<R>& ln, int prim
             V3<R> td = normalize(mk<R>(ln.d.x * Nr + n.x * k, ln.d.y * Nr + n.y * k, ln.d.z * Nr + n.z * k));
             ln.o = mk<R>(p.x + (-eps * n.x), p.y + (-eps * n.y), p.z + (-eps * n.z));
             ln.d = td;
+            if (sizeof(R) == 4) ln.qshift = mk<R>(-eps * n.x / td.x, -eps * n.y / td.y, -eps * n.z / td.z);
         } else {
             V3<R> r = reflect_dir<R>(ln.d, n);
             ln.o = mk<R>(p.x + eps * n.x, p.y + eps * n.y, p.z + eps * n.z);
             ln.d = r;
+            if (sizeof(R) == 4) ln.qshift = mk<R>(eps * n.x / r.x, eps * n.y / r.y, eps * n.z / r.z);
         }
     } else {
         ok = false;                                                     // "error" branch, :143-145
@@ -381,7 +386,9 @@ template <typename R, int SEM, int LF>
 LT_DEVINL int shade_shadow(const WalkParams<R>& P, Lane<R>& ln, Frame<R>* frames, int64_t gtid, bool occluded,
                            uint32_t& frame_overflow, uint32_t& max_frames, R& adv_rand0) {
     if (ln.pdf_zero & 2) occluded = true;                               // float32: the surface shadows its own back side (see shade_extension_with)
-    if (ln.pdf_zero & 1) { ln.o = ln.new_o; ln.d = ln.new_d; ln.skip = (ln.pdf_zero >> 2) - 1; }   // the untouched incoming ray
+    const R e_ = (R)P.eps;
+    ln.qshift = mk<R>(e_, e_, e_);                                      // the pending ray starts at x + EPSILON*dir (:82): every slab distance shifts by EPSILON
+    if (ln.pdf_zero & 1) { ln.o = ln.new_o; ln.d = ln.new_d; ln.skip = (ln.pdf_zero >> 2) - 1; }   // the untouched incoming ray (its own shift is not kept: ~1e-7 of the bounces)
     if (SEM == LT_SEM_ITERATIVE) {
         if (!occluded) ln.L = ln.L + ln.T * ln.contrib;                 // fix1:59
         if (ln.pdf_zero & 1) return ST_ADVANCE_ENDED;                   // fix1:64-67
@@ -431,6 +438,7 @@ LT_DEVINL void start_path(const WalkParams<R>& P, Lane<R>& ln, int64_t pix, int 
     ln.d = normalize(end - cam);
     ln.tlimit = Lim<R>::inf();
     ln.skip = -1;
+    ln.qshift = mk<R>((R)0, (R)0, (R)0);
     ln.memo = 0;
     ln.qtype = P.max_depth > 0 ? 1 : 0;
 }

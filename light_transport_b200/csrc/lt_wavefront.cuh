@@ -177,7 +177,8 @@ __global__ void __launch_bounds__(WfCfg<R>::NT, WfCfg<R>::MINB) walk_wavefront(c
             R t;
             const bool anyhit = ln.qtype == 2;
             if (TRAV == LT_TRAV_COMPAT)
-                compat_query<R>(am, cnodes, cleaves, P.S.n_cleaves, slabtab, flatprim, tris, ln.o, ln.d, eps, ln.tlimit, anyhit, ln.skip, prim, t, st);
+                compat_query<R>(am, cnodes, cleaves, P.S.n_cleaves, slabtab, flatprim, tris, ln.o, ln.d, eps, ln.tlimit, anyhit, ln.skip, prim, t, st, true,
+                                WarpScratch<R>(), ChainTab(), true, ln.qshift);
             else if (TRAV == LT_TRAV_NEAREST)
                 nearest_query<R>(tris, P.S.n_tris, ln.o, ln.d, eps, ln.tlimit, anyhit, ln.skip, prim, t, st);
             else

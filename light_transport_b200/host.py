@@ -402,6 +402,11 @@ def _pack_eps():
     return EPSILON
 
 
+def _lbvh_mode(traversal):
+    """what Renderer(build_lbvh=...) has to build for a traversal: nothing, the 8-wide hierarchy, or that plus the binary nodes"""
+    return "binary" if traversal == "lbvh2" else traversal == "lbvh"
+
+
 def _nodes_from_bvh(bvh, packed):
     if bvh is None:
         return compat_bvh.build_compat_nodes(packed.tri_v0, packed.tri_v1, packed.tri_v2)
@@ -414,7 +419,7 @@ def intersect(primitives, bvh, o, d, *, lights=(), traversal="compat", real="f64
     """Batch form of ``intersect_bvh(ray, primitives, linear_bvh)`` (R/src/bvh_new.py:413-482)."""
     packed = primitives if isinstance(primitives, _pack.PackedScene) else _pack.pack_scene(primitives, lights)
     r = Renderer(packed, _nodes_from_bvh(bvh, packed) if traversal == "compat" else None, device=device,
-                 build_lbvh=(traversal == "lbvh"))
+                 build_lbvh=_lbvh_mode(traversal))
     try:
         return r.intersect(o, d, traversal, real)
     finally:
@@ -423,7 +428,7 @@ def intersect(primitives, bvh, o, d, *, lights=(), traversal="compat", real="f64
 
 def render_scene(scene, primitives, bvh=None, *, spp=None, rng=None, seed=0, semantics="reference", traversal="compat",
                  light_idx=None, real=None, return_samples=False, world=None, device=None, return_info=False,
-                 scheduler="auto", all_ranks=False):
+                 scheduler="auto", all_ranks=False, film_blend=None):
     """Drop-in for ``render_scene(scene, primitives, bvh)``.
 
     ``scene``/``primitives``/``bvh`` are the reference's objects (or the ``api`` mirrors / a
@@ -438,6 +443,9 @@ def render_scene(scene, primitives, bvh=None, *, spp=None, rng=None, seed=0, sem
     ``[r*spp/R, (r+1)*spp/R)`` across ranks and sums the film with ONE reduce to rank 0 (NCCL on GPUs): rank 0
     finalizes, copies the image to the host and returns it, the other ranks return ``None`` for the image
     (``all_ranks=True``: all-reduce, every rank gets the image).
+    ``film_blend=b`` reproduces ``path_tracing_fix1.render_scene`` (R/src/path_tracing_fix1.py:165-166): instead of being
+    overwritten, ``scene.image`` ACCUMULATES ``b * clip(mean radiance, 0, 1)`` (the reference uses b = 0.25 and calls it
+    four times); the accumulated ``scene.image`` is returned.
     """
     H, W, D = int(scene.height), int(scene.width), int(scene.max_depth)
     n_spp = int(scene.number_of_samples) if spp is None else int(spp)
@@ -471,7 +479,7 @@ def render_scene(scene, primitives, bvh=None, *, spp=None, rng=None, seed=0, sem
         device = int(os.environ.get("LOCAL_RANK", "0")) if use_dist else 0
     s0, s1 = parallel.sample_range(rank, size, n_spp)
 
-    r = Renderer(packed, nodes, device=device, build_lbvh=(traversal == "lbvh"))
+    r = Renderer(packed, nodes, device=device, build_lbvh=_lbvh_mode(traversal))
     try:
         film = None
         if use_dist:
@@ -491,6 +499,10 @@ def render_scene(scene, primitives, bvh=None, *, spp=None, rng=None, seed=0, sem
                 image = film.cpu().numpy().reshape(H, W, 3)
     finally:
         r.close()
+    if image is not None and film_blend is not None:
+        if getattr(scene, "image", None) is None:
+            raise ValueError("film_blend accumulates into scene.image, which this scene does not have")
+        image = np.asarray(scene.image, dtype=np.float64) + float(film_blend) * image      # fix1:166
     if image is not None and getattr(scene, "image", None) is not None and (size == 1 or use_dist):
         try:
             scene.image[...] = image
@@ -519,7 +531,7 @@ def render_scene_full(scene, primitives, bvh=None, *, light_idx=None, traversal=
         raise ValueError("render_scene_full replays scene.rand_0/rand_1")
     packed = primitives if isinstance(primitives, _pack.PackedScene) else _pack.pack_scene(primitives, scene.lights)
     nodes = _nodes_from_bvh(bvh, packed) if traversal == "compat" else None
-    r = Renderer(packed, nodes, device=device, build_lbvh=(traversal == "lbvh"))
+    r = Renderer(packed, nodes, device=device, build_lbvh=_lbvh_mode(traversal))
     try:
         o = r.render_records(width=W, height=H, spp=S, max_depth=D, camera=scene.camera, f_distance=scene.f_distance,
                              rand0=np.asarray(scene.rand_0), rand1=np.asarray(scene.rand_1), light_idx=light_idx,

@@ -649,6 +649,63 @@ int lto_render(const lto_scene *S, const lto_params *P, const double *rand0, con
     return err;
 }
 
+/* Per-pixel statistics of a pixel SUBSET of a (possibly huge) film: mean[n][3] and m2[n][3] = sum of squares of the
+ * per-sample radiance over samples [s0, s1) of each listed pixel (row-major pixel indices of the W x H film).  Same
+ * ray generation and walk as lto_render (R/src/path_tracing.py:263-305), Philox streams only.  Lets the tests
+ * compare single pixels of config C2 (1024 x 1024 x 1024 spp) without a whole-film array. */
+int lto_render_pixels(const lto_scene *S, const lto_params *P, const int32_t *pixels, int32_t n_pixels, double *sum,
+                      double *sumsq, lto_counters *cnt) {
+    const int W = P->width, H = P->height, spp = P->spp;
+    const double aspect = (double)W / (double)H, top = 1 / aspect, bottom = -1 / aspect;
+    const double step_y = H > 1 ? (bottom - top) / (double)(H - 1) : 0;
+    const double step_x = W > 1 ? (1.0 - (-1.0)) / (double)(W - 1) : 0;
+    lto_counters total;
+    memset(&total, 0, sizeof total);
+    int err = 0;
+#ifdef _OPENMP
+    if (P->n_threads > 0) omp_set_num_threads(P->n_threads);
+#endif
+#pragma omp parallel
+    {
+        walk_t w;
+        memset(&w, 0, sizeof w);
+        w.S = S; w.P = P;
+#pragma omp for schedule(dynamic, 1)
+        for (int32_t k = 0; k < n_pixels; ++k) {
+            const int64_t pix = pixels[k];
+            int i = (int)(pix / W), j = (int)(pix % W);
+            double y = (H > 1 && i == H - 1) ? bottom : top + i * step_y;
+            double x = (W > 1 && j == W - 1) ? 1.0 : -1.0 + j * step_x;
+            double a[3] = {0, 0, 0}, b[3] = {0, 0, 0};
+            for (int s = P->s0; s < P->s1; ++s) {
+                w.path_id = (uint64_t)pix * (uint64_t)spp + (uint64_t)s;
+                w.r0 = 0; w.r1 = 0; w.lidx = 0;
+                w.nee_count = 0;
+                w.depth_frames = 0;
+                double u0, u1;
+                get_rand(&w, 0, &u0, &u1);
+                ray_t ray;
+                double end[3] = {x + u0 / W, y + u0 / H, P->f_distance};
+                for (int c = 0; c < 3; ++c) { ray.o[c] = P->camera[c]; ray.d[c] = end[c] - P->camera[c]; }
+                normalize3(ray.d);
+                double L[3];
+                if (P->semantics == 0) trace_path_reference(&w, &ray, 0, L);
+                else trace_path_iterative(&w, &ray, 0, L);
+                w.c.paths++;
+                for (int c = 0; c < 3; ++c) { a[c] += L[c]; b[c] += L[c] * L[c]; }
+            }
+            for (int c = 0; c < 3; ++c) { sum[3 * k + c] = a[c]; sumsq[3 * k + c] = b[c]; }
+        }
+#pragma omp critical
+        {
+            add_counters(&total, &w.c);
+            if (w.error) err = -1;
+        }
+    }
+    if (cnt) *cnt = total;
+    return err;
+}
+
 
 /* ================================================================================================
  * C4b — photon random walk in a homogeneous medium (sigma_t = 1): free flight, collision, absorption

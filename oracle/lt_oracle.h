@@ -59,6 +59,11 @@ int lto_intersect(const lto_scene *S, int traversal, const double *o, const doub
 int lto_render(const lto_scene *S, const lto_params *P, const double *rand0, const double *rand1,
                const int32_t *light_idx, double *film_sum, double *samples_out, lto_counters *c);
 
+/* per-pixel sum and sum of squares of the per-sample radiance for a SUBSET of pixels (row-major indices) of the W x H film,
+ * samples [s0,s1), Philox streams: single pixels of a film too large to hold (config C2) */
+int lto_render_pixels(const lto_scene *S, const lto_params *P, const int32_t *pixels, int32_t n_pixels, double *sum,
+                      double *sumsq, lto_counters *c);
+
 /* render_scene_samples' per-sample outputs for replayed random numbers:
  * samples [H][W][spp][3]; record_log_pdf (the array trace_path RETURNS), scene_record_log_pdf and
  * bounce_record (the arrays it writes into Scene) [H][W][spp][D]; direct/indirect lists of the root frame

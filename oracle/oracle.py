@@ -133,6 +133,28 @@ def render(scene: OracleScene, *, width, height, spp, max_depth, camera, f_dista
     return film, samples, cnt.as_dict()
 
 
+def render_pixels(scene: OracleScene, pixels, *, width, height, spp, max_depth, camera, f_distance, s0=0, s1=None, semantics="reference",
+                  traversal="compat", seed=0, rr_start=None, n_threads=0):
+    """(sum[n,3], sumsq[n,3], counters) of the per-sample radiance of the listed pixels (row-major indices) of a W x H film."""
+    p = LtoParams()
+    p.width, p.height, p.spp, p.s0, p.s1, p.max_depth = width, height, spp, s0, spp if s1 is None else s1, max_depth
+    p.semantics = 0 if semantics == "reference" else 1
+    p.traversal = 0 if traversal == "compat" else 1
+    p.rr_start = (3 if p.semantics == 0 else 5) if rr_start is None else rr_start
+    p.rr_floor, p.eps, p.f_distance, p.seed, p.n_threads = 0.05, 0.000001, float(f_distance), int(seed), n_threads
+    for k in range(3):
+        p.camera[k] = float(camera[k])
+    pixels = np.ascontiguousarray(pixels, dtype=np.int32)
+    a, b = np.zeros((len(pixels), 3)), np.zeros((len(pixels), 3))
+    cnt = LtoCounters()
+    L = lib()
+    L.lto_render_pixels.restype = C.c_int
+    rc = L.lto_render_pixels(C.byref(scene.c), C.byref(p), _p(pixels, PI32), C.c_int32(len(pixels)), _p(a, PD), _p(b, PD), C.byref(cnt))
+    if rc:
+        raise IndexError("setitem out of range (Q9b)")
+    return a, b, cnt.as_dict()
+
+
 def render_records(scene: OracleScene, *, width, height, spp, max_depth, camera, f_distance, rand0, rand1, light_idx=None,
                    traversal="compat", gradients=False, n_threads=0):
     """render_scene_samples' per-sample outputs (lto_render_records): dict with samples, record_log_pdf,

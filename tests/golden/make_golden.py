@@ -12,6 +12,7 @@ What is pinned (SURVEY.md §4, §8c — the reference has no tests or golden vec
   mirror_scene.npz    same for the C4a mirror box
   rays_*.npz          ray sets → (prim id, t) from the reference's intersect_bvh (COMPAT) and
                       from brute-force triangle_intersect (NEAREST semantics)
+  hg_table.npz        the reference's henyey_greenstein(cosTheta, g) on a grid (R/src/medium_samples.py:14-16)
   paths_*.npz         per-(pixel, sample) radiance from the reference's trace_path with
                       replayed rand_0/rand_1 and replayed light indices
                       (semantics REFERENCE = path_tracing.trace_path,
@@ -307,8 +308,21 @@ def golden_paths(name, objects, lin, lights, camera, fdist, W, H, spp, D, rand_s
                         image=np.clip(out.mean(axis=2), 0, 1))
 
 
+def golden_hg():
+    """hg_table.npz: the reference's own henyey_greenstein (R/src/medium_samples.py:14-16) on a (g, cos theta) grid"""
+    r_ms = importlib.import_module(P + "medium_samples")
+    g = np.array([-0.9, -0.5, -0.1, 0.0, 0.1, 0.3, 0.8, 0.95])
+    cos_theta = np.linspace(-1, 1, 41)
+    value = np.array([[r_ms.henyey_greenstein(c, gg) for c in cos_theta] for gg in g])
+    np.savez_compressed(os.path.join(OUT, "hg_table.npz"), g=g, cos_theta=cos_theta, value=value)
+    print("hg_table.npz:", value.shape)
+
+
 def main():
     only = sys.argv[1] if len(sys.argv) > 1 else None
+    if only == "hg":
+        golden_hg()
+        return
     if only == "records":
         objects, lights, camera, depth = scenes.lts_scene(ref_ns, new_list=numba.typed.List)
         lin = ref_bvh(objects)
@@ -353,6 +367,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "mirror_scene.npz"), **d)
     golden_rays("rays_mirror.npz", mobj, mlin, mpacked, mcam, mf, seed=12)
     golden_paths("paths_mirror_ref_d256.npz", mobj, mlin, mlights, mcam, mf, 32, 32, 2, 256, 4, 1, "reference")
+    golden_hg()
 
 
 if __name__ == "__main__":

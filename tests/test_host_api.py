@@ -54,6 +54,10 @@ def test_scene_mirror_semantics():
     assert np.array_equal(sc.rand_0, np.random.rand(4, 6, 2, 3))      # R/src/scene.py:68-69 order
     assert np.array_equal(sc.rand_1, np.random.rand(4, 6, 2, 3))
     assert sc.top == 1 / (6 / 4) and sc.bottom == -sc.top and sc.image.shape == (4, 6, 3)
+    # R/src/scene.py:70-73: logits of the random numbers and the two side-effect arrays trace_path writes
+    assert np.array_equal(sc.rand_0_logit, np.log(sc.rand_0 / (1 - sc.rand_0))) and sc.rand_1_logit.shape == sc.rand_1.shape
+    assert sc.bounce_record.dtype == np.int8 and sc.bounce_record.shape == (4, 6, 2, 3) and (sc.bounce_record == 1).all()
+    assert sc.record_log_pdf.dtype == np.float64 and (sc.record_log_pdf == 0).all()
     big = api.Scene(camera=np.array([0, 0, 8, 1.0]), lights=[], width=1024, height=1024, max_depth=16,
                     number_of_samples=1024, allocate=False)           # Q15: 704 GB otherwise
     assert big.rand_0 is None

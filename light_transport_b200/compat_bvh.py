@@ -56,6 +56,11 @@ def build_compat_nodes(v0, v1, v2) -> CompatNodes:
             return idx
         pmid = (cmin[dim] + cmax[dim]) / 2
         mid = start + int(np.count_nonzero(cen[start:end, dim] < pmid))
+        if mid == start or mid == end:
+            # (cmin + cmax) / 2 rounded onto cmin (adjacent floats): nothing lies left of the midpoint.  The reference's
+            # build_bvh would recurse into an empty range here and fail; keep the primitives together in one leaf instead.
+            rows[idx] = (bmin, bmax, start, -1, n, -1)
+            return idx
         rec(start, mid)
         last = rec(mid, end)
         rows[idx] = (bmin, bmax, -1, last, 0, dim)

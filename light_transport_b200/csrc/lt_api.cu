@@ -3,6 +3,7 @@
 #include <cstdio>
 #include <cstring>
 #include <vector>
+#include <mutex>
 #include <algorithm>
 #include <cmath>
 
@@ -24,18 +25,19 @@ void set_error(const char* fmt, ...) {
 // ---- pointer staging: caller data may live on the host or on the device -------------------------
 // ---- device memory (see lt_host.h) ---------------------------------------------------------------
 static cudaStream_t g_alloc_stream[64] = {};
+static std::once_flag g_alloc_once[64];
 static cudaStream_t alloc_stream() {
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64) return nullptr;
-    if (!g_alloc_stream[dev]) {
+    std::call_once(g_alloc_once[dev], [dev] {              // distinct handles may be used from distinct threads
         cudaStreamCreateWithFlags(&g_alloc_stream[dev], cudaStreamNonBlocking);
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
             unsigned long long keep = ~0ull;
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
         }
-    }
+    });
     return g_alloc_stream[dev];
 }
 cudaError_t lt_dev_malloc_impl(void** p, size_t bytes) {
@@ -162,7 +164,8 @@ static int upload_raw(T** dst, const T* src, size_t n, cudaStream_t st) {
 template <typename R>
 static int ensure_arrays(lt_scene* s) {
     SceneArrays<R>& a = s->arrays<R>();
-    if (a.tris) return LT_OK;
+    if (a.tris && a.complete) return LT_OK;
+    a.release();                                       // a half-built set from a failed earlier attempt is rebuilt from scratch
     cudaStream_t st = s->ctx->stream;
     const int n = s->n_tris;
     LT_CUDA_OK(lt_dev_malloc(&a.tris, (size_t)n * sizeof(TriRec<R>)));
@@ -216,6 +219,7 @@ static int ensure_arrays(lt_scene* s) {
         s->n_nleaves = n;
     }
     LT_CUDA_OK(cudaStreamSynchronize(st));
+    a.complete = true;
     return LT_OK;
 }
 
@@ -329,7 +333,9 @@ static int do_render(lt_scene* s, const lt_render_params* p, const double* rand0
     lt_ctx* ctx = s->ctx;
     cudaStream_t st = ctx->stream;
     const int W = p->width, H = p->height, D = p->max_depth;
-    const int64_t pix0 = p->pixel0, pix1 = (p->pixel1 > p->pixel0) ? p->pixel1 : (int64_t)W * H;
+    // only (0, 0) means "the whole film"; any other pixel1 <= pixel0 is an EMPTY share (a pixel-sharded caller with nothing to do)
+    const bool whole = p->pixel0 == 0 && p->pixel1 == 0;
+    const int64_t pix0 = p->pixel0, pix1 = whole ? (int64_t)W * H : std::max<int64_t>(p->pixel1, p->pixel0);
     const int ns = p->s1 - p->s0;
     const size_t npix_all = (size_t)W * H;
     InBuf<double> b0, b1;
@@ -589,13 +595,17 @@ int lt_init(int device, lt_ctx** out) {
     LT_CUDA_OK(cudaSetDevice(device));
     lt_ctx* c = new lt_ctx();
     c->device = device;
-    LT_CUDA_OK(cudaGetDeviceProperties(&c->prop, device));
-    LT_CUDA_OK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
-    c->stream = c->own_stream;
-    LT_CUDA_OK(lt_dev_malloc(&c->d_counters, sizeof(lt_counters)));
-    LT_CUDA_OK(lt_dev_malloc(&c->d_granule, sizeof(unsigned long long)));
-    LT_CUDA_OK(cudaEventCreate(&c->ev0));
-    LT_CUDA_OK(cudaEventCreate(&c->ev1));
+    const int rc = [c, device]() -> int {
+        LT_CUDA_OK(cudaGetDeviceProperties(&c->prop, device));
+        LT_CUDA_OK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+        c->stream = c->own_stream;
+        LT_CUDA_OK(lt_dev_malloc(&c->d_counters, sizeof(lt_counters)));
+        LT_CUDA_OK(lt_dev_malloc(&c->d_granule, sizeof(unsigned long long)));
+        LT_CUDA_OK(cudaEventCreate(&c->ev0));
+        LT_CUDA_OK(cudaEventCreate(&c->ev1));
+        return LT_OK;
+    }();
+    if (rc) { lt_destroy(c); return rc; }                  // a half-built context is released, not leaked
     *out = c;
     return LT_OK;
 }
@@ -605,6 +615,7 @@ void lt_destroy(lt_ctx* c) {
     cudaSetDevice(c->device);
     if (c->arena) lt_dev_free(c->arena);
     if (c->film) lt_dev_free(c->film);
+    if (c->pinned) cudaFreeHost(c->pinned);
     if (c->d_counters) lt_dev_free(c->d_counters);
     if (c->d_granule) lt_dev_free(c->d_granule);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -765,7 +776,10 @@ int lt_render(lt_scene* s, const lt_render_params* p, const double* rand0, const
     if (s->n_lights <= 0) { set_error("scene has no Light (next-event estimation needs one)"); return LT_E_INVALID; }
     if (p->semantics != LT_SEM_REFERENCE && p->semantics != LT_SEM_ITERATIVE) { set_error("unknown semantics"); return LT_E_INVALID; }
     if (p->scheduler != LT_SCHED_MEGAKERNEL && p->scheduler != LT_SCHED_WAVEFRONT) { set_error("unknown scheduler %d", p->scheduler); return LT_E_INVALID; }
-    if (p->pixel1 > p->width * p->height || p->pixel0 < 0) { set_error("bad pixel range"); return LT_E_INVALID; }
+    if (p->pixel1 > p->width * p->height || p->pixel0 < 0 || p->pixel1 < 0 || (p->pixel1 < p->pixel0 && p->pixel1 != 0)) {
+        set_error("bad pixel range [%d, %d) for a %d x %d film", p->pixel0, p->pixel1, p->width, p->height);
+        return LT_E_INVALID;
+    }
     LT_CUDA_OK(cudaSetDevice(s->ctx->device));
     int rc = check_traversal(s, p->traversal);
     if (rc) return rc;
@@ -797,8 +811,22 @@ int lt_render_image(lt_scene* s, const lt_render_params* p, const double* rand0,
     double* dst = dev_out ? image_out : ctx->film;
     finalize_div_kernel<<<std::max(grid, 1), 256, 0, ctx->stream>>>(ctx->film, (int64_t)n, (double)std::max(ns, 1), dst);
     LT_CUDA_OK(cudaGetLastError());
-    if (!dev_out) LT_CUDA_OK(cudaMemcpyAsync(image_out, ctx->film, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    LT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    if (!dev_out) {
+        // D2H through the context's pinned staging buffer (full-rate DMA), then one host copy into the caller's pageable array
+        const size_t bytes = n * sizeof(double);
+        if (bytes > ctx->pinned_bytes) {
+            if (ctx->pinned) cudaFreeHost(ctx->pinned);
+            ctx->pinned = nullptr; ctx->pinned_bytes = 0;
+            if (cudaHostAlloc(&ctx->pinned, bytes, cudaHostAllocDefault) == cudaSuccess) ctx->pinned_bytes = bytes;
+            else cudaGetLastError();                                    // no pinned memory to be had: copy straight into the caller's array
+        }
+        void* dst_h = ctx->pinned_bytes >= bytes ? ctx->pinned : (void*)image_out;
+        LT_CUDA_OK(cudaMemcpyAsync(dst_h, ctx->film, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        LT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+        if (dst_h != (void*)image_out) memcpy(image_out, dst_h, bytes);
+    } else {
+        LT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    }
     if (c) c->launches += 1;
     return LT_OK;
 }

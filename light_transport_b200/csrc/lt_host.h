@@ -16,6 +16,17 @@ cudaError_t lt_dev_free_impl(void* p);
 template <typename T> inline cudaError_t lt_dev_malloc(T** p, size_t bytes) { return lt_dev_malloc_impl(reinterpret_cast<void**>(p), bytes); }
 inline cudaError_t lt_dev_free(void* p) { return lt_dev_free_impl(p); }
 
+// RAII device buffer for the temporaries of an API call: every early (error) return releases it
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    cudaError_t alloc(size_t n) { return lt_dev_malloc(&p, (n ? n : 1) * sizeof(T)); }
+    ~DevBuf() { if (p) lt_dev_free(p); }
+};
+
 template <typename R>
 struct SceneArrays {
     TriRec<R>* tris = nullptr;
@@ -24,7 +35,9 @@ struct SceneArrays {
     CompatNode<R>* cnodes = nullptr;
     CompatLeaf<R>* cleaves = nullptr;   // leaves in descending node order
     CompatLeaf<R>* nleaves = nullptr;   // NEAREST on small scenes: one bounds record per triangle, in primitive order
+    bool complete = false;              // set by ensure_arrays once every upload has succeeded
     void release() {
+        complete = false;
         if (tris) lt_dev_free(tris);
         if (mats) lt_dev_free(mats);
         if (lights) lt_dev_free(lights);
@@ -55,6 +68,8 @@ struct lt_ctx {
     size_t arena_bytes = 0;
     double* film = nullptr;              // device film of lt_render_image
     size_t film_values = 0;
+    void* pinned = nullptr;              // pinned host staging for the image read-back of lt_render_image
+    size_t pinned_bytes = 0;
 };
 
 struct lt_scene {

@@ -214,13 +214,14 @@ extern "C" int lt_medium_walk(lt_ctx* ctx, const lt_medium_params* p, uint64_t n
     LT_CUDA_OK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const int D = p->max_depth, NB = p->n_rbins;
-    unsigned long long* d_hist = nullptr;
-    double *d_rbins = nullptr, *d_tot = nullptr;
-    unsigned long long* d_cnt = nullptr;
-    LT_CUDA_OK(lt_dev_malloc(&d_hist, sizeof(unsigned long long) * (D + 1)));
-    LT_CUDA_OK(lt_dev_malloc(&d_rbins, sizeof(double) * std::max(NB, 1)));
-    LT_CUDA_OK(lt_dev_malloc(&d_tot, sizeof(double) * 6));
-    LT_CUDA_OK(lt_dev_malloc(&d_cnt, sizeof(unsigned long long) * 3));
+    DevBuf<unsigned long long> b_hist, b_cnt;        // released on every return path
+    DevBuf<double> b_rbins, b_tot;
+    LT_CUDA_OK(b_hist.alloc(D + 1));
+    LT_CUDA_OK(b_rbins.alloc(std::max(NB, 1)));
+    LT_CUDA_OK(b_tot.alloc(6));
+    LT_CUDA_OK(b_cnt.alloc(3));
+    unsigned long long *d_hist = b_hist.p, *d_cnt = b_cnt.p;
+    double *d_rbins = b_rbins.p, *d_tot = b_tot.p;
     LT_CUDA_OK(cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * (D + 1), st));
     LT_CUDA_OK(cudaMemsetAsync(d_rbins, 0, sizeof(double) * std::max(NB, 1), st));
     LT_CUDA_OK(cudaMemsetAsync(d_tot, 0, sizeof(double) * 6, st));
@@ -261,7 +262,6 @@ extern "C" int lt_medium_walk(lt_ctx* ctx, const lt_medium_params* p, uint64_t n
     totals->rr_gained = h_tot[4]; totals->sum_mu = h_tot[5];
     totals->n_collisions = h_cnt[0]; totals->n_segments = h_cnt[1]; totals->n_scatters = h_cnt[2];
     if (kernel_ms) LT_CUDA_OK(cudaEventElapsedTime(kernel_ms, ctx->ev0, ctx->ev1));
-    lt_dev_free(d_hist); lt_dev_free(d_rbins); lt_dev_free(d_tot); lt_dev_free(d_cnt);
     return LT_OK;
 }
 

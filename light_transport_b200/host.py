@@ -487,7 +487,15 @@ def render_scene(scene, primitives, bvh=None, *, spp=None, rng=None, seed=0, sem
             torch.cuda.set_device(device)
             r.set_stream(torch.cuda.current_stream().cuda_stream)   # one stream: zero-fill → walk → reduce → finalize
             film = torch.zeros(H * W * 3, dtype=torch.float64, device=f"cuda:{device}")
-        image = None if use_dist else np.empty((H, W, 3), np.float64)
+        image = None
+        if not use_dist:
+            # like the reference, hand back scene.image itself when it can take the result (path_tracing_old.py:171 returns scene.image)
+            si = getattr(scene, "image", None)
+            if (size == 1 and film_blend is None and isinstance(si, np.ndarray) and si.dtype == np.float64 and si.shape == (H, W, 3)
+                    and si.flags.c_contiguous and si.flags.writeable):
+                image = si
+            else:
+                image = np.empty((H, W, 3), np.float64)
         film_out, samples, info = r.render(width=W, height=H, spp=n_spp, max_depth=D, camera=scene.camera,
                                            f_distance=scene.f_distance, s0=s0, s1=s1, semantics=semantics, traversal=traversal,
                                            real=real, rand0=rand0, rand1=rand1, light_idx=light_idx, seed=seed, film=film,
@@ -503,7 +511,7 @@ def render_scene(scene, primitives, bvh=None, *, spp=None, rng=None, seed=0, sem
         if getattr(scene, "image", None) is None:
             raise ValueError("film_blend accumulates into scene.image, which this scene does not have")
         image = np.asarray(scene.image, dtype=np.float64) + float(film_blend) * image      # fix1:166
-    if image is not None and getattr(scene, "image", None) is not None and (size == 1 or use_dist):
+    if image is not None and getattr(scene, "image", None) is not None and image is not getattr(scene, "image", None) and (size == 1 or use_dist):
         try:
             scene.image[...] = image
         except Exception:

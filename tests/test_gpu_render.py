@@ -433,3 +433,16 @@ def test_fix1_film_blend(oracle):
     assert np.allclose(out, 0.125 + 0.25 * plain, rtol=0, atol=1e-15) and np.array_equal(sc.image, out)
     out2 = lt.render_scene(sc, objs, None, semantics="iterative", film_blend=0.25)  # the notebook calls it repeatedly
     assert np.allclose(out2, 0.125 + 0.5 * plain, rtol=0, atol=1e-15)
+
+
+def test_empty_pixel_share_renders_nothing(R_lts):
+    """Only pixel_range (0, 0) means the whole film; an empty share (k, k) renders nothing, a reversed one is refused."""
+    from light_transport_b200 import host
+    ps, nodes, cam, f = load_scene("lts_scene.npz")
+    kw = dict(width=16, height=12, spp=2, max_depth=4, camera=cam, f_distance=f, seed=2, real="f64")
+    film, _, cnt = R_lts.render(pixel_range=(5, 5), **kw)
+    assert cnt["paths"] == 0 and not film.any()
+    film, _, cnt = R_lts.render(pixel_range=(0, 0), **kw)
+    assert cnt["paths"] == 16 * 12 * 2
+    with pytest.raises(host.LtError):
+        R_lts.render(pixel_range=(7, 3), **kw)

@@ -265,7 +265,7 @@ static int build_compat_arrays(lt_scene* s) {
 static size_t staged_bytes(const lt_scene* s, int trav, int real) {
     size_t r = real == LT_REAL_F64 ? 8 : 4;
     auto al = [](size_t x) { return (x + 15) / 16 * 16; };
-    size_t tri = r == 8 ? sizeof(TriRec<double>) : sizeof(TriRec<float>);
+    size_t tri = r == 8 ? sizeof(TriRec<double>) : sizeof(TriPad);          // float32 triangles are staged with the padded stride
     size_t mat = r == 8 ? sizeof(MatRec<double>) : sizeof(MatRec<float>);
     size_t nod = r == 8 ? sizeof(CompatNode<double>) : sizeof(CompatNode<float>);
     size_t lef = r == 8 ? sizeof(CompatLeaf<double>) : sizeof(CompatLeaf<float>);

@@ -268,9 +268,9 @@ LT_DEVINL double shfl_real(double v, int src) { return __shfl_sync(0xffffffffu, 
 // Bounds tests are pure functions of (leaf, ray): they are all evaluated first, converged, into a hit
 // mask; then every lane repeatedly takes its lowest hit-and-unvisited position.  Loops are
 // warp-uniform (`amask` = the lanes running this query together) so the lanes stay in lock step.
-template <typename R>
+template <typename R, typename TR = TriRec<R>>
 LT_DEVINL void compat_query(unsigned amask, const CompatNode<R>* nodes, const CompatLeaf<R>* leaves, int n_leaves, const float* slabtab,
-                            const uint8_t* flatprim, const TriRec<R>* tris, V3<R> o, V3<R> d, R eps, R tlimit, bool anyhit, int skip, int& prim, R& best,
+                            const uint8_t* flatprim, const TR* tris, V3<R> o, V3<R> d, R eps, R tlimit, bool anyhit, int skip, int& prim, R& best,
                             Stats& st, bool live = true, WarpScratch<R> ws = WarpScratch<R>(), ChainTab chain = ChainTab(), bool descent = true,
                             V3<R> sh = V3<R>{(R)0, (R)0, (R)0}) {
     V3<R> inv = mk<R>((R)1 / d.x, (R)1 / d.y, (R)1 / d.z);
@@ -455,8 +455,8 @@ LT_DEVINL void compat_query(unsigned amask, const CompatNode<R>* nodes, const Co
 }
 
 // ---- NEAREST (all primitives) ----------------------------------------------------------------------
-template <typename R>
-LT_DEVINL void nearest_query(const TriRec<R>* tris, int n_tris, V3<R> o, V3<R> d, R eps, R tlimit, bool anyhit, int skip,
+template <typename R, typename TR = TriRec<R>>
+LT_DEVINL void nearest_query(const TR* tris, int n_tris, V3<R> o, V3<R> d, R eps, R tlimit, bool anyhit, int skip,
                              int& prim, R& best, Stats& st) {
     prim = -1;
     best = tlimit;

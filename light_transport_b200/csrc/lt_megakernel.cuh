@@ -10,11 +10,23 @@
 // warp-aggregated across lanes holding the same pixel at granule end) only when the lane's pixel
 // changes.  Small scenes (COMPAT / NEAREST) are staged in shared memory once per CTA.
 #pragma once
+#include <type_traits>
+
 #include "lt_walk.cuh"
 
 namespace lt {
 
 #define LT_BLOCK 128
+
+// float32 triangle records re-laid with an 80-byte stride (TriPad, lt_scene.cuh)
+LT_DEVINL const TriPad* stage_tris_padded(char*& cursor, const TriRec<float>* src, int n) {
+    TriPad* dst = reinterpret_cast<TriPad*>(cursor);
+    const int4* s4 = reinterpret_cast<const int4*>(src);
+    int4* d4 = reinterpret_cast<int4*>(dst);
+    for (int i = threadIdx.x; i < 4 * n; i += blockDim.x) d4[5 * (i >> 2) + (i & 3)] = __ldg(s4 + i);
+    cursor += (size_t)n * sizeof(TriPad);
+    return dst;
+}
 
 template <typename T>
 LT_DEVINL const T* stage_array(char*& cursor, const T* src, int n) {
@@ -86,17 +98,20 @@ __global__ void __launch_bounds__(LT_BLOCK, sizeof(R) == 4 ? (TRAV == LT_TRAV_LB
                                                            : LT_MIN_BLOCKS_F64)
 walk_megakernel(const WalkParams<R> P) {
     extern __shared__ __align__(16) char smem[];
-    const TriRec<R>* tris = P.S.tris;
+    constexpr bool HIER = TRAV == LT_TRAV_LBVH || TRAV == LT_TRAV_LBVH2;      // a GPU-built hierarchy in global memory
+    constexpr bool PADDED = sizeof(R) == 4 && !HIER;                          // shared-memory triangles with the conflict-free stride
+    using TRS = typename std::conditional<PADDED, TriPad, TriRec<R>>::type;
+    const TRS* tris = reinterpret_cast<const TRS*>(P.S.tris);                 // (re-pointed at the staged copy below unless HIER)
     const MatRec<R>* mats = P.S.mats;
     const CompatNode<R>* cnodes = P.S.cnodes;
     const CompatLeaf<R>* cleaves = P.S.cleaves;
     const float* slabtab = nullptr;
     const uint8_t* flatprim = nullptr;
     ChainTab chain;
-    constexpr bool HIER = TRAV == LT_TRAV_LBVH || TRAV == LT_TRAV_LBVH2;      // a GPU-built hierarchy in global memory
     if (!HIER) {
         char* cur = smem;
-        tris = stage_array(cur, P.S.tris, P.S.n_tris);
+        if constexpr (PADDED) tris = stage_tris_padded(cur, reinterpret_cast<const TriRec<float>*>(P.S.tris), P.S.n_tris);
+        else tris = reinterpret_cast<const TRS*>(stage_array(cur, P.S.tris, P.S.n_tris));
         mats = stage_array(cur, P.S.mats, P.S.n_mats);
         if (TRAV == LT_TRAV_COMPAT) {
             cnodes = stage_array(cur, P.S.cnodes, P.S.n_cnodes);
@@ -277,10 +292,10 @@ walk_megakernel(const WalkParams<R> P) {
             if (TRAV == LT_TRAV_COMPAT) {
                 if (LT_POOLED) {
                     // the whole warp enters: lanes without a query of their own help with the pooled triangle tests
-                    compat_query<R>(full, cnodes, cleaves, P.S.n_cleaves, slabtab, flatprim, tris, ln.o, ln.d, eps, ln.tlimit, ln.qtype == 2, ln.skip,
+                    compat_query<R, TRS>(full, cnodes, cleaves, P.S.n_cleaves, slabtab, flatprim, tris, ln.o, ln.d, eps, ln.tlimit, ln.qtype == 2, ln.skip,
                                     prim, t, st, active, ws, chain, true, ln.qshift);
                 } else if (active) {
-                    compat_query<R>(am, cnodes, cleaves, P.S.n_cleaves, slabtab, flatprim, tris, ln.o, ln.d, eps, ln.tlimit, ln.qtype == 2, ln.skip, prim, t, st,
+                    compat_query<R, TRS>(am, cnodes, cleaves, P.S.n_cleaves, slabtab, flatprim, tris, ln.o, ln.d, eps, ln.tlimit, ln.qtype == 2, ln.skip, prim, t, st,
                                     true, ws, chain, true, ln.qshift);
                 }
             }
@@ -288,10 +303,10 @@ walk_megakernel(const WalkParams<R> P) {
                 const bool anyhit = ln.qtype == 2;
                 if (TRAV == LT_TRAV_NEAREST) {
                     if (flatprim)
-                        compat_query<R>(am, nullptr, cleaves, P.S.n_nleaves, slabtab, flatprim, tris, ln.o, ln.d, eps, ln.tlimit, anyhit, ln.skip, prim, t, st,
+                        compat_query<R, TRS>(am, nullptr, cleaves, P.S.n_nleaves, slabtab, flatprim, tris, ln.o, ln.d, eps, ln.tlimit, anyhit, ln.skip, prim, t, st,
                                         true, WarpScratch<R>(), ChainTab(), false);
                     else
-                        nearest_query<R>(tris, P.S.n_tris, ln.o, ln.d, eps, ln.tlimit, anyhit, ln.skip, prim, t, st);
+                        nearest_query<R, TRS>(tris, P.S.n_tris, ln.o, ln.d, eps, ln.tlimit, anyhit, ln.skip, prim, t, st);
                 }
                 (void)anyhit;
                 int stt;
@@ -309,7 +324,7 @@ walk_megakernel(const WalkParams<R> P) {
                             hit_rec.mat = ml & 0x7fffffff; hit_rec.is_light = (ml >> 31) & 1; hit_rec.valid = true;
                         }
                     }
-                    stt = shade_extension<R, SEM>(P, ln, prim, t, tris, mats, it_lidx, adv_rand0, hit_rec);
+                    stt = shade_extension<R, SEM, TRS>(P, ln, prim, t, tris, mats, it_lidx, adv_rand0, hit_rec);
                 } else {
                     stt = shade_shadow<R, SEM, LT_LOCAL_FRAMES>(P, ln, frames, gtid, prim >= 0, it_fovf, it_maxf, adv_rand0);
                 }

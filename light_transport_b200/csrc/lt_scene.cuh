@@ -22,6 +22,15 @@ struct alignas(16) TriRec {
     int32_t is_light;
     int32_t pad[2];
 };
+// Shared-memory copy of a float32 triangle record, padded to 80 bytes: with 64-byte records lanes that test DIFFERENT triangles
+// collide on 128-bit loads (record stride 16 words: the 16-byte chunk a lane reads falls in bank group (4k + c) mod 8, two
+// groups for a whole quarter-warp; ncu round 1: 23 % of the shared wavefronts were conflict replays).  Stride 20 words puts
+// triangle k's chunk c in group (5k + c) mod 8 - eight distinct groups for k mod 8 distinct.
+struct alignas(16) TriPad : TriRec<float> {
+    float pad80[4];
+};
+static_assert(sizeof(TriPad) == 80, "TriPad must be 80 bytes");
+
 template <typename R>
 struct alignas(16) MatRec {
     R kd[3], emission, ior, transmission;

@@ -264,8 +264,8 @@ LT_DEVINL bool advance(const WalkParams<R>& P, Lane<R>& ln, const Frame<R>* fram
 enum { ST_QUERY = 0, ST_ADVANCE = 1, ST_ADVANCE_ENDED = 2 };
 
 // Shading after an EXTENSION query, given the bounce's two random numbers.
-template <typename R, int SEM>
-LT_DEVINL int shade_extension_with(const WalkParams<R>& P, Lane<R>& ln, int prim, R t, const TriRec<R>* tris, const MatRec<R>* mats,
+template <typename R, int SEM, typename TR = TriRec<R>>
+LT_DEVINL int shade_extension_with(const WalkParams<R>& P, Lane<R>& ln, int prim, R t, const TR* tris, const MatRec<R>* mats,
                                    uint32_t& lidx_overflow, R& adv_rand0, R rand_0, R rand_1, HitRec<R> hit_rec = HitRec<R>()) {
     const R eps = (R)P.eps;
     const R inv_pi = (R)(1 / 3.141592653589793);
@@ -373,12 +373,12 @@ LT_DEVINL int shade_extension_with(const WalkParams<R>& P, Lane<R>& ln, int prim
 }
 
 // Shading after an EXTENSION query; draws rand(path, bounce) only when something was hit.
-template <typename R, int SEM>
-LT_DEVINL int shade_extension(const WalkParams<R>& P, Lane<R>& ln, int prim, R t, const TriRec<R>* tris, const MatRec<R>* mats,
+template <typename R, int SEM, typename TR = TriRec<R>>
+LT_DEVINL int shade_extension(const WalkParams<R>& P, Lane<R>& ln, int prim, R t, const TR* tris, const MatRec<R>* mats,
                               uint32_t& lidx_overflow, R& adv_rand0, HitRec<R> hit_rec = HitRec<R>()) {
     R rand_0 = (R)0, rand_1 = (R)0;
     if (prim >= 0) get_rand<R>(P, path_id_of(P, ln), ln.bounce, rand_0, rand_1);
-    return shade_extension_with<R, SEM>(P, ln, prim, t, tris, mats, lidx_overflow, adv_rand0, rand_0, rand_1, hit_rec);
+    return shade_extension_with<R, SEM, TR>(P, ln, prim, t, tris, mats, lidx_overflow, adv_rand0, rand_0, rand_1, hit_rec);
 }
 
 // After the SHADOW query.  occluded = a hit was found in (eps, r - eps).

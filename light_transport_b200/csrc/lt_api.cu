@@ -316,12 +316,18 @@ static int do_intersect(lt_scene* s, int traversal, const double* o, const doubl
     P.traversal = traversal;
     int grid = (int)std::min<int64_t>((n + LT_BLOCK - 1) / LT_BLOCK, (int64_t)ctx->prop.multiProcessorCount * 16);
     if (grid < 1) grid = 1;
+    LT_CUDA_OK(cudaEventRecord(ctx->ev0, st));
     if (n > 0 && (rc = launch_intersect<R>(P, grid, st))) return rc;
+    LT_CUDA_OK(cudaEventRecord(ctx->ev1, st));
     if ((rc = bp.finish(st)) || (rc = bt.finish(st))) return rc;
     LT_CUDA_OK(cudaStreamSynchronize(st));
     if (c) {
         LT_CUDA_OK(cudaMemcpy(c, ctx->d_counters, sizeof(lt_counters), cudaMemcpyDeviceToHost));
         c->rays_ext = (uint64_t)n;
+        float ms = 0;
+        LT_CUDA_OK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        c->kernel_ns = (uint64_t)(ms * 1e6);
+        c->launches = 1;
     }
     return LT_OK;
 }

@@ -87,7 +87,7 @@ struct lt_scene {
     lt::WNode* wnodes = nullptr;               // 8-wide compressed hierarchy
     lt::WTri* wtris = nullptr;                 // float32 triangle records, leaf order
     int32_t* wleaf_prims = nullptr;            // leaf order -> primitive
-    int n_wnodes = 0, wbvh_depth = 0;
+    int n_wnodes = 0, wbvh_depth = 0, lbvh2_depth = 0;
     // raw float64 scene arrays on the device (uploaded once): input of the record builders and of the LBVH build
     double *d_v0 = nullptr, *d_v1 = nullptr, *d_v2 = nullptr, *d_n = nullptr;
     int32_t* d_mat = nullptr;

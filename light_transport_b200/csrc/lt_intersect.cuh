@@ -525,7 +525,8 @@ LT_DEVINL void slab_t2(float4 X, float4 Y, float4 Z, V3<double> o, V3<double> in
 // others keep their state and get their turn when they become the majority (a leaf is never lost, a
 // minority only grows).  The classic per-lane while-while loop ran with 5.5 of 32 lanes active on the
 // 1 M-triangle scene (ncu, round 1) because lanes drifted between the two phases.
-// Near child first, far child on the stack (local memory, LT_LBVH_STACK deep, checked at build time).
+// Near child first, far child on the stack (entry k of a lane at stack[k * stride]: shared memory [level][thread] in the walk,
+// thread-local in the whole-query form; as deep as the tree, checked at build time).
 // Traversal state of one lane; the stack lives in the caller's local memory so that a traversal can be
 // suspended and resumed (the megakernel runs it in bounded chunks, see lt_megakernel.cuh).
 template <typename R>
@@ -545,7 +546,7 @@ LT_DEVINL void lbvh2_begin(LbvhState<R>& s, int n_tris, R tlimit, bool live) {
 // Runs at most `max_steps` warp-voted steps (every lane of `amask` must call it, finished or idle lanes
 // with cur == LT_LBVH_DONE).  Returns when all lanes are done or the budget is used up.
 template <typename R>
-LT_DEVINL void lbvh2_run(unsigned amask, LbvhState<R>& s, int* stack, const LbvhNode* __restrict__ nodes,
+LT_DEVINL void lbvh2_run(unsigned amask, LbvhState<R>& s, int* stack, int stride, const LbvhNode* __restrict__ nodes,
                         const TriRec<R>* __restrict__ tris, V3<R> o, V3<R> d, V3<R> inv, R eps, bool anyhit, int skip, Stats& st,
                         int max_steps) {
     // (dropping stale stack entries at pop time — entry distance kept beside the node — was measured:
@@ -567,9 +568,10 @@ LT_DEVINL void lbvh2_run(unsigned amask, LbvhState<R>& s, int* stack, const Lbvh
                 slab_t2(X, Y, Z, o, inv, s.best, t0n, t1n, h0, h1);
                 bool swap = t1n < t0n;
                 int nearc = swap ? r.y : r.x, farc = swap ? r.x : r.y;
-                if (h0 & h1) { stack[s.sp++] = farc; s.cur = nearc; }
+                if (h0 & h1) { stack[s.sp * stride] = farc; s.sp++; s.cur = nearc; }
                 else if (h0 | h1) s.cur = h0 ? r.x : r.y;
-                else s.cur = s.sp > 0 ? stack[--s.sp] : LT_LBVH_DONE;
+                else if (s.sp > 0) { s.sp--; s.cur = stack[s.sp * stride]; }
+                else s.cur = LT_LBVH_DONE;
             }
         } else if (at_leaf) {
             int k = ~s.cur;
@@ -580,7 +582,8 @@ LT_DEVINL void lbvh2_run(unsigned amask, LbvhState<R>& s, int* stack, const Lbvh
                 s.best = t;
                 s.prim = k;
             }
-            s.cur = (s.sp > 0 && !(anyhit && s.prim >= 0)) ? stack[--s.sp] : LT_LBVH_DONE;
+            if (s.sp > 0 && !(anyhit && s.prim >= 0)) { s.sp--; s.cur = stack[s.sp * stride]; }
+            else s.cur = LT_LBVH_DONE;
         }
     }
 }
@@ -592,7 +595,7 @@ LT_DEVINL void lbvh2_query(unsigned amask, const LbvhNode* __restrict__ nodes, c
     LbvhState<R> s;
     lbvh2_begin<R>(s, n_tris, tlimit, true);
     V3<R> inv = mk<R>((R)1 / d.x, (R)1 / d.y, (R)1 / d.z);
-    lbvh2_run<R>(amask, s, stack, nodes, tris, o, d, inv, eps, anyhit, skip, st, 0x7fffffff);
+    lbvh2_run<R>(amask, s, stack, 1, nodes, tris, o, d, inv, eps, anyhit, skip, st, 0x7fffffff);
     prim = s.prim;
     best = s.best;
 }

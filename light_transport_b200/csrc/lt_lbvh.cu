@@ -540,7 +540,7 @@ static void free_hierarchy(lt_scene* s) {
     if (s->wtris) lt_dev_free(s->wtris);
     if (s->wleaf_prims) lt_dev_free(s->wleaf_prims);
     s->lbvh_nodes = nullptr; s->wnodes = nullptr; s->wtris = nullptr; s->wleaf_prims = nullptr;
-    s->n_lbvh_nodes = 0; s->n_wnodes = 0; s->wbvh_depth = 0;
+    s->n_lbvh_nodes = 0; s->n_wnodes = 0; s->wbvh_depth = 0; s->lbvh2_depth = 0;
 }
 
 extern "C" int lt_bvh_build(lt_scene* s, int flags, lt_bvh_stats* out) {
@@ -652,6 +652,7 @@ extern "C" int lt_bvh_build(lt_scene* s, int flags, lt_bvh_stats* out) {
     LT_CUDA_OK(cudaMemcpy(&cost, sah.p, sizeof(double), cudaMemcpyDeviceToHost));
     s->n_wnodes = n_wide;
     s->wbvh_depth = levels;
+    s->lbvh2_depth = depth;
     stats.n_nodes = n_wide;
     stats.max_depth = levels;
     stats.binary_depth = depth;

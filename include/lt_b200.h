@@ -95,7 +95,8 @@ typedef struct {
     int32_t paths_per_warp;      /* megakernel work granule; 0 = auto */
     int32_t flags;               /* bits 8-15: LBVH traversal steps per megakernel iteration (0 = default 24);
                                     bit 16 / bit 17: force phase-aligned iterations off / on (default: from the scene);
-                                    bits 20-23: resident CTAs per SM of the LBVH walk (0 = default); rest reserved */
+                                    bit 19: persisting-L2 window on the hierarchy nodes (A/B: measured slower); bits 20-23: cap on resident CTAs per SM
+                                    (0 = what the kernel was built for); rest reserved */
 } lt_render_params;
 
 typedef struct {
@@ -118,6 +119,7 @@ typedef struct {
     float collapse_ms;           /* of build_ms: collapse + quantise + triangle records */
     float reserved;
     int64_t bytes;               /* nodes (80 B) + float32 triangle records (48 B): what a float32 traversal touches */
+    int64_t binary_bytes;        /* LT_BVH_KEEP_BINARY: binary nodes (64 B) + the same triangle records; else 0 */
 } lt_bvh_stats;
 /* lt_bvh_build flags */
 /* bits 8-9: triangles per leaf slot of the wide hierarchy, 1..3 (0 = default 3) */

@@ -429,14 +429,42 @@ static int do_render(lt_scene* s, const lt_render_params* p, const double* rand0
         P.arena = reinterpret_cast<R*>(ctx->arena);
     }
     if (wavefront) LT_CUDA_OK(cudaMemsetAsync(ctx->d_granule, 0, sizeof(unsigned long long), st));
+    // Hierarchy walks, opt-in (flags bit 19): pin the node array in the L2 with a persisting access-policy window on the stream.
+    // Measured on C3 (1 M triangles: 64 MB of binary nodes + 48 MB of triangle records against a 126 MB L2): 2.87 Grays/s with the
+    // window, 3.03 without — what the window keeps, the triangle records lose; the 8-wide hierarchy (11 MB of nodes) does not care.
+    bool l2_window = false;
+    if ((p->traversal == LT_TRAV_LBVH || p->traversal == LT_TRAV_LBVH2) && (p->flags & (1 << 19)) && ctx->prop.persistingL2CacheMaxSize > 0) {
+        const void* base = p->traversal == LT_TRAV_LBVH ? (const void*)s->wnodes : (const void*)s->lbvh_nodes;
+        const size_t bytes = p->traversal == LT_TRAV_LBVH ? (size_t)s->n_wnodes * sizeof(WNode) : (size_t)s->n_lbvh_nodes * sizeof(LbvhNode);
+        if (base && bytes > 0) {
+            const size_t carve = (size_t)ctx->prop.persistingL2CacheMaxSize;
+            if (!ctx->l2_limit_set) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve); ctx->l2_limit_set = true; }
+            cudaStreamAttrValue av;
+            memset(&av, 0, sizeof av);
+            av.accessPolicyWindow.base_ptr = const_cast<void*>(base);
+            av.accessPolicyWindow.num_bytes = std::min(bytes, (size_t)ctx->prop.accessPolicyMaxWindowSize);
+            av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)av.accessPolicyWindow.num_bytes);
+            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            l2_window = cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av) == cudaSuccess;
+            if (!l2_window) cudaGetLastError();
+        }
+    }
     LT_CUDA_OK(cudaEventRecord(ctx->ev0, st));
     if (P.total_paths > 0) {
         rc = wavefront ? launch_wavefront<R>(P, ctx->d_granule, grid, smem, st) : launch_walk<R>(P, grid, smem, st);
         if (rc) return rc;
     }
     LT_CUDA_OK(cudaEventRecord(ctx->ev1, st));
+    if (l2_window) {
+        cudaStreamAttrValue av;
+        memset(&av, 0, sizeof av);
+        av.accessPolicyWindow.num_bytes = 0;                     // window off; persisting lines return to normal
+        cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
+    }
     if ((rc = bf.finish(st)) || (rc = bs.finish(st))) return rc;
     LT_CUDA_OK(cudaStreamSynchronize(st));
+    if (l2_window) cudaCtxResetPersistingL2Cache();
     lt_counters hc;
     LT_CUDA_OK(cudaMemcpy(&hc, ctx->d_counters, sizeof hc, cudaMemcpyDeviceToHost));
     float ms = 0;

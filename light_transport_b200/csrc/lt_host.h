@@ -68,6 +68,7 @@ struct lt_ctx {
     size_t arena_bytes = 0;
     double* film = nullptr;              // device film of lt_render_image
     size_t film_values = 0;
+    bool l2_limit_set = false;           // cudaLimitPersistingL2CacheSize raised once
     void* pinned = nullptr;              // pinned host staging for the image read-back of lt_render_image
     size_t pinned_bytes = 0;
 };

@@ -531,74 +531,9 @@ LT_DEVINL void slab_t2(float4 X, float4 Y, float4 Z, V3<double> o, V3<double> in
 // suspended and resumed (the megakernel runs it in bounded chunks, see lt_megakernel.cuh).
 template <typename R>
 struct LbvhState {
-    int cur, sp, prim;       // interior node index >= 0, leaf ~prim < 0, LT_LBVH_DONE; stack pointer; best primitive
+    int cur, sp, prim, leaf; // interior node index >= 0, leaf ~position < 0, LT_LBVH_DONE; stack pointer; best primitive and its leaf-order position
     R best;
 };
-
-template <typename R>
-LT_DEVINL void lbvh2_begin(LbvhState<R>& s, int n_tris, R tlimit, bool live) {
-    s.prim = -1;
-    s.best = tlimit;
-    s.sp = 0;
-    s.cur = live ? (n_tris > 1 ? 0 : ~0) : LT_LBVH_DONE;
-}
-
-// Runs at most `max_steps` warp-voted steps (every lane of `amask` must call it, finished or idle lanes
-// with cur == LT_LBVH_DONE).  Returns when all lanes are done or the budget is used up.
-template <typename R>
-LT_DEVINL void lbvh2_run(unsigned amask, LbvhState<R>& s, int* stack, int stride, const LbvhNode* __restrict__ nodes,
-                        const TriRec<R>* __restrict__ tris, V3<R> o, V3<R> d, V3<R> inv, R eps, bool anyhit, int skip, Stats& st,
-                        int max_steps) {
-    // (dropping stale stack entries at pop time — entry distance kept beside the node — was measured:
-    //  fewer node visits but 6-9 % slower overall on both the 28- and the 1 M-triangle scene.
-    //  prefetch.global.L1 of the children while the slab tests run: both children 3x slower, the chosen
-    //  child 1.4x slower, the pushed far child -1.5 %: the loads are latency-bound but L1 requests are not free.)
-    for (int step = 0; step < max_steps; ++step) {
-        const bool at_node = s.cur >= 0, at_leaf = (s.cur < 0) & (s.cur != LT_LBVH_DONE);
-        const unsigned nm = __ballot_sync(amask, at_node), lm = __ballot_sync(amask, at_leaf);
-        if (!(nm | lm)) break;
-        if (__popc(nm) >= __popc(lm)) {
-            if (at_node) {
-                const float4* p = reinterpret_cast<const float4*>(nodes + s.cur);
-                const float4 X = __ldg(p), Y = __ldg(p + 1), Z = __ldg(p + 2);
-                const int4 r = __ldg(reinterpret_cast<const int4*>(p + 3));
-                R t0n, t1n;
-                st.box_tests += 2;
-                bool h0, h1;
-                slab_t2(X, Y, Z, o, inv, s.best, t0n, t1n, h0, h1);
-                bool swap = t1n < t0n;
-                int nearc = swap ? r.y : r.x, farc = swap ? r.x : r.y;
-                if (h0 & h1) { stack[s.sp * stride] = farc; s.sp++; s.cur = nearc; }
-                else if (h0 | h1) s.cur = h0 ? r.x : r.y;
-                else if (s.sp > 0) { s.sp--; s.cur = stack[s.sp * stride]; }
-                else s.cur = LT_LBVH_DONE;
-            }
-        } else if (at_leaf) {
-            int k = ~s.cur;
-            R t;
-            st.tri_tests++;
-            bool h = tri_intersect(tris[k], o, d, t);
-            if (h & (k != skip) & (eps < t) & ((t < s.best) | ((t == s.best) & (k < s.prim)))) {
-                s.best = t;
-                s.prim = k;
-            }
-            if (s.sp > 0 && !(anyhit && s.prim >= 0)) { s.sp--; s.cur = stack[s.sp * stride]; }
-            else s.cur = LT_LBVH_DONE;
-        }
-    }
-}
-
-template <typename R>
-LT_DEVINL void lbvh2_query(unsigned amask, const LbvhNode* __restrict__ nodes, const TriRec<R>* __restrict__ tris, int n_tris,
-                          V3<R> o, V3<R> d, R eps, R tlimit, bool anyhit, int skip, int& prim, R& best, Stats& st) {
-    int stack[LT_LBVH_STACK];
-    LbvhState<R> s;
-    lbvh2_begin<R>(s, n_tris, tlimit, true);
-    V3<R> inv = mk<R>((R)1 / d.x, (R)1 / d.y, (R)1 / d.z);
-    lbvh2_run<R>(amask, s, stack, 1, nodes, tris, o, d, inv, eps, anyhit, skip, st, 0x7fffffff);
-    prim = s.prim;
-    best = s.best;
-}
 
 // ---- 8-wide compressed hierarchy (WNode / WTri, lt_scene.cuh) -------------------------------------------------------
 // Same query semantics as the binary LBVH above (true closest hit, eps < t < tlimit, ties -> lowest primitive index), on
@@ -836,13 +771,82 @@ LT_DEVINL void wbvh_query(unsigned amask, uint2* stack, int stride, const WNode*
     leaf = s.leaf;
 }
 
+template <typename R>
+LT_DEVINL void lbvh2_begin(LbvhState<R>& s, int n_tris, R tlimit, bool live) {
+    s.prim = -1;
+    s.leaf = -1;
+    s.best = tlimit;
+    s.sp = 0;
+    s.cur = live ? (n_tris > 1 ? 0 : ~0) : LT_LBVH_DONE;
+}
+
+// Runs at most `max_steps` warp-voted steps (every lane of `amask` must call it, finished or idle lanes
+// with cur == LT_LBVH_DONE).  Returns when all lanes are done or the budget is used up.
+template <typename R>
+LT_DEVINL void lbvh2_run(unsigned amask, LbvhState<R>& s, int* stack, int stride, const LbvhNode* __restrict__ nodes,
+                         const WTri* __restrict__ wtris, const int32_t* __restrict__ leaf_prims, const TriRec<R>* __restrict__ tris, V3<R> o, V3<R> d,
+                         V3<R> inv, R eps, bool anyhit, int skip, Stats& st, int max_steps) {
+    // (dropping stale stack entries at pop time — entry distance kept beside the node — was measured:
+    //  fewer node visits but 6-9 % slower overall on both the 28- and the 1 M-triangle scene.
+    //  prefetch.global.L1 of the children while the slab tests run: both children 3x slower, the chosen
+    //  child 1.4x slower, the pushed far child -1.5 %: the loads are latency-bound but L1 requests are not free.)
+    for (int step = 0; step < max_steps; ++step) {
+        const bool at_node = s.cur >= 0, at_leaf = (s.cur < 0) & (s.cur != LT_LBVH_DONE);
+        const unsigned nm = __ballot_sync(amask, at_node), lm = __ballot_sync(amask, at_leaf);
+        if (!(nm | lm)) break;
+        if (__popc(nm) >= __popc(lm)) {
+            if (at_node) {
+                const float4* p = reinterpret_cast<const float4*>(nodes + s.cur);
+                const float4 X = __ldg(p), Y = __ldg(p + 1), Z = __ldg(p + 2);
+                const int4 r = __ldg(reinterpret_cast<const int4*>(p + 3));
+                R t0n, t1n;
+                bool h0, h1;
+                st.box_tests += 2;
+                slab_t2(X, Y, Z, o, inv, s.best, t0n, t1n, h0, h1);
+                const int r0 = r.x, r1 = r.y;
+                bool swap = t1n < t0n;
+                int nearc = swap ? r1 : r0, farc = swap ? r0 : r1;
+                if (h0 & h1) { stack[s.sp * stride] = farc; s.sp++; s.cur = nearc; }
+                else if (h0 | h1) s.cur = h0 ? r0 : r1;
+                else if (s.sp > 0) { s.sp--; s.cur = stack[s.sp * stride]; }
+                else s.cur = LT_LBVH_DONE;
+            }
+        } else if (at_leaf) {
+            const uint32_t ti = (uint32_t)~s.cur;          // position in the leaf-ordered triangle arrays
+            R t;
+            int k;
+            st.tri_tests++;
+            const bool h = wtri_test(wtris, leaf_prims, tris, ti, o, d, t, k);
+            if (h & (k != skip) & (eps < t) & ((t < s.best) | ((t == s.best) & (k < s.prim)))) {
+                s.best = t;
+                s.prim = k;
+                s.leaf = (int)ti;
+            }
+            if (s.sp > 0 && !(anyhit && s.prim >= 0)) { s.sp--; s.cur = stack[s.sp * stride]; }
+            else s.cur = LT_LBVH_DONE;
+        }
+    }
+}
+
+template <typename R>
+LT_DEVINL void lbvh2_query(unsigned amask, const SceneView<R>& S, const TriRec<R>* __restrict__ tris, V3<R> o, V3<R> d, R eps, R tlimit, bool anyhit,
+                           int skip, int& prim, R& best, Stats& st) {
+    int stack[LT_LBVH_STACK];
+    LbvhState<R> s;
+    lbvh2_begin<R>(s, S.n_tris, tlimit, true);
+    V3<R> inv = mk<R>((R)1 / d.x, (R)1 / d.y, (R)1 / d.z);
+    lbvh2_run<R>(amask, s, stack, 1, S.lbvh, S.wtris, S.wleaf_prims, tris, o, d, inv, eps, anyhit, skip, st, 0x7fffffff);
+    prim = s.prim;
+    best = s.best;
+}
+
 // whole-query form with a thread-local stack (record / wavefront / explicit-ray kernels); `binary` picks the Karras tree
 // (kept by lt_bvh_build(..., LT_BVH_KEEP_BINARY, ...)) instead of the 8-wide hierarchy
 template <typename R>
 LT_DEVINL void lbvh_query(unsigned amask, const SceneView<R>& S, const TriRec<R>* __restrict__ tris, V3<R> o, V3<R> d, R eps, R tlimit, bool anyhit,
                           int skip, int& prim, R& best, Stats& st, bool binary = false) {
     if (binary) {
-        lbvh2_query<R>(amask, S.lbvh, tris, S.n_tris, o, d, eps, tlimit, anyhit, skip, prim, best, st);
+        lbvh2_query<R>(amask, S, tris, o, d, eps, tlimit, anyhit, skip, prim, best, st);
     } else {
         uint2 stack[LT_WBVH_MAX_DEPTH];
         int leaf;

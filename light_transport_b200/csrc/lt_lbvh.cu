@@ -280,9 +280,11 @@ __global__ void depth_kernel(int n, const int* __restrict__ parent_internal, con
     if ((threadIdx.x & 31) == 0) atomicMax(max_depth, d);
 }
 
-// ---- 6a. binary traversal nodes (A/B arm of the traversal, flag LT_BVH_KEEP_BINARY) ----------------------------------
+// ---- 6a. binary traversal nodes (LT_TRAV_LBVH2, flag LT_BVH_KEEP_BINARY) -----------------------------------------------
+// leaf refs point into the LEAF-ordered triangle arrays the collapse has produced (wpos: primitive -> position)
 __global__ void emit_kernel(const Box* __restrict__ prim_boxes, const uint32_t* __restrict__ sorted_prim, int n, const int* __restrict__ left,
-                            const int* __restrict__ right, const Box* __restrict__ node_boxes, LbvhNode* __restrict__ out) {
+                            const int* __restrict__ right, const Box* __restrict__ node_boxes, const int32_t* __restrict__ wpos,
+                            LbvhNode* __restrict__ out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
     int c0 = left[i], c1 = right[i];
@@ -292,7 +294,7 @@ __global__ void emit_kernel(const Box* __restrict__ prim_boxes, const uint32_t* 
     nd.x = make_float4(b0.lo[0], b1.lo[0], b0.hi[0], b1.hi[0]);
     nd.y = make_float4(b0.lo[1], b1.lo[1], b0.hi[1], b1.hi[1]);
     nd.z = make_float4(b0.lo[2], b1.lo[2], b0.hi[2], b1.hi[2]);
-    nd.d = make_int4(c0 >= 0 ? c0 : ~(int)sorted_prim[~c0], c1 >= 0 ? c1 : ~(int)sorted_prim[~c1], 0, 0);
+    nd.d = make_int4(c0 >= 0 ? c0 : ~wpos[sorted_prim[~c0]], c1 >= 0 ? c1 : ~wpos[sorted_prim[~c1]], 0, 0);
     out[i] = nd;
 }
 
@@ -406,7 +408,8 @@ LT_DEVINL void write_wtri(const RawTris& r, int prim, WTri* __restrict__ out) {
 // and the binary nodes of the next level's wide nodes.
 __global__ void emit_wide_kernel(TreeView t, RawTris raw, int* __restrict__ wb, int level_start, int level_n, int next_start, int tri_start,
                                  const int* __restrict__ slots, const uint32_t* __restrict__ off_int, const uint32_t* __restrict__ off_tri,
-                                 WNode* __restrict__ out, WTri* __restrict__ wtris, int32_t* __restrict__ leaf_prims, double* __restrict__ sah) {
+                                 WNode* __restrict__ out, WTri* __restrict__ wtris, int32_t* __restrict__ leaf_prims, int32_t* __restrict__ wpos,
+                                 double* __restrict__ sah) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     double cost = 0.0;
     if (k < level_n) {
@@ -485,6 +488,7 @@ __global__ void emit_wide_kernel(TreeView t, RawTris raw, int* __restrict__ wb, 
                     const int prim = (int)t.sorted_prim[first + j];
                     write_wtri(raw, prim, wtris + tri_base + n_tri + j);
                     leaf_prims[tri_base + n_tri + j] = prim;
+                    wpos[prim] = (int32_t)(tri_base + n_tri + j);
                 }
                 n_tri += (uint32_t)cnt;
                 cost += (double)box_area(bx[i]) * cnt;
@@ -569,7 +573,7 @@ extern "C" int lt_bvh_build(lt_scene* s, int flags, lt_bvh_stats* out) {
     Tmp<float> block_cb, cb;
     Tmp<uint64_t> keys_a, keys_b;
     Tmp<uint32_t> vals_a, vals_b, hist, cnt_int, cnt_tri, totals;
-    Tmp<int> left, right, par_i, par_l, arrive, maxd, rng_lo, rng_hi, wb, slots;
+    Tmp<int> left, right, par_i, par_l, arrive, maxd, rng_lo, rng_hi, wb, slots, wpos;
     Tmp<WNode> wtmp;
     Tmp<double> sah;
     LT_CUDA_OK(prim_boxes.alloc(n)); LT_CUDA_OK(node_boxes.alloc(n));
@@ -579,7 +583,7 @@ extern "C" int lt_bvh_build(lt_scene* s, int flags, lt_bvh_stats* out) {
     LT_CUDA_OK(left.alloc(n)); LT_CUDA_OK(right.alloc(n)); LT_CUDA_OK(par_i.alloc(n)); LT_CUDA_OK(par_l.alloc(n));
     LT_CUDA_OK(rng_lo.alloc(n)); LT_CUDA_OK(rng_hi.alloc(n));
     LT_CUDA_OK(arrive.alloc(n)); LT_CUDA_OK(maxd.alloc(1));
-    LT_CUDA_OK(wb.alloc(n)); LT_CUDA_OK(slots.alloc(8 * (size_t)n)); LT_CUDA_OK(cnt_int.alloc(n)); LT_CUDA_OK(cnt_tri.alloc(n));
+    LT_CUDA_OK(wb.alloc(n)); LT_CUDA_OK(wpos.alloc(n)); LT_CUDA_OK(slots.alloc(8 * (size_t)n)); LT_CUDA_OK(cnt_int.alloc(n)); LT_CUDA_OK(cnt_tri.alloc(n));
     LT_CUDA_OK(totals.alloc(2)); LT_CUDA_OK(wtmp.alloc(n)); LT_CUDA_OK(sah.alloc(1));
     LT_CUDA_OK(cudaMemsetAsync(arrive.p, 0, (size_t)n * sizeof(int), st));
     LT_CUDA_OK(cudaMemsetAsync(maxd.p, 0, sizeof(int), st));
@@ -607,11 +611,6 @@ extern "C" int lt_bvh_build(lt_scene* s, int flags, lt_bvh_stats* out) {
     karras_kernel<<<iblocks, LB_THREADS, 0, st>>>(ki, n, left.p, right.p, par_i.p, par_l.p, rng_lo.p, rng_hi.p);
     refit_kernel<<<blocks, LB_THREADS, 0, st>>>(prim_boxes.p, vi, n, left.p, right.p, par_i.p, par_l.p, node_boxes.p, arrive.p);
     depth_kernel<<<blocks, LB_THREADS, 0, st>>>(n, par_i.p, par_l.p, maxd.p);
-    if (flags & LT_BVH_KEEP_BINARY) {
-        LT_CUDA_OK(lt_dev_malloc(&s->lbvh_nodes, (size_t)(n - 1) * sizeof(LbvhNode)));
-        emit_kernel<<<iblocks, LB_THREADS, 0, st>>>(prim_boxes.p, vi, n, left.p, right.p, node_boxes.p, s->lbvh_nodes);
-        s->n_lbvh_nodes = n - 1;
-    }
     cudaEventRecord(ev.e[3], st);
     LT_CUDA_OK(cudaGetLastError());
     // ---- collapse, breadth first: the wide nodes of a level are contiguous, children in slot order
@@ -623,7 +622,7 @@ extern "C" int lt_bvh_build(lt_scene* s, int flags, lt_bvh_stats* out) {
         collapse_kernel<<<lb, LB_THREADS, 0, st>>>(tv, wb.p, level_start, level_n, slots.p, cnt_int.p, cnt_tri.p);
         scan2_kernel<<<1, 1024, 0, st>>>(cnt_int.p, cnt_tri.p, level_n, totals.p);
         emit_wide_kernel<<<lb, LB_THREADS, 0, st>>>(tv, raw, wb.p, level_start, level_n, level_start + level_n, tri_cursor, slots.p, cnt_int.p,
-                                                    cnt_tri.p, wtmp.p, s->wtris, s->wleaf_prims, sah.p);
+                                                    cnt_tri.p, wtmp.p, s->wtris, s->wleaf_prims, wpos.p, sah.p);
         uint32_t tot[2];
         LT_CUDA_OK(cudaMemcpyAsync(tot, totals.p, sizeof tot, cudaMemcpyDeviceToHost, st));
         LT_CUDA_OK(cudaStreamSynchronize(st));
@@ -635,6 +634,11 @@ extern "C" int lt_bvh_build(lt_scene* s, int flags, lt_bvh_stats* out) {
     }
     const int n_wide = level_start;
     if (tri_cursor != n) { free_hierarchy(s); set_error("wide-BVH collapse placed %d of %d triangles", tri_cursor, n); return LT_E_OVERFLOW; }
+    if (flags & LT_BVH_KEEP_BINARY) {
+        LT_CUDA_OK(lt_dev_malloc(&s->lbvh_nodes, (size_t)(n - 1) * sizeof(LbvhNode)));
+        emit_kernel<<<iblocks, LB_THREADS, 0, st>>>(prim_boxes.p, vi, n, left.p, right.p, node_boxes.p, wpos.p, s->lbvh_nodes);
+        s->n_lbvh_nodes = n - 1;
+    }
     LT_CUDA_OK(lt_dev_malloc(&s->wnodes, (size_t)n_wide * sizeof(WNode)));
     LT_CUDA_OK(cudaMemcpyAsync(s->wnodes, wtmp.p, (size_t)n_wide * sizeof(WNode), cudaMemcpyDeviceToDevice, st));
     cudaEventRecord(ev.e[4], st);
@@ -660,6 +664,7 @@ extern "C" int lt_bvh_build(lt_scene* s, int flags, lt_bvh_stats* out) {
     stats.sort_ms = ms_sort;
     stats.collapse_ms = ms_collapse;
     stats.bytes = (int64_t)n_wide * (int64_t)sizeof(WNode) + (int64_t)n * (int64_t)sizeof(WTri);
+    stats.binary_bytes = (flags & LT_BVH_KEEP_BINARY) ? (int64_t)(n - 1) * (int64_t)sizeof(LbvhNode) + (int64_t)n * (int64_t)sizeof(WTri) : 0;
     for (int k = 0; k < 3; ++k) { stats.root_bmin[k] = root.lo[k]; stats.root_bmax[k] = root.hi[k]; }
     const double ra = (double)box_area(root);
     stats.sah_cost = ra > 0 ? cost / ra : 0.0;

@@ -173,7 +173,7 @@ walk_megakernel(const WalkParams<R> P) {
     // binary tree: stack in local memory (measured on C3: 3.35 Grays/s; the same stack in shared memory, [level][thread]: 3.28)
     int tstack[TRAV == LT_TRAV_LBVH2 ? LT_LBVH_STACK : 1];
     LbvhState<R> ts;
-    ts.cur = LT_LBVH_DONE; ts.sp = 0; ts.prim = -1; ts.best = (R)0;
+    ts.cur = LT_LBVH_DONE; ts.sp = 0; ts.prim = -1; ts.leaf = -1; ts.best = (R)0;
     V3<R> tinv = mk<R>((R)0, (R)0, (R)0);
     bool tracing = false;
     Stats st;
@@ -265,7 +265,7 @@ walk_megakernel(const WalkParams<R> P) {
                 wbvh_run<R>(full, ws8, wstack, LT_BLOCK, P.S.wnodes, P.S.wtris, P.S.wleaf_prims, tris, ln.o, ln.d, tinv, eps, ln.qtype == 2, ln.skip, st,
                             P.lbvh_chunk, P.S.wmagic);
                 active = tracing && ws8.sp < 0;                   // only lanes whose query just completed go on to shade
-                if (active) { tracing = false; ts.prim = ws8.prim; ts.best = ws8.best; }
+                if (active) { tracing = false; ts.prim = ws8.prim; ts.best = ws8.best; ts.leaf = ws8.leaf; }
             }
             if constexpr (TRAV == LT_TRAV_LBVH2) {
                 if (active && !tracing) {
@@ -273,7 +273,8 @@ walk_megakernel(const WalkParams<R> P) {
                     tinv = mk<R>((R)1 / ln.d.x, (R)1 / ln.d.y, (R)1 / ln.d.z);
                     tracing = true;
                 }
-                lbvh2_run<R>(full, ts, tstack, 1, P.S.lbvh, tris, ln.o, ln.d, tinv, eps, ln.qtype == 2, ln.skip, st, P.lbvh_chunk);
+                lbvh2_run<R>(full, ts, tstack, 1, P.S.lbvh, P.S.wtris, P.S.wleaf_prims, tris, ln.o, ln.d, tinv, eps, ln.qtype == 2, ln.skip, st,
+                             P.lbvh_chunk);
                 active = tracing && ts.cur == LT_LBVH_DONE;       // only lanes whose query just completed go on to shade
                 if (active) tracing = false;
             }
@@ -313,11 +314,11 @@ walk_megakernel(const WalkParams<R> P) {
                 R adv_rand0 = (R)0;
                 if (want == 1) {            // warp-uniform when phases are aligned
                     HitRec<R> hit_rec;
-                    if constexpr (TRAV == LT_TRAV_LBVH && sizeof(R) == 4) {
-                        // the float32 wide-BVH walk shades from the compact leaf-order record it has just tested: the
+                    if constexpr (HIER && sizeof(R) == 4) {
+                        // the float32 hierarchy walks shade from the compact leaf-order record they have just tested: the
                         // normal is rebuilt from ab x ac (R/src/primitives.py:108-111), material and is_light ride in c.w
                         if (prim >= 0) {
-                            const float4* wp = reinterpret_cast<const float4*>(P.S.wtris + ws8.leaf);
+                            const float4* wp = reinterpret_cast<const float4*>(P.S.wtris + ts.leaf);
                             const float4 wb = __ldg(wp + 1), wc = __ldg(wp + 2);
                             hit_rec.n = normalize_fast(cross(mk<float>(wb.x, wb.y, wb.z), mk<float>(wc.x, wc.y, wc.z)));
                             const int ml = __float_as_int(wc.w);

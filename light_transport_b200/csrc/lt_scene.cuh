@@ -54,8 +54,13 @@ struct alignas(16) CompatLeaf {
     int32_t flat_base; // position of its first primitive in the flattened (leaf-list order) primitive sequence
     int32_t pad;
 };
-// BVH2 node for the GPU LBVH: child boxes live in the parent so that one 64-byte fetch decides both
-// children.  ref >= 0: interior node index; ref < 0: leaf holding primitive ~ref.
+// BVH2 node of the Karras tree (LT_TRAV_LBVH2): child boxes live in the parent so that one 64-byte fetch decides both
+// children.  ref >= 0: interior node index; ref < 0: leaf holding the triangle at position ~ref of the leaf-ordered arrays
+// (WTri / wleaf_prims).  Boxes are EXACT float32 (rounded outwards from the float64 vertices): a 32-byte node with 16-bit planes
+// on a scene-wide grid (quantum = extent / 65000 = 2.4e-4 here) was built and measured in round 2 — half the bytes, but rays that
+// START on the rough mesh then enter 2.7x as many leaf boxes (tri tests 2.24 -> 6.16 per ray; the 8-wide hierarchy's per-node
+// 8-bit grid has the same quantum at leaf level and the same penalty) and the twelve I2F conversions per node cost more than
+// the two saved loads: 2.35 vs 3.35 Grays/s on C3.
 struct alignas(16) LbvhNode {
     float4 x;   // lo0.x lo1.x hi0.x hi1.x   one 128-bit word per axis, the two children side by side: the float32
     float4 y;   // lo0.y lo1.y hi0.y hi1.y   node step subtracts and multiplies both children at once (add/mul.f32x2)

@@ -67,7 +67,7 @@ class LtBvhStats(C.Structure):
     _fields_ = [("n_prims", C.c_int32), ("n_nodes", C.c_int32), ("max_depth", C.c_int32), ("binary_depth", C.c_int32),
                 ("build_ms", C.c_float), ("sort_ms", C.c_float), ("root_bmin", C.c_double * 3),
                 ("root_bmax", C.c_double * 3), ("sah_cost", C.c_double), ("collapse_ms", C.c_float), ("reserved", C.c_float),
-                ("bytes", C.c_int64)]
+                ("bytes", C.c_int64), ("binary_bytes", C.c_int64)]
 
 
 class LtError(RuntimeError):
@@ -211,7 +211,7 @@ class Renderer:
         _check(lib().lt_bvh_build(self._scene, C.c_int((1 if keep_binary else 0) | ((int(leaf_max) & 3) << 8)), C.byref(st)))
         self.lbvh_stats = dict(n_prims=st.n_prims, n_nodes=st.n_nodes, max_depth=st.max_depth, binary_depth=st.binary_depth,
                                build_ms=st.build_ms, sort_ms=st.sort_ms, collapse_ms=st.collapse_ms, sah_cost=st.sah_cost,
-                               bytes=st.bytes, root_bmin=list(st.root_bmin), root_bmax=list(st.root_bmax))
+                               bytes=st.bytes, binary_bytes=st.binary_bytes, root_bmin=list(st.root_bmin), root_bmax=list(st.root_bmax))
         return self.lbvh_stats
 
     # -- queries -----------------------------------------------------------------------------------
@@ -233,7 +233,7 @@ class Renderer:
     def render(self, *, width, height, spp, max_depth, camera, f_distance, s0=0, s1=None, semantics="reference",
                traversal="compat", real="f32", rand0=None, rand1=None, light_idx=None, seed=0, rr_start=None,
                film=None, return_samples=False, pixel_range=None, paths_per_warp=0, image=None, scheduler="megakernel", lbvh_chunk=0,
-               phased=None, ctas_per_sm=0):
+               phased=None, ctas_per_sm=0, l2_window=False):
         """One pass of the walk over samples ``[s0,s1)`` of every pixel.  Returns
         ``(film_sum, samples|None, counters)``; ``film`` may be a preallocated float64 buffer (numpy or a
         CUDA tensor / device address of H*W*3 doubles) that is accumulated into."""
@@ -248,6 +248,8 @@ class Renderer:
         p.paths_per_warp = int(paths_per_warp)
         p.flags = (int(lbvh_chunk) & 0xff) << 8          # LBVH traversal steps per megakernel iteration (0 = default)
         p.flags |= (int(ctas_per_sm) & 0xf) << 20        # A/B: cap on resident CTAs per SM (0 = what the kernel was built for)
+        if l2_window:
+            p.flags |= 1 << 19                           # A/B: persisting-L2 window on the hierarchy nodes (measured slower on C3)
         if phased is not None:                           # phase-aligned iterations: None = chosen from the scene, True / False = forced (A/B)
             p.flags |= (1 << 17) if phased else (1 << 16)
         cam = np.asarray(camera, dtype=np.float64)

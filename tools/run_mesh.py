@@ -14,6 +14,7 @@ ap.add_argument("--ny", type=int, default=500)
 ap.add_argument("--l2", action="store_true", help="also run the L2 / FP peaks micro-benchmarks")
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--leaf", type=int, default=0)
+ap.add_argument("--l2", action="store_true", dest="l2win")
 ap.add_argument("--trav", default="lbvh2", choices=["lbvh", "lbvh2"])
 a = ap.parse_args()
 import torch
@@ -30,7 +31,7 @@ kw = dict(width=1920, height=1080, spp=a.spp, max_depth=8, camera=cam, f_distanc
 for ct in [int(x) for x in a.ctas.split(",")]:
     for ch in [int(x) for x in a.chunks.split(",")]:
         for _ in range(a.reps):
-            c = R.render(lbvh_chunk=ch, ctas_per_sm=ct, **kw)[2]
+            c = R.render(lbvh_chunk=ch, ctas_per_sm=ct, l2_window=a.l2win, **kw)[2]
         rays = c["rays_ext"] + c["rays_shadow"]
         print(f"ctas {ct} chunk {ch:3d}: {c['kernel_ns']/1e6:8.2f} ms  {rays / c['kernel_ns'] * 1e3:8.1f} Mrays/s  box/ray {c['box_tests']/rays:.1f}  "
               f"tri/ray {c['tri_tests']/rays:.2f}  rays/path {rays / c['paths']:.2f}  lane util {c['lane_steps'] / max(c['lane_slots'], 1):.2f}  "

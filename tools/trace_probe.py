@@ -3,7 +3,7 @@ whole-query voted traversal) on camera rays and on the first and second generati
 sorted by (origin cell, direction octant).   trace_probe.py [--n 2000000]"""
 import argparse, sys
 sys.path.insert(0, ".")
-ap = argparse.ArgumentParser(); ap.add_argument("--n", type=int, default=2_000_000); ap.add_argument("--lib", default=None)
+ap = argparse.ArgumentParser(); ap.add_argument("--n", type=int, default=2_000_000); ap.add_argument("--lib", default=None); ap.add_argument("--off", type=float, default=1e-4)
 a = ap.parse_args()
 import numpy as np
 from light_transport_b200 import api, host, pack_scene, scenes, from_arrays
@@ -34,7 +34,7 @@ def bounce(o, d, prim, t):
     a_ = np.where(np.abs(nn[:, :1]) > 0.9, np.array([[0, 1.0, 0]]), np.array([[1.0, 0, 0]]))
     tx = np.cross(nn, a_); tx /= np.linalg.norm(tx, axis=1, keepdims=True); ty = np.cross(nn, tx)
     nd = rr[:, None] * np.cos(phi)[:, None] * tx + rr[:, None] * np.sin(phi)[:, None] * ty + z[:, None] * nn
-    no = p + 1e-4 * nn
+    no = p + a.off * nn
     return no[hit], nd[hit]
 
 def sort_rays(o, d, bits=5):

@@ -95,7 +95,8 @@ typedef struct {
     int32_t paths_per_warp;      /* megakernel work granule; 0 = auto */
     int32_t flags;               /* bits 8-15: LBVH traversal steps per megakernel iteration (0 = default 24);
                                     bit 16 / bit 17: force phase-aligned iterations off / on (default: from the scene);
-                                    bit 19: persisting-L2 window on the hierarchy nodes (A/B: measured slower); bits 20-23: cap on resident CTAs per SM
+                                    bit 18 (lt_render_records): gradient replays are NOT gated by bounce_record (calculate_grad=False, the
+                                    "more samples" block R/src/path_tracing.py:347); bit 19: persisting-L2 window on the hierarchy nodes (A/B: measured slower); bits 20-23: cap on resident CTAs per SM
                                     (0 = what the kernel was built for); rest reserved */
 } lt_render_params;
 
@@ -165,7 +166,9 @@ int lt_render_image(lt_scene *, const lt_render_params *, const double *rand0, c
  *   bounce_record          [H][W][spp][D] i8  Scene.bounce_record side effect                     (:50-52,77-79,151-153)
  *   direct_list, indirect_list [H][W][spp][3][D]  the root frame's lists, optional               (:99-100)
  *   rlp_minus, rlp_plus    [H][W][spp][2D][D] calculate_gradients' replays (:203-249), optional; need
- *                          logit0/logit1 [H][W][spp][D] = log(u/(1-u)) (Scene.rand_0_logit, scene.py:70-71). */
+ *                          logit0/logit1 [H][W][spp][D] = log(u/(1-u)) (Scene.rand_0_logit, scene.py:70-71).
+ * With a pixel sub-range (params.pixel0 < params.pixel1) only those pixels are walked and every array holds
+ * (pixel1 - pixel0) * spp rows instead of H * W * spp. */
 int lt_render_records(lt_scene *, const lt_render_params *, const double *rand0, const double *rand1,
                       const double *logit0, const double *logit1, const int32_t *light_idx, double *samples_out,
                       double *record_log_pdf, double *scene_record_log_pdf, int8_t *bounce_record, double *direct_list,

@@ -9,12 +9,12 @@ from . import api, scenes, compat_bvh  # noqa: F401
 from ._pack import PackedScene, pack_scene, from_arrays  # noqa: F401
 from .mesh_io import load_obj  # noqa: F401
 
-__all__ = ["render_scene", "render_scene_full", "intersect", "Renderer", "api", "scenes", "compat_bvh", "PackedScene",
+__all__ = ["render_scene", "render_scene_full", "render_more_samples", "intersect", "Renderer", "api", "scenes", "compat_bvh", "PackedScene",
            "pack_scene", "from_arrays", "load_obj"]
 
 
 def __getattr__(name):
-    if name in ("render_scene", "render_scene_full", "intersect", "Renderer", "lib"):
+    if name in ("render_scene", "render_scene_full", "render_more_samples", "intersect", "Renderer", "lib"):
         from . import host
         return getattr(host, name)
     raise AttributeError(name)

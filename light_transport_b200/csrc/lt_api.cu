@@ -485,7 +485,11 @@ static int do_records(lt_scene* s, const lt_render_params* p, const double* rand
     lt_ctx* ctx = s->ctx;
     cudaStream_t st = ctx->stream;
     const int W = p->width, H = p->height, D = p->max_depth, spp = p->spp;
-    const size_t paths = (size_t)W * H * spp;
+    // pixel sub-range [pixel0, pixel1): every array then holds (pixel1 - pixel0) * spp rows (0, 0 = the whole film)
+    const bool whole = p->pixel0 == 0 && p->pixel1 == 0;
+    const int64_t pix0 = whole ? 0 : p->pixel0, pix1 = whole ? (int64_t)W * H : p->pixel1;
+    if (pix0 < 0 || pix1 > (int64_t)W * H || pix1 < pix0) { set_error("lt_render_records: bad pixel range"); return LT_E_INVALID; }
+    const size_t paths = (size_t)(pix1 - pix0) * spp;
     const bool grads = rlp_minus && rlp_plus;
     InBuf<double> b0, b1, bl0, bl1;
     InBuf<int32_t> bl;
@@ -518,8 +522,12 @@ static int do_records(lt_scene* s, const lt_render_params* p, const double* rand
     P.rand0 = b0.dev; P.rand1 = b1.dev; P.light_idx = bl.dev;
     P.samples = o_s.dev;
     P.counters = reinterpret_cast<unsigned long long*>(ctx->d_counters);
+    P.pixel0 = (int32_t)pix0;
+    P.row_base = pix0 * spp;
     RecParams RP;
     memset(&RP, 0, sizeof RP);
+    RP.row_base = pix0 * spp;
+    RP.gate = (p->flags & (1 << 18)) ? 0 : 1;
     RP.rlp_a = o_rlp.dev; RP.scene_rlp = o_srlp.dev; RP.bounce_record = reinterpret_cast<signed char*>(o_br.dev);
     RP.direct = (o_dl.dev && o_il.dev) ? o_dl.dev : nullptr; RP.indirect = RP.direct ? o_il.dev : nullptr;
     RP.grad = 0; RP.mult = 1;

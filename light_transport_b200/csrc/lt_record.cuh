@@ -35,7 +35,9 @@ struct RecParams {
     const double* logit0;     // [paths][D]                 (grad, in)
     const double* logit1;
     int grad;                 // 0 base walk with records, 1 gradient replays
+    int gate;                 // gradient replays stop where bounce_record is 0 (calculate_grad=True, :37-39); 0: the "more samples" block
     int mult;                 // work items per sample: 1 (base) or 4*D (grad)
+    long long row_base;       // pixel sub-range: array rows are path_id - row_base (= pixel0 * spp)
 };
 
 template <typename R>
@@ -50,10 +52,10 @@ struct RecLane {
 
 template <typename R>
 LT_DEVINL void rec_rand(const WalkParams<R>& P, const RecParams& RP, const Lane<R>& ln, const RecLane<R>& rl, int bounce, R& r0, R& r1) {
-    if (!RP.grad) { get_rand<R>(P, ln.path_id, bounce, r0, r1); return; }
+    if (!RP.grad) { get_rand<R>(P, ln.path_id, bounce, r0, r1); return; }      // (replay rows: P.row_base)
     const int D = P.max_depth;
     const int which = rl.variant / (2 * D), ri = (rl.variant % (2 * D)) / 2, sign = rl.variant & 1;
-    double l0 = RP.logit0[(size_t)ln.path_id * D + bounce], l1 = RP.logit1[(size_t)ln.path_id * D + bounce];
+    double l0 = RP.logit0[(size_t)(ln.path_id - RP.row_base) * D + bounce], l1 = RP.logit1[(size_t)(ln.path_id - RP.row_base) * D + bounce];
     const double s = sign ? 0.01 : -0.01;                              // :210-214, :230-234
     if (bounce == ri) { if (which == 0) l0 += s; else l1 += s; }
     r0 = (R)(1.0 / (1.0 + exp(l0)));                                   // sigmoid of :19-21
@@ -62,7 +64,7 @@ LT_DEVINL void rec_rand(const WalkParams<R>& P, const RecParams& RP, const Lane<
 
 template <typename R>
 LT_DEVINL bool rec_gate(const WalkParams<R>& P, const RecParams& RP, const Lane<R>& ln) {   // :37-39, then :41
-    if (RP.grad && ln.bounce < P.max_depth && RP.bounce_record[(size_t)ln.path_id * P.max_depth + ln.bounce] == 0) return true;
+    if (RP.grad && RP.gate && ln.bounce < P.max_depth && RP.bounce_record[(size_t)(ln.path_id - RP.row_base) * P.max_depth + ln.bounce] == 0) return true;
     return ln.bounce >= P.max_depth;
 }
 
@@ -99,9 +101,9 @@ LT_DEVINL bool rec_advance(const WalkParams<R>& P, const RecParams& RP, Lane<R>&
         rl.row[ln.bounce] = lp;                                            // :94
         rl.has |= 1ull << ln.nframes;
         if (!RP.grad) {
-            RP.scene_rlp[(size_t)ln.path_id * D + ln.bounce] = lp;         // :95-96
+            RP.scene_rlp[(size_t)(ln.path_id - RP.row_base) * D + ln.bounce] = lp;         // :95-96
             if (ln.nframes == 0 && RP.indirect) {                           // :98,100 indirect = throughput * tp
-                double* il = RP.indirect + (size_t)ln.path_id * 3 * D;
+                double* il = RP.indirect + (size_t)(ln.path_id - RP.row_base) * 3 * D;
                 il[0 * D + ln.bounce] = (double)(ln.L.x - rl.Lsnap.x);
                 il[1 * D + ln.bounce] = (double)(ln.L.y - rl.Lsnap.y);
                 il[2 * D + ln.bounce] = (double)(ln.L.z - rl.Lsnap.z);
@@ -144,19 +146,19 @@ __global__ void __launch_bounds__(LT_BLOCK) record_kernel(const WalkParams<R> P,
                 rl.has = 0; rl.min_zero = D;
                 rl.Lsnap = mk<R>((R)0, (R)0, (R)0);
                 if (!RP.grad) {
-                    rl.row = RP.rlp_a + (size_t)ln.path_id * D;
-                    for (int b = 0; b < D; ++b) RP.scene_rlp[(size_t)ln.path_id * D + b] = 0.0;
-                    if (RP.direct) for (int k = 0; k < 3 * D; ++k) { RP.direct[(size_t)ln.path_id * 3 * D + k] = 0.0; RP.indirect[(size_t)ln.path_id * 3 * D + k] = 0.0; }
+                    rl.row = RP.rlp_a + (size_t)(ln.path_id - RP.row_base) * D;
+                    for (int b = 0; b < D; ++b) RP.scene_rlp[(size_t)(ln.path_id - RP.row_base) * D + b] = 0.0;
+                    if (RP.direct) for (int k = 0; k < 3 * D; ++k) { RP.direct[(size_t)(ln.path_id - RP.row_base) * 3 * D + k] = 0.0; RP.indirect[(size_t)(ln.path_id - RP.row_base) * 3 * D + k] = 0.0; }
                 } else {
                     const int which = rl.variant / (2 * D), ri = (rl.variant % (2 * D)) / 2, sign = rl.variant & 1;
-                    rl.row = (sign ? RP.rlp_b : RP.rlp_a) + ((size_t)ln.path_id * 2 * D + (size_t)(which * D + ri)) * D;
+                    rl.row = (sign ? RP.rlp_b : RP.rlp_a) + ((size_t)(ln.path_id - RP.row_base) * 2 * D + (size_t)(which * D + ri)) * D;
                 }
                 for (int b = 0; b < D; ++b) rl.row[b] = 0.0;
                 if (ln.qtype != 0 && rec_gate<R>(P, RP, ln)) ln.qtype = 0;   // gated at bounce 0: nothing traced
                 if (ln.qtype == 0) {                                          // ended before the first query
                     n_paths++;
-                    if (!RP.grad) for (int b = 0; b < D; ++b) RP.bounce_record[(size_t)ln.path_id * D + b] = 1;
-                    if (!RP.grad && P.samples) { double* o = P.samples + ((size_t)pix * P.ns + s_rel) * 3; o[0] = o[1] = o[2] = 0; }
+                    if (!RP.grad) for (int b = 0; b < D; ++b) RP.bounce_record[(size_t)(ln.path_id - RP.row_base) * D + b] = 1;
+                    if (!RP.grad && P.samples) { double* o = P.samples + ((size_t)(pix - P.pixel0) * P.ns + s_rel) * 3; o[0] = o[1] = o[2] = 0; }
                 }
             }
         }
@@ -198,7 +200,7 @@ __global__ void __launch_bounds__(LT_BLOCK) record_kernel(const WalkParams<R> P,
                     if (ln.nframes == 0) {
                         rl.Lsnap = ln.L;
                         if (!RP.grad && RP.direct) {                                                  // :99
-                            double* dl = RP.direct + (size_t)ln.path_id * 3 * D;
+                            double* dl = RP.direct + (size_t)(ln.path_id - RP.row_base) * 3 * D;
                             dl[0 * D + ln.bounce] = occluded ? 0.0 : (double)ln.contrib.x;
                             dl[1 * D + ln.bounce] = occluded ? 0.0 : (double)ln.contrib.y;
                             dl[2 * D + ln.bounce] = occluded ? 0.0 : (double)ln.contrib.z;
@@ -233,9 +235,9 @@ __global__ void __launch_bounds__(LT_BLOCK) record_kernel(const WalkParams<R> P,
                 n_paths++;
                 if (!(rl.has & 1ull)) for (int b = 0; b < D; ++b) rl.row[b] = 0.0;     // the root never recursed: zeros
                 if (!RP.grad) {
-                    for (int b = 0; b < D; ++b) RP.bounce_record[(size_t)ln.path_id * D + b] = b < rl.min_zero ? 1 : 0;
+                    for (int b = 0; b < D; ++b) RP.bounce_record[(size_t)(ln.path_id - RP.row_base) * D + b] = b < rl.min_zero ? 1 : 0;
                     if (P.samples) {
-                        double* o = P.samples + ((size_t)ln.pix * P.ns + ln.s_rel) * 3;
+                        double* o = P.samples + ((size_t)(ln.pix - P.pixel0) * P.ns + ln.s_rel) * 3;
                         o[0] = (double)ln.L.x; o[1] = (double)ln.L.y; o[2] = (double)ln.L.z;
                     }
                     if (P.film) {

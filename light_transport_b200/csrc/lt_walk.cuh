@@ -27,6 +27,7 @@ struct WalkParams {
     int32_t lbvh_chunk;           // megakernel, LBVH: voted traversal steps per loop iteration
     int32_t phased;               // megakernel, COMPAT / NEAREST: phase-aligned iterations (see lt_megakernel.cuh)
     int64_t total_paths;          // (pixel1 - pixel0) * ns
+    int64_t row_base;             // replayed rand_0 / rand_1 / light_idx rows are path_id - row_base (lt_render_records on a pixel sub-range; else 0)
     double rr_floor, eps, cam[3], f_distance, top, bottom, step_x, step_y;
     uint64_t seed;
     const double* rand0;          // [H][W][spp][D] or null
@@ -97,7 +98,7 @@ LT_DEVINL uint64_t path_id_of(const WalkParams<R>& P, const Lane<R>& ln) {
 template <typename R>
 LT_DEVINL void get_rand(const WalkParams<R>& P, uint64_t path_id, int bounce, R& r0, R& r1) {
     if (P.rand0) {
-        size_t idx = (size_t)path_id * (size_t)P.max_depth + (size_t)bounce;
+        size_t idx = (size_t)(path_id - (uint64_t)P.row_base) * (size_t)P.max_depth + (size_t)bounce;
         r0 = (R)__ldg(P.rand0 + idx);
         r1 = (R)__ldg(P.rand1 + idx);
     } else {
@@ -120,7 +121,7 @@ LT_DEVINL int pick_light(const WalkParams<R>& P, Lane<R>& ln, uint32_t& overflow
     const uint64_t path_id = path_id_of(P, ln);
     if (P.light_idx) {
         if ((int)k >= P.n_light_idx) { overflow++; return 0; }
-        return __ldg(P.light_idx + (size_t)path_id * (size_t)P.n_light_idx + k);
+        return __ldg(P.light_idx + (size_t)(path_id - (uint64_t)P.row_base) * (size_t)P.n_light_idx + k);
     }
     if (P.S.n_lights == 1) return 0;
     uint32_t w[4];

@@ -287,12 +287,17 @@ class Renderer:
         return film_buf, samples, cnt.as_dict()
 
     def render_records(self, *, width, height, spp, max_depth, camera, f_distance, rand0, rand1, light_idx=None,
-                       traversal="compat", real="f64", gradients=False, lists=True, seed=0):
+                       traversal="compat", real="f64", gradients=False, lists=True, seed=0, pixel_range=None, ungated=False,
+                       logits=None):
         """The per-sample outputs of the reference's ``render_scene_samples`` (R/src/path_tracing.py:251-303) for
         replayed random numbers: dict with ``samples``, ``record_log_pdf`` (the array ``trace_path`` returns),
         ``scene_record_log_pdf`` / ``bounce_record`` (what it writes into ``Scene``), ``direct_list`` /
         ``indirect_list`` (root frame) and, with ``gradients=True``, ``rlp_minus`` / ``rlp_plus`` / ``record_s`` of
-        ``calculate_gradients`` (:203-249).  REFERENCE semantics, ``max_depth <= 32``."""
+        ``calculate_gradients`` (:203-249).  REFERENCE semantics, ``max_depth <= 32``.
+        ``pixel_range=(p0, p1)`` walks only those pixels (row-major) of the ``width x height`` film; every array, in and
+        out, then has the leading shape ``[p1 - p0, spp, ...]`` instead of ``[H, W, spp, ...]``.  ``ungated=True`` runs the
+        gradient replays with ``calculate_grad=False`` and ``logits=(l0, l1)`` overrides the logits derived from the
+        uniforms — together they are the "more samples" block of the reference (:310-364)."""
         p = LtRenderParams()
         p.width, p.height, p.spp, p.s0, p.s1, p.max_depth = width, height, spp, 0, spp, max_depth
         p.semantics, p.traversal, p.real, p.scheduler = 0, TRAVERSAL[traversal], REAL[real], 0
@@ -302,27 +307,40 @@ class Renderer:
             p.camera[k] = float(cam[k])
         rand0 = np.ascontiguousarray(rand0, dtype=np.float64)
         rand1 = np.ascontiguousarray(rand1, dtype=np.float64)
-        if rand0.shape != (height, width, spp, max_depth) or rand1.shape != rand0.shape:
-            raise ValueError("rand_0/rand_1 must be [H,W,spp,max_depth]")
+        lead = (height, width)
+        if pixel_range is not None:
+            p.pixel0, p.pixel1 = int(pixel_range[0]), int(pixel_range[1])
+            if not (0 <= p.pixel0 < p.pixel1 <= width * height):
+                raise ValueError("pixel_range must satisfy 0 <= p0 < p1 <= W*H")
+            lead = (p.pixel1 - p.pixel0,)
+        if ungated:
+            p.flags |= 1 << 18
+        if rand0.shape != lead + (spp, max_depth) or rand1.shape != rand0.shape:
+            raise ValueError(f"rand_0/rand_1 must be {lead + (spp, max_depth)}")
         if light_idx is not None:
             light_idx = np.ascontiguousarray(light_idx, dtype=np.int32)
-            if light_idx.shape[:3] != (height, width, spp):
-                raise ValueError("light_idx must be [H,W,spp,K]")
-            p.n_light_idx = light_idx.shape[3]
+            if light_idx.shape[:-1] != lead + (spp,):
+                raise ValueError("light_idx must be [..., spp, K] like rand_0")
+            p.n_light_idx = light_idx.shape[-1]
         D = max_depth
-        out = dict(samples=np.zeros((height, width, spp, 3)), record_log_pdf=np.zeros((height, width, spp, D)),
-                   scene_record_log_pdf=np.zeros((height, width, spp, D)), bounce_record=np.ones((height, width, spp, D), np.int8))
+        out = dict(samples=np.zeros(lead + (spp, 3)), record_log_pdf=np.zeros(lead + (spp, D)),
+                   scene_record_log_pdf=np.zeros(lead + (spp, D)), bounce_record=np.ones(lead + (spp, D), np.int8))
         if lists:
-            out["direct_list"] = np.zeros((height, width, spp, 3, D))
-            out["indirect_list"] = np.zeros((height, width, spp, 3, D))
+            out["direct_list"] = np.zeros(lead + (spp, 3, D))
+            out["indirect_list"] = np.zeros(lead + (spp, 3, D))
         l0 = l1 = None
         if gradients:
-            with np.errstate(divide="ignore"):
-                l0 = np.log(rand0 / (1 - rand0))              # Scene.rand_0_logit, R/src/scene.py:70-71
-                l1 = np.log(rand1 / (1 - rand1))
-            out["rlp_minus"] = np.zeros((height, width, spp, 2 * D, D))
-            out["rlp_plus"] = np.zeros((height, width, spp, 2 * D, D))
-            out["record_s"] = np.full((height, width, spp, 2 * D), 0.01)      # _s of :210,230
+            if logits is not None:
+                l0, l1 = (np.ascontiguousarray(a, dtype=np.float64) for a in logits)
+                if l0.shape != rand0.shape or l1.shape != rand0.shape:
+                    raise ValueError("logits must have the shape of rand_0")
+            else:
+                with np.errstate(divide="ignore"):
+                    l0 = np.log(rand0 / (1 - rand0))              # Scene.rand_0_logit, R/src/scene.py:70-71
+                    l1 = np.log(rand1 / (1 - rand1))
+            out["rlp_minus"] = np.zeros(lead + (spp, 2 * D, D))
+            out["rlp_plus"] = np.zeros(lead + (spp, 2 * D, D))
+            out["record_s"] = np.full(lead + (spp, 2 * D), 0.01)      # _s of :210,230
         cnt = LtCounters()
         self._bind()
         _check(lib().lt_render_records(self._scene, C.byref(p), _ptr(rand0, PD), _ptr(rand1, PD), _ptr(l0, PD), _ptr(l1, PD),
@@ -526,7 +544,50 @@ def render_scene(scene, primitives, bvh=None, *, spp=None, rng=None, seed=0, sem
     return out[0] if len(out) == 1 else out
 
 
-def render_scene_full(scene, primitives, bvh=None, *, light_idx=None, traversal="compat", real="f64", device=0):
+MORE_SAMPLES_PIXELS = ((20, 60), (60, 25), (60, 80), (65, 110))      # more_samples_h / more_samples_w, R/src/path_tracing.py:313-314
+
+
+def render_more_samples(scene, primitives, bvh=None, *, pixels=MORE_SAMPLES_PIXELS, n=500, rand0=None, rand1=None, light_idx=None,
+                        traversal="compat", real="f64", device=0, renderer=None):
+    """The "more samples" block of the reference's ``render_scene_samples`` (R/src/path_tracing.py:310-364): ``n`` extra
+    samples at a few fixed pixels ``(i, j)``, each with its 4*D finite-difference replays, returned as the reference's
+    5-tuple ``(samples_2 [P,n,3], record_log_pdf_2 [P,n,D], record_log_pdf_minus_set_2 [P,n,2D,D], ..._plus_set_2, record_s_set_2
+    [P,n,2D])``.  Two quirks of the block are kept: it hands the UNIFORM numbers to ``calculate_gradients`` where that expects
+    logits (:347), and it replays with ``calculate_grad=False`` (no gating by ``bounce_record``).  Not reproduced: the block's
+    writes into ``scene.bounce_record`` / ``scene.record_log_pdf`` at sample indices up to ``n-1``, which run past
+    ``number_of_samples`` in the reference.  ``rand0`` / ``rand1``: ``[P, n, D]`` uniforms (the reference draws them from numba's
+    private generator inside the loop, :328-329; default: ``np.random.rand``)."""
+    H, W, D = int(scene.height), int(scene.width), int(scene.max_depth)
+    Pn = len(pixels)
+    rand0 = np.random.rand(Pn, n, D) if rand0 is None else np.ascontiguousarray(rand0, dtype=np.float64)
+    rand1 = np.random.rand(Pn, n, D) if rand1 is None else np.ascontiguousarray(rand1, dtype=np.float64)
+    if rand0.shape != (Pn, n, D) or rand1.shape != (Pn, n, D):
+        raise ValueError(f"rand0/rand1 must be {(Pn, n, D)}")
+    own = renderer is None
+    if own:
+        packed = primitives if isinstance(primitives, _pack.PackedScene) else _pack.pack_scene(primitives, scene.lights)
+        nodes = _nodes_from_bvh(bvh, packed) if traversal == "compat" else None
+        renderer = Renderer(packed, nodes, device=device, build_lbvh=_lbvh_mode(traversal))
+    try:
+        parts = []
+        for k, (i, j) in enumerate(pixels):
+            if not (0 <= i < H and 0 <= j < W):
+                raise ValueError(f"pixel {(i, j)} outside the {H} x {W} film")
+            pix = i * W + j
+            o = renderer.render_records(width=W, height=H, spp=n, max_depth=D, camera=scene.camera, f_distance=scene.f_distance,
+                                        rand0=rand0[k:k + 1], rand1=rand1[k:k + 1],
+                                        light_idx=None if light_idx is None else np.asarray(light_idx)[k:k + 1], traversal=traversal,
+                                        real=real, gradients=True, lists=False, pixel_range=(pix, pix + 1), ungated=True,
+                                        logits=(rand0[k:k + 1], rand1[k:k + 1]))
+            parts.append(o)
+    finally:
+        if own:
+            renderer.close()
+    cat = lambda key: np.concatenate([p_[key] for p_ in parts], axis=0)
+    return cat("samples"), cat("record_log_pdf"), cat("rlp_minus"), cat("rlp_plus"), cat("record_s")
+
+
+def render_scene_full(scene, primitives, bvh=None, *, light_idx=None, traversal="compat", real="f64", device=0, more_samples=None):
     """The reference's CURRENT ``path_tracing.render_scene`` (R/src/path_tracing.py:371-387), whose return value
     feeds the control-variate cells of ``R/examples/LTS.ipynb``: the 10-tuple
 
@@ -534,8 +595,9 @@ def render_scene_full(scene, primitives, bvh=None, *, light_idx=None, traversal=
         record_log_pdf_plus_set, record_s_set, data_more_samples, two_light_list
 
     and the side effects on ``scene.image`` / ``scene.bounce_record`` / ``scene.record_log_pdf``.  Consumes
-    ``scene.rand_0/rand_1`` (replay).  ``data_more_samples`` is ``None``: that block (:310-364) draws from numba's
-    private generator inside njit and indexes fixed pixels of a 150x150 film — notebook-specific."""
+    ``scene.rand_0/rand_1`` (replay).  ``data_more_samples`` is the 5-tuple of ``render_more_samples`` (the block :310-364 with
+    its fixed pixels of a 150x150 film) when the film contains those pixels — ``more_samples=False`` skips it, a dict of
+    keyword arguments (``pixels``, ``n``, ``rand0``, ``rand1``) customises it — else ``None``."""
     H, W, D, S = int(scene.height), int(scene.width), int(scene.max_depth), int(scene.number_of_samples)
     if getattr(scene, "rand_0", None) is None:
         raise ValueError("render_scene_full replays scene.rand_0/rand_1")
@@ -546,6 +608,11 @@ def render_scene_full(scene, primitives, bvh=None, *, light_idx=None, traversal=
         o = r.render_records(width=W, height=H, spp=S, max_depth=D, camera=scene.camera, f_distance=scene.f_distance,
                              rand0=np.asarray(scene.rand_0), rand1=np.asarray(scene.rand_1), light_idx=light_idx,
                              traversal=traversal, real=real, gradients=True)
+        more = None
+        mkw = dict(more_samples) if isinstance(more_samples, dict) else {}
+        pixels = mkw.get("pixels", MORE_SAMPLES_PIXELS)
+        if more_samples is not False and all(0 <= i < H and 0 <= j < W for i, j in pixels):
+            more = render_more_samples(scene, primitives, bvh, traversal=traversal, real=real, renderer=r, **mkw)
     finally:
         r.close()
     image_ver0 = np.array(scene.image, dtype=np.float64, copy=True)        # :373 copies scene.image BEFORE rendering
@@ -556,5 +623,5 @@ def render_scene_full(scene, primitives, bvh=None, *, light_idx=None, traversal=
             getattr(scene, name)[...] = val
         except Exception:
             setattr(scene, name, val)
-    return (image_ver0, image, image_ver2, o["samples"], o["record_log_pdf"], o["rlp_minus"], o["rlp_plus"], o["record_s"], None,
+    return (image_ver0, image, image_ver2, o["samples"], o["record_log_pdf"], o["rlp_minus"], o["rlp_plus"], o["record_s"], more,
             (o["direct_list"], o["indirect_list"]))

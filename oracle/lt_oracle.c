@@ -359,7 +359,8 @@ typedef struct {
     double *scene_rlp;      /* scene.record_log_pdf[i,j,s,:]  (written when !grad) */
     int8_t *bounce_record;  /* scene.bounce_record[i,j,s,:]   (written when !grad, read when grad) */
     const double *r0, *r1;  /* rand sets of THIS replay (may differ from the walk's base rows) */
-    int grad;
+    int grad;               /* a gradient replay: no side effects on the scene arrays */
+    int gate;               /* replays stop where bounce_record is 0 (calculate_grad=True, :37-39) */
 } rec_t;
 
 static void trace_path_reference_rec(walk_t *w, const rec_t *rc, ray_t *ray, int bounce, double *light, double *rlp,
@@ -373,7 +374,7 @@ static void trace_path_reference_rec(walk_t *w, const rec_t *rc, ray_t *ray, int
     if (dl) for (int k = 0; k < 3 * D; ++k) { dl[k] = 0; il[k] = 0; }
     for (;;) {
         /* :33-34 read rand_set[bounce] before any test (index D is read but unused there) */
-        if (rc->grad && bounce < D && rc->bounce_record[bounce] == 0) break;       /* :37-39 */
+        if (rc->grad && rc->gate && bounce < D && rc->bounce_record[bounce] == 0) break;       /* :37-39 (calculate_grad is True) */
         if (bounce >= D) break;
         double rand_0 = rc->r0[bounce], rand_1 = rc->r1[bounce];
         int prim; double t;
@@ -446,15 +447,16 @@ int lto_render_records(const lto_scene *S, const lto_params *P, const double *ra
         memset(&w, 0, sizeof w);
         w.S = S; w.P = P;
         double *r0s = (double *)malloc(sizeof(double) * 2 * (size_t)D), *r1s = r0s + D;
+        const int64_t pix_lo = (P->pixel0 == 0 && P->pixel1 == 0) ? 0 : P->pixel0, pix_hi = (P->pixel0 == 0 && P->pixel1 == 0) ? (int64_t)W * H : P->pixel1;
 #pragma omp for schedule(dynamic, 16)
-        for (int64_t pix = 0; pix < (int64_t)W * H; ++pix) {
+        for (int64_t pix = pix_lo; pix < pix_hi; ++pix) {
             int i = (int)(pix / W), j = (int)(pix % W);
             double y = (H > 1 && i == H - 1) ? bottom : top + i * step_y;
             double x = (W > 1 && j == W - 1) ? 1.0 : -1.0 + j * step_x;
             for (int s = 0; s < spp; ++s) {
-                uint64_t path = (uint64_t)pix * (uint64_t)spp + (uint64_t)s;
+                uint64_t path = (uint64_t)(pix - pix_lo) * (uint64_t)spp + (uint64_t)s;      /* row of the (sub-range) arrays */
                 const double *b0 = rand0 + path * (uint64_t)D, *b1 = rand1 + path * (uint64_t)D;
-                w.path_id = path;
+                w.path_id = (uint64_t)pix * (uint64_t)spp + (uint64_t)s;
                 w.r0 = b0; w.r1 = b1;
                 w.lidx = light_idx ? light_idx + path * (uint64_t)P->n_light_idx : 0;
                 w.nee_count = 0;
@@ -466,7 +468,7 @@ int lto_render_records(const lto_scene *S, const lto_params *P, const double *ra
                 rc.scene_rlp = scene_record_log_pdf + path * (uint64_t)D;
                 rc.bounce_record = bounce_record + path * (uint64_t)D;
                 for (int b = 0; b < D; ++b) { rc.scene_rlp[b] = 0; rc.bounce_record[b] = 1; }   /* R/src/scene.py:72-73 */
-                rc.r0 = b0; rc.r1 = b1; rc.grad = 0;
+                rc.r0 = b0; rc.r1 = b1; rc.grad = 0; rc.gate = P->grad_ungated ? 0 : 1;
                 double L[3];
                 ray = cam_ray;
                 trace_path_reference_rec(&w, &rc, &ray, 0, L, record_log_pdf + path * (uint64_t)D,

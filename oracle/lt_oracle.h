@@ -41,6 +41,11 @@ typedef struct {
     int32_t pad_;
     double rr_floor, eps, camera[3], f_distance;
     uint64_t seed;       /* Philox key when rand0 == NULL */
+    int32_t pixel0, pixel1;   /* lto_render_records only: pixel sub-range [pixel0, pixel1) (row-major; 0,0 = whole film); the arrays then
+                                 hold (pixel1 - pixel0) * spp rows */
+    int32_t grad_ungated;     /* lto_render_records only: the gradient replays run with calculate_grad=False (not gated by bounce_record):
+                                 the "more samples" block, R/src/path_tracing.py:347-348 */
+    int32_t pad2_;
 } lto_params;
 
 typedef struct {

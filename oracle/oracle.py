@@ -31,7 +31,7 @@ class LtoParams(C.Structure):
                 ("max_depth", C.c_int32), ("semantics", C.c_int32), ("traversal", C.c_int32), ("rr_start", C.c_int32),
                 ("n_light_idx", C.c_int32), ("n_threads", C.c_int32), ("pad_", C.c_int32),
                 ("rr_floor", C.c_double), ("eps", C.c_double), ("camera", C.c_double * 3), ("f_distance", C.c_double),
-                ("seed", C.c_uint64)]
+                ("seed", C.c_uint64), ("pixel0", C.c_int32), ("pixel1", C.c_int32), ("grad_ungated", C.c_int32), ("pad2_", C.c_int32)]
 
 
 class LtoCounters(C.Structure):
@@ -156,7 +156,7 @@ def render_pixels(scene: OracleScene, pixels, *, width, height, spp, max_depth, 
 
 
 def render_records(scene: OracleScene, *, width, height, spp, max_depth, camera, f_distance, rand0, rand1, light_idx=None,
-                   traversal="compat", gradients=False, n_threads=0):
+                   traversal="compat", gradients=False, n_threads=0, pixel_range=None, ungated=False, logits=None):
     """render_scene_samples' per-sample outputs (lto_render_records): dict with samples, record_log_pdf,
     scene_record_log_pdf, bounce_record, direct_list, indirect_list and (gradients=True) rlp_minus/rlp_plus/record_s."""
     p = LtoParams()
@@ -167,20 +167,28 @@ def render_records(scene: OracleScene, *, width, height, spp, max_depth, camera,
         p.camera[k] = float(camera[k])
     rand0 = np.ascontiguousarray(rand0, dtype=np.float64)
     rand1 = np.ascontiguousarray(rand1, dtype=np.float64)
-    assert rand0.shape == (height, width, spp, max_depth)
-    l0 = np.log(rand0 / (1 - rand0))          # R/src/scene.py:70-71
-    l1 = np.log(rand1 / (1 - rand1))
+    lead = (height, width)
+    if pixel_range is not None:           # arrays cover the pixels [pixel0, pixel1) only: shape [n_pixels, spp, ...]
+        p.pixel0, p.pixel1 = int(pixel_range[0]), int(pixel_range[1])
+        lead = (p.pixel1 - p.pixel0,)
+    p.grad_ungated = 1 if ungated else 0
+    assert rand0.shape == lead + (spp, max_depth)
+    if logits is not None:                # the "more samples" block hands the uniforms themselves to calculate_gradients (:347)
+        l0, l1 = (np.ascontiguousarray(a, dtype=np.float64) for a in logits)
+    else:
+        l0 = np.log(rand0 / (1 - rand0))          # R/src/scene.py:70-71
+        l1 = np.log(rand1 / (1 - rand1))
     if light_idx is not None:
         light_idx = np.ascontiguousarray(light_idx, dtype=np.int32)
-        p.n_light_idx = light_idx.shape[3]
+        p.n_light_idx = light_idx.shape[-1]
     D = max_depth
-    out = dict(samples=np.zeros((height, width, spp, 3)), record_log_pdf=np.zeros((height, width, spp, D)),
-               scene_record_log_pdf=np.zeros((height, width, spp, D)), bounce_record=np.ones((height, width, spp, D), np.int8),
-               direct_list=np.zeros((height, width, spp, 3, D)), indirect_list=np.zeros((height, width, spp, 3, D)))
+    out = dict(samples=np.zeros(lead + (spp, 3)), record_log_pdf=np.zeros(lead + (spp, D)),
+               scene_record_log_pdf=np.zeros(lead + (spp, D)), bounce_record=np.ones(lead + (spp, D), np.int8),
+               direct_list=np.zeros(lead + (spp, 3, D)), indirect_list=np.zeros(lead + (spp, 3, D)))
     if gradients:
-        out["rlp_minus"] = np.zeros((height, width, spp, 2 * D, D))
-        out["rlp_plus"] = np.zeros((height, width, spp, 2 * D, D))
-        out["record_s"] = np.full((height, width, spp, 2 * D), 0.01)
+        out["rlp_minus"] = np.zeros(lead + (spp, 2 * D, D))
+        out["rlp_plus"] = np.zeros(lead + (spp, 2 * D, D))
+        out["record_s"] = np.full(lead + (spp, 2 * D), 0.01)
     cnt = LtoCounters()
     L = lib()
     L.lto_render_records.restype = C.c_int

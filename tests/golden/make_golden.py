@@ -12,6 +12,7 @@ What is pinned (SURVEY.md §4, §8c — the reference has no tests or golden vec
   mirror_scene.npz    same for the C4a mirror box
   rays_*.npz          ray sets → (prim id, t) from the reference's intersect_bvh (COMPAT) and
                       from brute-force triangle_intersect (NEAREST semantics)
+  more_samples_*.npz  the "more samples" block (R/src/path_tracing.py:310-364) around the reference's trace_path + calculate_gradients
   hg_table.npz        the reference's henyey_greenstein(cosTheta, g) on a grid (R/src/medium_samples.py:14-16)
   paths_*.npz         per-(pixel, sample) radiance from the reference's trace_path with
                       replayed rand_0/rand_1 and replayed light indices
@@ -308,6 +309,63 @@ def golden_paths(name, objects, lin, lights, camera, fdist, W, H, spp, D, rand_s
                         image=np.clip(out.mean(axis=2), 0, 1))
 
 
+@numba.njit
+def drive_more(scene, prims, bvh, seed_base, px_h, px_w, rand_0_2, rand_1_2, samples_2, rlp_2, minus_2, plus_2, s_2):
+    # restates the "more samples" block of render_scene_samples, R/src/path_tracing.py:310-364, for given pixels and random
+    # numbers (the block itself draws them from numba's generator inside its loop, :328-329, and is what stops the
+    # reference's top-level render_scene from compiling under numba 0.65)
+    H, W = scene.height, scene.width
+    top_bottom = np.linspace(scene.top, scene.bottom, H)
+    left_right = np.linspace(scene.left, scene.right, W)
+    n = rand_0_2.shape[1]
+    for _i in range(len(px_h)):
+        i = px_h[_i]
+        j = px_w[_i]
+        y = top_bottom[i]
+        for _sample in range(n):
+            rand_0_set = rand_0_2[_i, _sample, :]
+            rand_1_set = rand_1_2[_i, _sample, :]
+            x = left_right[j]
+            end = np.array([x, y, scene.f_distance, 1], dtype=np.float64)
+            end[0] += rand_0_set[0] / W
+            end[1] += rand_0_set[0] / H
+            origin = np.array([scene.camera[0], scene.camera[1], scene.camera[2], 1], dtype=np.float64)
+            direction = normalize(end - origin)
+            ray = Ray(origin, direction)
+            np.random.seed(seed_base + _i * n + _sample)
+            tp_result, _rlp, _ll = ref_trace(scene, prims, bvh, ray, 0, rand_0_set, rand_1_set, (i, j, _sample), False)
+            m, p, ss = ref_grads(scene, prims, bvh, origin, direction, rand_0_set, rand_1_set, (i, j, _sample), False)
+            samples_2[_i, _sample, :] = tp_result
+            rlp_2[_i, _sample, :] = _rlp
+            minus_2[_i, _sample, :, :] = m
+            plus_2[_i, _sample, :, :] = p
+            s_2[_i, _sample, :] = ss
+
+
+def golden_more(name, objects, lin, lights, camera, fdist, W, H, n, D, pixels, rand_seed, seed_base):
+    sc = r_scene.Scene(camera=camera, lights=lights, width=W, height=H, max_depth=D, f_distance=fdist, number_of_samples=n)
+    P_ = len(pixels)
+    np.random.seed(rand_seed)
+    rand_0_2 = np.random.rand(P_, n, D)
+    rand_1_2 = np.random.rand(P_, n, D)
+    px_h = np.array([p[0] for p in pixels], np.int64)
+    px_w = np.array([p[1] for p in pixels], np.int64)
+    samples_2 = np.zeros((P_, n, 3)); rlp_2 = np.zeros((P_, n, D))
+    minus_2 = np.zeros((P_, n, 2 * D, D)); plus_2 = np.zeros((P_, n, 2 * D, D)); s_2 = np.zeros((P_, n, 2 * D))
+    t0 = time.time()
+    drive_more(sc, objects, lin, seed_base, px_h, px_w, rand_0_2, rand_1_2, samples_2, rlp_2, minus_2, plus_2, s_2)
+    nL = len(lights)
+    lidx = np.zeros((P_ * n, K_LIGHT), np.int16)
+    tmp = np.zeros(K_LIGHT, np.int64)
+    for p in range(P_ * n):
+        draw_light_idx(seed_base + p, nL, tmp)
+        lidx[p] = tmp
+    print(f"{name}: {P_} pixels x {n} more samples (+ {4*D} ungated replays each) in {time.time()-t0:.1f}s")
+    np.savez_compressed(os.path.join(OUT, name), samples_2=samples_2, record_log_pdf_2=rlp_2, rlp_minus_2=minus_2, rlp_plus_2=plus_2,
+                        record_s_2=s_2, rand_0_2=rand_0_2, rand_1_2=rand_1_2, pixels=np.array(pixels, np.int32),
+                        light_idx=lidx.reshape(P_, n, K_LIGHT), W=W, H=H, n=n, D=D, camera=camera[:3], f_distance=fdist)
+
+
 def golden_hg():
     """hg_table.npz: the reference's own henyey_greenstein (R/src/medium_samples.py:14-16) on a (g, cos theta) grid"""
     r_ms = importlib.import_module(P + "medium_samples")
@@ -322,6 +380,11 @@ def main():
     only = sys.argv[1] if len(sys.argv) > 1 else None
     if only == "hg":
         golden_hg()
+        return
+    if only == "more":
+        objects, lights, camera, depth = scenes.lts_scene(ref_ns, new_list=numba.typed.List)
+        lin = ref_bvh(objects)
+        golden_more("more_samples_lts_d4.npz", objects, lin, lights, camera, depth, 24, 20, 6, 4, [(5, 7), (10, 3), (19, 23), (12, 12)], 9, 300000)
         return
     if only == "records":
         objects, lights, camera, depth = scenes.lts_scene(ref_ns, new_list=numba.typed.List)
@@ -368,6 +431,7 @@ def main():
     golden_rays("rays_mirror.npz", mobj, mlin, mpacked, mcam, mf, seed=12)
     golden_paths("paths_mirror_ref_d256.npz", mobj, mlin, mlights, mcam, mf, 32, 32, 2, 256, 4, 1, "reference")
     golden_hg()
+    golden_more("more_samples_lts_d4.npz", objects, lin, lights, camera, depth, 24, 20, 6, 4, [(5, 7), (10, 3), (19, 23), (12, 12)], 9, 300000)
 
 
 if __name__ == "__main__":

@@ -89,3 +89,25 @@ def test_records_argument_checks(R_lts):
                light_idx=None)
     with pytest.raises(host.LtError):
         R_lts.render_records(**big)
+
+
+def test_more_samples_block_matches_reference(R_lts):
+    """render_more_samples (R/src/path_tracing.py:310-364) against golden vectors produced by the reference's own trace_path and
+    calculate_gradients: per-sample radiance, the returned record_log_pdf arrays and the 4*D ungated replays of every sample."""
+    import os
+    import light_transport_b200 as lt
+    from light_transport_b200 import api
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "more_samples_lts_d4.npz"))
+    W, H, n, D = int(g["W"]), int(g["H"]), int(g["n"]), int(g["D"])
+    sc = api.Scene(camera=np.append(g["camera"], 1.0), lights=[], width=W, height=H, max_depth=D, f_distance=float(g["f_distance"]),
+                   number_of_samples=1, allocate=False)
+    pixels = [tuple(int(v) for v in p) for p in g["pixels"]]
+    s2, rlp2, m2, p2, ss2 = lt.render_more_samples(sc, None, None, pixels=pixels, n=n, rand0=g["rand_0_2"], rand1=g["rand_1_2"],
+                                                   light_idx=g["light_idx"].astype(np.int32), renderer=R_lts)
+    assert s2.shape == (len(pixels), n, 3) and m2.shape == (len(pixels), n, 2 * D, D)
+    assert np.allclose(s2, g["samples_2"], rtol=1e-9, atol=1e-12)
+    for mine, ref in ((rlp2, g["record_log_pdf_2"]), (m2, g["rlp_minus_2"]), (p2, g["rlp_plus_2"])):
+        assert np.array_equal(mine == 0, ref == 0)
+        assert np.allclose(mine, ref, rtol=1e-9, atol=1e-12)
+    assert np.array_equal(ss2, g["record_s_2"])

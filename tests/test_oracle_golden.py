@@ -120,3 +120,24 @@ def test_records_and_gradients_bit_exact(oracle, name):
                   ("rlp_minus", "rlp_minus"), ("rlp_plus", "rlp_plus"), ("record_s", "record_s")):
         assert np.array_equal(out[k], g[gk]), k
     assert (g["rlp_minus"] != g["rlp_plus"]).any()        # the replays do differ: the fixture exercises them
+
+
+def test_more_samples_block_bit_exact(oracle):
+    """R/src/path_tracing.py:310-364: extra samples at fixed pixels, each with 4*D UNGATED replays whose "logits" are the
+    uniforms themselves (:347) — golden vectors from the reference's own trace_path + calculate_gradients."""
+    from conftest import load_scene
+    g = np.load(os.path.join(GOLDEN, "more_samples_lts_d4.npz"))
+    ps, nodes, _, _ = load_scene("lts_scene.npz")
+    S = oracle.OracleScene(ps, nodes)
+    W, H, n, D = int(g["W"]), int(g["H"]), int(g["n"]), int(g["D"])
+    for k, (i, j) in enumerate(g["pixels"]):
+        pix = int(i) * W + int(j)
+        r0, r1 = g["rand_0_2"][k:k + 1], g["rand_1_2"][k:k + 1]
+        o = oracle.render_records(S, width=W, height=H, spp=n, max_depth=D, camera=g["camera"], f_distance=float(g["f_distance"]), rand0=r0,
+                                  rand1=r1, light_idx=g["light_idx"][k:k + 1].astype(np.int32), gradients=True, pixel_range=(pix, pix + 1),
+                                  ungated=True, logits=(r0, r1))
+        assert np.array_equal(o["samples"][0], g["samples_2"][k])
+        assert np.array_equal(o["record_log_pdf"][0], g["record_log_pdf_2"][k])
+        assert np.array_equal(o["rlp_minus"][0], g["rlp_minus_2"][k]) and np.array_equal(o["rlp_plus"][0], g["rlp_plus_2"][k])
+        assert np.array_equal(o["record_s"][0], g["record_s_2"][k])
+    assert np.abs(g["rlp_minus_2"]).sum() > 0 and not np.array_equal(g["rlp_minus_2"], g["rlp_plus_2"])

@@ -14,7 +14,7 @@ ap.add_argument("--ny", type=int, default=500)
 ap.add_argument("--l2", action="store_true", help="also run the L2 / FP peaks micro-benchmarks")
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--leaf", type=int, default=0)
-ap.add_argument("--l2", action="store_true", dest="l2win")
+ap.add_argument("--l2win", action="store_true")
 ap.add_argument("--trav", default="lbvh2", choices=["lbvh", "lbvh2"])
 a = ap.parse_args()
 import torch

@@ -220,13 +220,13 @@ def peaks(R):
     return _PEAKS
 
 
-def traffic_of(key):
-    """dram bytes of one launch of the dominant kernel from the committed ncu capture of the same command"""
+def traffic_of(key, field="bytes"):
+    """dram bytes of one launch of the dominant kernel (or another field) from the committed ncu capture of the same command"""
     for f in ("r02_traffic.json", "r01_traffic.json"):
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", f)))
-            if key in tj:
-                return tj[key]["bytes"], f
+            if key in tj and field in tj[key]:
+                return tj[key][field], f
         except Exception:
             pass
     return None, None
@@ -256,14 +256,19 @@ def roofline_of(R, wl, traversal, real, counters_sum, kernel_ns, launches, key):
     # hit out.  They are served by L1/L2 (the hierarchy is L2-resident), so the physical bound is the L2 -> SM gather bandwidth
     # measured by lt_measure_l2_bandwidth (one random 64-byte granule per lane); the HBM view uses the real dram bytes of ncu.
     wide = traversal == "lbvh"
-    bytes_all = ((80.0 / 8 if wide else 64.0 / 2) * counters_sum["box_tests"] + (48.0 if wide else 64.0) * counters_sum["tri_tests"] + 48.0 * rays)
-    gbs = bytes_all / (kernel_ns * 1e-9) / 1e9
+    bytes_all = ((80.0 / 8 if wide else 64.0 / 2) * counters_sum["box_tests"] + 48.0 * counters_sum["tri_tests"] + 48.0 * rays)
+    gbs_alg = bytes_all / (kernel_ns * 1e-9) / 1e9
+    # what the L2 really delivered per ray: lts__t_sectors_srcunit_tex_op_read x 32 B of the ncu capture of this kernel on this scene
+    # (profiles/r02_traffic.json), scaled by the live ray rate; without a capture the algorithmic bytes stand in (an upper bound)
+    l2_per_ray, l2src = traffic_of(key, "l2_read_bytes_per_ray")
+    gbs = (l2_per_ray * rays / (kernel_ns * 1e-9) / 1e9) if l2_per_ray else gbs_alg
     out = {"bound": "l2", "achieved": gbs, "peak": pk["l2_gather_gbs"], "unit": "GB/s", "frac": gbs / pk["l2_gather_gbs"],
+           "achieved_source": (f"L2 -> SM sectors per ray measured by ncu (profiles/{l2src}: {l2_per_ray:.0f} B/ray, L1 misses only) x the live ray rate"
+                               if l2_per_ray else "algorithmic bytes (no ncu capture for this variant): an upper bound, L1 hits included"),
            "traffic": traffic, "traffic_unit": fp["traffic_unit"], "kernel": "lt::walk_megakernel", "kernel_ms_per_launch": fp["kernel_ms_per_launch"],
-           "bytes_model": ("80 B x visited 8-wide nodes (= box_tests/8) + 48 B x tri_tests + 48 B x rays" if wide else
-                           "64 B x visited binary nodes (= box_tests/2) + 64 B x tri_tests + 48 B x rays") + " (SURVEY.md 8d); algorithmic bytes, "
-                          "an UPPER bound on what the L2 delivers (L1 hits are included)",
-           "bytes_per_ray": bytes_all / max(rays, 1),
+           "algorithmic": {"bytes_per_ray": bytes_all / max(rays, 1), "gbs": gbs_alg,
+                           "model": ("80 B x visited 8-wide nodes (= box_tests/8)" if wide else "64 B x visited binary nodes (= box_tests/2)")
+                                    + " + 48 B x tri_tests + 48 B x rays (SURVEY.md 8d); served by L1 + L2"},
            "peak_source": "lt_measure_l2_bandwidth in this process: 128-bit ld.global.cg gathers, one random 64-byte granule per lane, 48 MiB buffer "
                           f"(streaming: {pk['l2_stream_gbs']:.0f} GB/s)",
            "hbm": {"peak": pk["hbm_gbs"], "peak_source": pk["hbm_source"], "unit": "GB/s",

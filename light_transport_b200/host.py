@@ -524,7 +524,13 @@ def render_scene(scene, primitives, bvh=None, *, spp=None, rng=None, seed=0, sem
             # the single collective of a pass: lt_film_reduce (ncclReduce on the library's communicator + finalize on the root)
             parallel.reduce_film(film, group, root=None if all_ranks else 0, device=device, spp_total=n_spp)
             if all_ranks or rank == 0:
-                image = film.cpu().numpy().reshape(H, W, 3)
+                si = getattr(scene, "image", None)
+                if (film_blend is None and isinstance(si, np.ndarray) and si.dtype == np.float64 and si.shape == (H, W, 3)
+                        and si.flags.c_contiguous and si.flags.writeable):
+                    torch.from_numpy(si.reshape(-1)).copy_(film)          # one D2H, straight into scene.image (403 MB at 4096^2)
+                    image = si
+                else:
+                    image = film.cpu().numpy().reshape(H, W, 3)
     finally:
         r.close()
     if image is not None and film_blend is not None:

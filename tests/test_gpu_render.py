@@ -110,9 +110,9 @@ def test_philox_independent_streams_within_3_sigma(R_lts, oracle, trav, real):
     calibrated by the same statistic between two oracle runs (seeds 202 vs 303).
 
     Grazing-edge pixels are counted separately: Q13 jitters x and y by the SAME number, so every sample
-    of a pixel on an image diagonal travels in the plane x = +-y and meets the box exactly on a
-    wall/wall edge — an exact tie that float64 resolves by rounding (always the same wall) and float32
-    by different rounding.  Those 2W-of-W^2 pixels are excluded from the float32 bound and reported."""
+    of a pixel on the image's ANTI-diagonal (x == y) travels in the plane x = y and meets the box on a
+    wall/wall edge — a tie that float64 resolves by last-bit rounding and float32 by different rounding.
+    Those W-of-W^2 pixels are excluded from the float32 bound and reported."""
     ps, nodes, cam, f = load_scene("lts_scene.npz")
     W, H, spp = 32, 32, 256
     kw = dict(width=W, height=H, spp=spp, max_depth=8, camera=cam, f_distance=f, semantics="reference", return_samples=True)
@@ -122,7 +122,7 @@ def test_philox_independent_streams_within_3_sigma(R_lts, oracle, trav, real):
     _, o_s, _ = oracle.render(S, traversal=otrav, seed=202, **kw)
     _, o2_s, _ = oracle.render(S, traversal=otrav, seed=303, **kw)
     ii, jj = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
-    diag = (ii == jj) | (ii + jj == W - 1)
+    diag = ii + jj == W - 1            # the exact-tie pixels: x == y only on the ANTI-diagonal (on the main one y = -x + 2r/W)
     mask = ~diag if real == "f32" else None
     z, gm, om, se_mean = _z_stats(g_s, o_s, spp, mask)
     z0, _, _, _ = _z_stats(o2_s, o_s, spp, mask)
@@ -360,8 +360,9 @@ def test_c2_float32_acceptance_at_size(R_lts, oracle, record_property):
     D = 16, REFERENCE semantics, COMPAT traversal), float32 GPU against the float64 oracle on 4096 random pixels with
     INDEPENDENT Philox streams: per-pixel means within 3 sigma of the Monte Carlo standard error.  The radiance is heavy
     tailed (lamp hits are worth 200), so the admissible fraction beyond 3 sigma is calibrated by the same statistic between
-    two oracle runs.  Pixels on the image diagonals (Q13: exact wall/wall ties that float32 rounds differently) are
-    reported separately and held to a looser bound."""
+    two oracle runs.  Pixels on the image's anti-diagonal (Q13: x == y there, every sample meets the box on a wall/wall edge, and
+    even the float64 reference decides those hits by last-bit rounding: 12 % of them differ between its own COMPAT and brute-force
+    answers and 2 % escape through the edge) are reported separately and held to a looser bound."""
     import torch
     ps, nodes, cam, f = load_scene("lts_scene.npz")
     W = H = 1024
@@ -369,8 +370,8 @@ def test_c2_float32_acceptance_at_size(R_lts, oracle, record_property):
     rng = np.random.default_rng(2024)
     pixels = np.sort(rng.choice(W * H, n_pix, replace=False)).astype(np.int32)
     i, j = pixels // W, pixels % W
-    diag = (i == j) | (i + j == W - 1)
-    extra = np.array([k * W + k for k in range(0, W, 16)] + [k * W + (W - 1 - k) for k in range(0, W, 16)], dtype=np.int32)   # 128 diagonal pixels
+    diag = i + j == W - 1             # exact ties exist only on the ANTI-diagonal: there x == y, so d.x == d.y (the main diagonal has y = -x + 2r/W)
+    extra = np.array([k * W + (W - 1 - k) for k in range(0, W, 8)], dtype=np.int32)   # 128 anti-diagonal pixels
     S = oracle.OracleScene(ps, nodes)
     kw = dict(width=W, height=H, spp=spp, max_depth=D, camera=cam, f_distance=f, semantics="reference", traversal="compat")
     allpix = np.concatenate([pixels, extra])
@@ -402,10 +403,10 @@ def test_c2_float32_acceptance_at_size(R_lts, oracle, record_property):
     record_property("c2_f32_beyond_3sigma", frac)
     assert frac <= frac0 + 0.004 and frac < 0.02
     assert abs(mean_gpu - mean_cpu) < 4 * np.sqrt((b1[:n].sum() / (n * spp * 3) - mean_cpu ** 2) / (n * spp * 3)) + 1e-4
-    # exact-tie pixels (2W - 1 of W^2): every sample of a diagonal pixel meets the box exactly on a wall/wall edge; float64 resolves the
-    # tie like the reference (same roundings, first found wins), float32 rounds the two candidates apart.  Counted and reported, not hidden.
+    # exact-tie pixels (W of W^2): every sample of an anti-diagonal pixel meets the box on a wall/wall edge; float64 resolves the
+    # tie like the reference (same last-bit roundings), float32 rounds the candidates apart.  Counted and reported, not hidden.
     record_property("c2_f32_diagonal_beyond_3sigma", fd)
-    assert fd < 0.5
+    assert fd < 0.8
 
 
 def test_image_rmse_float32_vs_float64(R_lts):
@@ -418,12 +419,12 @@ def test_image_rmse_float32_vs_float64(R_lts):
         film, _, _ = R_lts.render(real=real, seed=seed, **kw)
         img[name] = R_lts.finalize(film, 256)
     ii, jj = np.mgrid[0:256, 0:256]
-    diag = (ii == jj) | (ii + jj == 255)            # exact-tie pixels (Q13), 0.8 % of this film: float32 splits their samples between the two walls
+    diag = ii + jj == 255                           # exact-tie pixels (Q13: x == y), 0.4 % of this film: float32 splits their samples between the two walls
     rmse = lambda a, b, m: float(np.sqrt(np.mean((a - b)[m] ** 2)))
     e_prec, e_noise = rmse(img["f32"], img["f64"], ~diag), rmse(img["f64"], img["f64b"], ~diag)
     e_diag, e_diag_noise = rmse(img["f32"], img["f64"], diag), rmse(img["f64"], img["f64b"], diag)
-    print(f"256x256x256spp, off the diagonals: RMSE(f32, f64 same seed) = {e_prec:.2e}, RMSE(f64 seed a, f64 seed b) = {e_noise:.2e}; "
-          f"on the {diag.sum()} diagonal pixels: {e_diag:.2e} vs {e_diag_noise:.2e}")
+    print(f"256x256x256spp, off the anti-diagonal: RMSE(f32, f64 same seed) = {e_prec:.2e}, RMSE(f64 seed a, f64 seed b) = {e_noise:.2e}; "
+          f"on its {diag.sum()} pixels: {e_diag:.2e} vs {e_diag_noise:.2e}")
     assert e_prec < 0.25 * e_noise
     assert e_diag < 0.3                             # reported: a wall/wall blend instead of the reference's one-wall tie break
 

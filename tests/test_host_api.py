@@ -132,3 +132,31 @@ def test_load_obj(tmp_path):
     with pytest.raises(ValueError):
         (tmp_path / "empty.obj").write_text("v 0 0 0\n")
         lt.load_obj(str(tmp_path / "empty.obj"))
+
+
+def test_film_reduce_rejects_bad_arguments_without_a_gpu():
+    """The collective's entry points validate before they touch CUDA or NCCL: null handles come back as LT_E_INVALID."""
+    import ctypes as C
+    from light_transport_b200 import host
+    L = host.lib()
+    for name in ("lt_comm_unique_id", "lt_comm_init", "lt_film_reduce", "lt_nccl_version"):
+        getattr(L, name).restype = C.c_int
+    assert L.lt_film_reduce(None, None, None, C.c_int64(0), C.c_int(0), C.c_int64(0)) == -1
+    assert L.lt_comm_init(None, C.c_int(2), C.c_int(0), None, None) == -1
+    assert L.lt_comm_unique_id(None) == -1
+    assert b"lt_" in L.lt_last_error() or len(L.lt_last_error()) > 0
+
+
+def test_renderer_close_is_idempotent_and_safe_after_context_loss():
+    """a Renderer that outlives its context must not touch freed memory; close() twice is fine (no GPU needed:
+    exercised on a stand-in object that skips __init__)."""
+    import ctypes as C
+    from light_transport_b200 import host
+    r = host.Renderer.__new__(host.Renderer)
+    r._device, r._ctx, r._scene, r._stream = 0, C.c_void_p(1234), C.c_void_p(5678), None      # a context that is NOT in the cache = gone
+    assert r._ctx_gone()
+    r.close()                       # must not call into the library with the dangling handles
+    assert not r._scene
+    r.close()
+    with pytest.raises(host.LtError):
+        r._bind()

@@ -141,3 +141,17 @@ def test_more_samples_block_bit_exact(oracle):
         assert np.array_equal(o["rlp_minus"][0], g["rlp_minus_2"][k]) and np.array_equal(o["rlp_plus"][0], g["rlp_plus_2"][k])
         assert np.array_equal(o["record_s"][0], g["record_s_2"][k])
     assert np.abs(g["rlp_minus_2"]).sum() > 0 and not np.array_equal(g["rlp_minus_2"], g["rlp_plus_2"])
+
+
+def test_render_pixels_equals_render_on_a_subset(oracle):
+    """lto_render_pixels (per-pixel sums and sums of squares for single pixels of a big film) == lto_render on those pixels."""
+    from conftest import load_scene
+    ps, nodes, cam, f = load_scene("lts_scene.npz")
+    S = oracle.OracleScene(ps, nodes)
+    kw = dict(width=40, height=28, spp=6, max_depth=8, camera=cam, f_distance=f, seed=4)
+    px = np.array([5 * 40 + 7, 100, 1119, 0], np.int32)
+    a, b, c = oracle.render_pixels(S, px, **kw)
+    film, samples, _ = oracle.render(S, return_samples=True, **kw)
+    sub = samples.reshape(-1, 6, 3)[px]
+    assert np.allclose(a, sub.sum(1), rtol=1e-14, atol=1e-14) and np.allclose(b, (sub ** 2).sum(1), rtol=1e-14, atol=1e-14)
+    assert c["paths"] == len(px) * 6

@@ -152,6 +152,12 @@ int lt_intersect(lt_scene *, int traversal, int real, const double *o, const dou
 int lt_render(lt_scene *, const lt_render_params *, const double *rand0, const double *rand1,
               const int32_t *light_idx, double *film_sum, double *samples_out, lt_counters *c);
 
+/* Page-lock a caller-owned host array (cudaHostRegister) so that read-backs into it (lt_render_image's image_out) are one
+ * DMA instead of a DMA into the library's staging buffer plus a host copy.  The reference hands scene.image back from every
+ * render_scene call (R/src/path_tracing_old.py:171); the host side registers that array once.  Unregister before freeing it. */
+int lt_host_register(lt_ctx *, void *ptr, size_t bytes);
+int lt_host_unregister(lt_ctx *, void *ptr);
+
 /* lt_render + lt_film_finalize in one call with the film kept on the device: renders samples
  * [s0,s1), writes image_out[H][W][3] = clip(film / (s1-s0), 0, 1) (host or device pointer).  This is
  * the whole of the reference's render_scene for one GPU: scene in (lt_scene_create), image out. */

@@ -55,6 +55,13 @@ static bool is_device_ptr(const void* p) {
     return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
+static bool is_pinned_host_ptr(const void* p) {        // cudaHostAlloc'ed or lt_host_register'ed: the DMA engine can write it directly
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
 template <typename T>
 struct InBuf {   // read-only input
     const T* dev = nullptr;
@@ -273,10 +280,11 @@ static size_t staged_bytes(const lt_scene* s, int trav, int real) {
     if (trav == LT_TRAV_LBVH2) return 0;
     size_t b = al(tri * s->n_tris) + al(mat * s->n_mats);
     if (trav == LT_TRAV_COMPAT) b += al(nod * s->n_cnodes) + al(lef * s->n_cleaves);
-    if (trav == LT_TRAV_COMPAT && r == 4) b += al((size_t)((s->n_cleaves + 1) / 2) * 96) + (8 * 4 * 12 * 4 + 32);   // slab_pairs_bytes + LT_CHAIN_BYTES
+    if (trav == LT_TRAV_COMPAT) b += al((size_t)((s->n_cleaves + 1) / 2) * 96 + 16);          // slab_pairs_bytes (float64: the filter)
+    if (trav == LT_TRAV_COMPAT && r == 4) b += 8 * 4 * 12 * 4 + 32;                           // LT_CHAIN_BYTES
     if (trav == LT_TRAV_COMPAT) b += 32;                                                     // flattened primitive table
     if (trav == LT_TRAV_NEAREST && s->n_nleaves > 0)                                          // per-triangle bounds + the same tables
-        b += al(lef * s->n_nleaves) + (r == 4 ? al((size_t)((s->n_nleaves + 1) / 2) * 96) : 0) + 32;
+        b += al(lef * s->n_nleaves) + al((size_t)((s->n_nleaves + 1) / 2) * 96 + 16) + 32;
     return b;
 }
 
@@ -284,9 +292,9 @@ static int check_traversal(const lt_scene* s, int trav) {
     if (trav == LT_TRAV_COMPAT) {
         if (s->n_cnodes == 0) { set_error("COMPAT traversal needs lt_scene_set_compat_bvh"); return LT_E_NO_BVH; }
     } else if (trav == LT_TRAV_LBVH) {
-        if (!s->wtris) { set_error("LBVH traversal needs lt_bvh_build"); return LT_E_NO_BVH; }
+        if (!s->wtris || !s->wleaf_prims || (!s->wnodes && s->n_tris > 1)) { set_error("LBVH traversal needs (a successful) lt_bvh_build"); return LT_E_NO_BVH; }
     } else if (trav == LT_TRAV_LBVH2) {
-        if (!s->lbvh_nodes && s->n_tris > 1) { set_error("LBVH2 traversal needs lt_bvh_build with LT_BVH_KEEP_BINARY"); return LT_E_NO_BVH; }
+        if (!s->wtris || !s->wleaf_prims || (!s->lbvh_nodes && s->n_tris > 1)) { set_error("LBVH2 traversal needs lt_bvh_build with LT_BVH_KEEP_BINARY"); return LT_E_NO_BVH; }
     } else if (trav != LT_TRAV_NEAREST) {
         set_error("unknown traversal %d", trav);
         return LT_E_INVALID;
@@ -831,6 +839,20 @@ int lt_render(lt_scene* s, const lt_render_params* p, const double* rand0, const
     return LT_E_INVALID;
 }
 
+int lt_host_register(lt_ctx* ctx, void* ptr, size_t bytes) {
+    if (!ctx || !ptr || bytes == 0) { set_error("lt_host_register: null argument"); return LT_E_INVALID; }
+    LT_CUDA_OK(cudaSetDevice(ctx->device));
+    LT_CUDA_OK(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+    return LT_OK;
+}
+
+int lt_host_unregister(lt_ctx* ctx, void* ptr) {
+    if (!ctx || !ptr) { set_error("lt_host_unregister: null argument"); return LT_E_INVALID; }
+    LT_CUDA_OK(cudaSetDevice(ctx->device));
+    LT_CUDA_OK(cudaHostUnregister(ptr));
+    return LT_OK;
+}
+
 int lt_render_image(lt_scene* s, const lt_render_params* p, const double* rand0, const double* rand1, const int32_t* light_idx,
                     double* image_out, double* samples_out, lt_counters* c) {
     if (!s || !p || !image_out) { set_error("lt_render_image: null argument"); return LT_E_INVALID; }
@@ -856,13 +878,15 @@ int lt_render_image(lt_scene* s, const lt_render_params* p, const double* rand0,
     if (!dev_out) {
         // D2H through the context's pinned staging buffer (full-rate DMA), then one host copy into the caller's pageable array
         const size_t bytes = n * sizeof(double);
-        if (bytes > ctx->pinned_bytes) {
+        // (a caller whose array is page-locked — lt_host_register — gets the DMA straight into it)
+        const bool direct = is_pinned_host_ptr(image_out);
+        if (!direct && bytes > ctx->pinned_bytes) {
             if (ctx->pinned) cudaFreeHost(ctx->pinned);
             ctx->pinned = nullptr; ctx->pinned_bytes = 0;
             if (cudaHostAlloc(&ctx->pinned, bytes, cudaHostAllocDefault) == cudaSuccess) ctx->pinned_bytes = bytes;
             else cudaGetLastError();                                    // no pinned memory to be had: copy straight into the caller's array
         }
-        void* dst_h = ctx->pinned_bytes >= bytes ? ctx->pinned : (void*)image_out;
+        void* dst_h = (!direct && ctx->pinned_bytes >= bytes) ? ctx->pinned : (void*)image_out;
         LT_CUDA_OK(cudaMemcpyAsync(dst_h, ctx->film, bytes, cudaMemcpyDeviceToHost, ctx->stream));
         LT_CUDA_OK(cudaStreamSynchronize(ctx->stream));
         if (dst_h != (void*)image_out) memcpy(image_out, dst_h, bytes);

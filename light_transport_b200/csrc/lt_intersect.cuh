@@ -109,17 +109,27 @@ LT_DEVINL bool slab(const float* bmin, const float* bmax, V3<float> o, V3<float>
 #endif
 #define LT_PRAGMA_(x) _Pragma(#x)
 #define LT_PRAGMA_UNROLL(n) LT_PRAGMA_(unroll n)
-LT_DEVINL int slab_pairs_bytes(int n_leaves) { return ((n_leaves + 1) >> 1) * LT_SLAB_PAIR_FLOATS * 4; }
+LT_DEVINL int slab_pairs_bytes(int n_leaves) { return ((n_leaves + 1) >> 1) * LT_SLAB_PAIR_FLOATS * 4 + 16; }
 
-LT_DEVINL void build_slab_pairs(float* tab, const CompatLeaf<float>* leaves, int n_leaves) {
+// Built by one WARP-ALIGNED group of threads of the CTA (all of them call it).  The float trailing the pairs holds the largest
+// |coordinate| of any leaf box: the float64 filter's error bound needs it (slab_pairs_filter).
+template <typename R>
+LT_DEVINL void build_slab_pairs(float* tab, const CompatLeaf<R>* leaves, int n_leaves) {
     const int n_pairs = (n_leaves + 1) >> 1;
     for (int i = threadIdx.x; i < n_pairs * 3; i += blockDim.x) {
         const int p = i / 3, k = i - 3 * p;
-        const CompatLeaf<float>& a = leaves[2 * p];
-        const CompatLeaf<float>& b = leaves[min(2 * p + 1, n_leaves - 1)];     // odd count: the last leaf twice, bit masked off
+        const CompatLeaf<R>& a = leaves[2 * p];
+        const CompatLeaf<R>& b = leaves[min(2 * p + 1, n_leaves - 1)];     // odd count: the last leaf twice, bit masked off
         float* t = tab + LT_SLAB_PAIR_FLOATS * p + 8 * k;
-        t[0] = a.bmin[k]; t[1] = b.bmin[k]; t[2] = a.bmax[k]; t[3] = b.bmax[k];     // direction component >= 0
-        t[4] = a.bmax[k]; t[5] = b.bmax[k]; t[6] = a.bmin[k]; t[7] = b.bmin[k];     // direction component < 0
+        const float an = (float)a.bmin[k], bn = (float)b.bmin[k], ax = (float)a.bmax[k], bx = (float)b.bmax[k];
+        t[0] = an; t[1] = bn; t[2] = ax; t[3] = bx;     // direction component >= 0
+        t[4] = ax; t[5] = bx; t[6] = an; t[7] = bn;     // direction component < 0
+    }
+    if (threadIdx.x == 0) {
+        float m = 0.0f;
+        for (int li = 0; li < n_leaves; ++li)
+            for (int k = 0; k < 3; ++k) m = fmaxf(m, fmaxf(fabsf((float)leaves[li].bmin[k]), fabsf((float)leaves[li].bmax[k])));
+        tab[LT_SLAB_PAIR_FLOATS * n_pairs] = m;
     }
 }
 
@@ -169,6 +179,63 @@ LT_PRAGMA_UNROLL(LT_SLAB_UNROLL)
     return n_leaves >= 64 ? hm : hm & ((1ull << n_leaves) - 1ull);
 }
 
+// ---- float64: the same table as a FILTER --------------------------------------------------------------
+// The float64 walk must take exactly the reference's decisions, but most leaf boxes are hit or missed by a wide
+// margin.  So the float64 query first evaluates all leaves in float32 from the table above (13.5 instructions
+// per leaf instead of ~45 float64 ones) and keeps the float32 verdict only where it is PROVABLY the float64
+// one: with b, o, 1/d rounded to float32 and two float32 operations per slab distance, each distance is within
+//     4 * 2^-24 * (|b| + |o_k|) * |1/d_k|
+// of the float64 value (three input roundings + subtract + multiply, |distance| <= (|b|+|o|)|1/d|), max/min are
+// 1-Lipschitz, and the widen factor adds 2^-24 relative.  `margin` = 2^-19 * max_k (B + |o_k|) |1/d_k| with B the
+// largest box coordinate is > 3x the sum of both sides' bounds; |t1 - t0| above it is a sure verdict, anything else
+// (incl. every NaN / infinite case: a zero direction component makes the margin infinite) is re-tested in float64.
+// Flat boxes (walls) that a ray really crosses are always ambiguous — t0 == t1 up to the widen factor — which is
+// 1-2 float64 tests per ray instead of one per leaf.
+LT_DEVINL float filter_margin(const float* tab, int n_leaves, V3<float> o, V3<float> inv) {
+    const float B = tab[LT_SLAB_PAIR_FLOATS * ((n_leaves + 1) >> 1)];
+    return 1.9073486328125e-06f * fmaxf(fmaxf((B + fabsf(o.x)) * fabsf(inv.x), (B + fabsf(o.y)) * fabsf(inv.y)), (B + fabsf(o.z)) * fabsf(inv.z));
+}
+LT_DEVINL void slab_pairs_filter(const float* tab, int n_leaves, V3<float> o, V3<float> inv, float margin, uint64_t& sure_hit, uint64_t& unsure) {
+    const float widen = 1.0f + 2.0f * ((3.0f * 5.9604644775390625e-08f) / (1.0f - 3.0f * 5.9604644775390625e-08f));
+    const int n_pairs = (n_leaves + 1) >> 1;
+    const float4* tx = reinterpret_cast<const float4*>(tab) + (__float_as_uint(inv.x) >> 31);
+    const float4* ty = reinterpret_cast<const float4*>(tab) + 2 + (__float_as_uint(inv.y) >> 31);
+    const float4* tz = reinterpret_cast<const float4*>(tab) + 4 + (__float_as_uint(inv.z) >> 31);
+    const float2 nox = make_float2(-o.x, -o.x), noy = make_float2(-o.y, -o.y), noz = make_float2(-o.z, -o.z);
+    const float2 ivx = make_float2(inv.x, inv.x), ivy = make_float2(inv.y, inv.y), ivz = make_float2(inv.z, inv.z);
+    const float2 w2 = make_float2(widen, widen);
+    uint64_t hs = 0, us = 0;
+    for (int p0 = 0; p0 < n_pairs; p0 += 16) {
+        const int pe = min(n_pairs - p0, 16);
+        uint32_t mh = 0, mu = 0, bit = 1u;
+LT_PRAGMA_UNROLL(LT_SLAB_UNROLL)
+        for (int q = 0; q < pe; ++q) {
+            const int p = p0 + q;
+            const float4 X = tx[6 * p], Y = ty[6 * p], Z = tz[6 * p];
+            const float2 nx = __fmul2_rn(__fadd2_rn(make_float2(X.x, X.y), nox), ivx);
+            const float2 fx = __fmul2_rn(__fadd2_rn(make_float2(X.z, X.w), nox), ivx);
+            const float2 ny = __fmul2_rn(__fadd2_rn(make_float2(Y.x, Y.y), noy), ivy);
+            const float2 fy = __fmul2_rn(__fadd2_rn(make_float2(Y.z, Y.w), noy), ivy);
+            const float2 nz = __fmul2_rn(__fadd2_rn(make_float2(Z.x, Z.y), noz), ivz);
+            const float2 fz = __fmul2_rn(__fadd2_rn(make_float2(Z.z, Z.w), noz), ivz);
+            const float t0a = fmaxf(fmaxf(nx.x, ny.x), fmaxf(nz.x, 0.0f));
+            const float t0b = fmaxf(fmaxf(nx.y, ny.y), fmaxf(nz.y, 0.0f));
+            const float2 t1 = __fmul2_rn(make_float2(fminf(fminf(fx.x, fy.x), fz.x), fminf(fminf(fx.y, fy.y), fz.y)), w2);
+            const float da = t1.x - t0a, db = t1.y - t0b;
+            if (da > margin) mh |= bit;
+            if (!(fabsf(da) > margin)) mu |= bit;
+            if (db > margin) mh |= bit << 1;
+            if (!(fabsf(db) > margin)) mu |= bit << 1;
+            bit <<= 2;
+        }
+        hs |= (uint64_t)mh << (2 * p0);
+        us |= (uint64_t)mu << (2 * p0);
+    }
+    const uint64_t all = n_leaves >= 64 ? ~0ull : ((1ull << n_leaves) - 1ull);
+    sure_hit = hs & all;
+    unsure = us & all;
+}
+
 // ---- float32 initial descent without a dependent chain ---------------------------------------------------
 // intersect_bvh's initial descent follows the NEAR child while interior bounds are hit, and "near" is decided by
 // the sign of the direction component on the node's split axis — so the chain of nodes a ray can visit is a
@@ -188,7 +255,8 @@ struct ChainTab {
     const uint16_t* meta = nullptr;   // [octant] interior nodes on the chain | leaf list position << 8; 0xffff = generic descent
 };
 
-LT_DEVINL void build_chains(float* tab, uint16_t* meta, const CompatNode<float>* nodes) {
+template <typename R>
+LT_DEVINL void build_chains(float* tab, uint16_t* meta, const CompatNode<R>* nodes) {
     if (threadIdx.x < 8) {
         const int oct = threadIdx.x;
         float* t = tab + oct * LT_CHAIN_PAIRS * 12;
@@ -200,8 +268,8 @@ LT_DEVINL void build_chains(float* tab, uint16_t* meta, const CompatNode<float>*
                 for (int k = 0; k < 3; ++k) {
                     const bool neg = (oct >> k) & 1;
                     float* b = t + (s2 >> 1) * 12 + k * 4 + (s2 & 1);
-                    b[0] = neg ? nodes[cur].bmax[k] : nodes[cur].bmin[k];
-                    b[2] = neg ? nodes[cur].bmin[k] : nodes[cur].bmax[k];
+                    b[0] = (float)(neg ? nodes[cur].bmax[k] : nodes[cur].bmin[k]);
+                    b[2] = (float)(neg ? nodes[cur].bmin[k] : nodes[cur].bmax[k]);
                 }
             cur = ((oct >> nodes[cur].axis) & 1) ? nodes[cur].second : cur + 1;
             ++j;
@@ -283,8 +351,8 @@ LT_DEVINL void compat_query(unsigned amask, const CompatNode<R>* nodes, const Co
     bool done = !live, descending = live && descent;     // a lane without a query of its own only helps with the pooled triangle tests;
                                                          // descent == false: NEAREST over per-triangle bounds (no tree, no kills)
     int chain_leaf = -1;
+    const V3<float> of = mk<float>((float)o.x, (float)o.y, (float)o.z), invf = mk<float>((float)inv.x, (float)inv.y, (float)inv.z);
     if (sizeof(R) == 4 && chain.tab && live) {            // float32: the descent as one branch-free chain evaluation
-        const V3<float> of = mk<float>((float)o.x, (float)o.y, (float)o.z), invf = mk<float>((float)inv.x, (float)inv.y, (float)inv.z);
         const unsigned oct = (__float_as_uint(invf.x) >> 31) | ((__float_as_uint(invf.y) >> 31) << 1) | ((__float_as_uint(invf.z) >> 31) << 2);
         const unsigned meta = chain.meta[oct];
         if (meta != 0xffffu) {
@@ -318,17 +386,18 @@ LT_DEVINL void compat_query(unsigned amask, const CompatNode<R>* nodes, const Co
     uint64_t hm = 0;
     if (!done) {
         if (sizeof(R) == 4 && slabtab) {            // float32: paired, sign-selected table (see slab_pairs_mask)
-            hm = slab_pairs_mask(slabtab, n_leaves, mk<float>((float)o.x, (float)o.y, (float)o.z), mk<float>((float)inv.x, (float)inv.y, (float)inv.z),
-                                 mk<float>((float)sh.x, (float)sh.y, (float)sh.z));
-        } else if (n_leaves <= 32) {                // 32-bit mask arithmetic
-            uint32_t m = 0;
-#pragma unroll 4
-            for (int li = 0; li < n_leaves; ++li) {
+            hm = slab_pairs_mask(slabtab, n_leaves, of, invf, mk<float>((float)sh.x, (float)sh.y, (float)sh.z));
+        } else if (sizeof(R) == 8 && slabtab) {     // float64: float32 filter, float64 only for the leaves it cannot decide
+            uint64_t unsure;
+            slab_pairs_filter(slabtab, n_leaves, of, invf, filter_margin(slabtab, n_leaves, of, invf), hm, unsure);
+            while (unsure) {
+                const int li = __ffsll((long long)unsure) - 1;
+                unsure &= unsure - 1;
                 const CompatLeaf<R>& lf = leaves[li];
-                m |= (uint32_t)slab(lf.bmin, lf.bmax, o, inv, sh) << li;
+                hm |= (uint64_t)slab(lf.bmin, lf.bmax, o, inv, sh) << li;
             }
-            hm = m;
-        } else {
+        } else {                                    // no table (the record kernel)
+#pragma unroll 1
             for (int li = 0; li < n_leaves; ++li) {
                 const CompatLeaf<R>& lf = leaves[li];
                 hm |= (uint64_t)slab(lf.bmin, lf.bmax, o, inv, sh) << li;

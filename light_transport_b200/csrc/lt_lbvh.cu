@@ -547,8 +547,16 @@ static void free_hierarchy(lt_scene* s) {
     s->n_lbvh_nodes = 0; s->n_wnodes = 0; s->wbvh_depth = 0; s->lbvh2_depth = 0;
 }
 
+static int bvh_build_body(lt_scene* s, int flags, lt_bvh_stats* out);
+
 extern "C" int lt_bvh_build(lt_scene* s, int flags, lt_bvh_stats* out) {
     if (!s) { set_error("lt_bvh_build: null scene"); return LT_E_INVALID; }
+    const int rc = bvh_build_body(s, flags, out);
+    if (rc != LT_OK) free_hierarchy(s);          // never leave half a hierarchy behind (the traversals check for its parts)
+    return rc;
+}
+
+static int bvh_build_body(lt_scene* s, int flags, lt_bvh_stats* out) {
     lt_ctx* ctx = s->ctx;
     LT_CUDA_OK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;

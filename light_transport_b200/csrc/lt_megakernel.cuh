@@ -78,11 +78,13 @@ LT_DEVINL void flush_film_warp(double* film, int32_t pix, double acc[3]) {
 #define LT_MIN_BLOCKS_F32_LBVH2 8         // binary tree, memory-latency bound: C3 probe 5: 2.29, 6: 2.53, 7: 2.64, 8: 2.74, 10: 2.73, 12: 2.72 Grays/s
 #endif
 #ifndef LT_MIN_BLOCKS_F64
-#define LT_MIN_BLOCKS_F64 3
+#define LT_MIN_BLOCKS_F64 4          // C2 float64, resident CTAs 2: 4.96, 3: 6.23, 4: 6.52, 5: 6.25, 6: 6.08 Grays/s (before the float32 leaf filter)
 #endif
 // COMPAT: triangle tests of a warp pooled across its lanes (lt_intersect.cuh).  Measured on C2: float64 5.36 -> 6.03
 // Grays/s (the test is expensive at the fp64 rate, balancing pays), float32 18.0 -> 16.9 (list + scan + two warp
-// syncs cost more than the idle lanes they fill): on for float64 only.
+// syncs cost more than the idle lanes they fill): on for float64 only.  Round 2, float32 again (C2, base 20.0): the pool for
+// every test 17.9; two tests per lane in place and the pool only for the tail 18.2; skipping a round's second test when no
+// lane has one (a vote) 19.85.  The tail is 3.3 rounds deep but cheaper than any scheme that balances it.
 #ifndef LT_POOLED
 #define LT_POOLED (sizeof(R) == 8)
 #endif
@@ -121,29 +123,25 @@ walk_megakernel(const WalkParams<R> P) {
         __syncthreads();
         if (TRAV == LT_TRAV_NEAREST && P.S.n_nleaves > 0) {
             // small scene: the all-primitive scan culls with per-triangle bounds through COMPAT's machinery (no descent, no kills)
-            if (sizeof(R) == 4) {
-                build_slab_pairs(reinterpret_cast<float*>(cur), reinterpret_cast<const CompatLeaf<float>*>(cleaves), P.S.n_nleaves);
-                slabtab = reinterpret_cast<const float*>(cur);
-                cur += (slab_pairs_bytes(P.S.n_nleaves) + 15) / 16 * 16;
-            }
+            build_slab_pairs(reinterpret_cast<float*>(cur), cleaves, P.S.n_nleaves);      // float64 uses it as a filter
+            slabtab = reinterpret_cast<const float*>(cur);
+            cur += (slab_pairs_bytes(P.S.n_nleaves) + 15) / 16 * 16;
             build_flat_prims<R>(reinterpret_cast<uint8_t*>(cur), cleaves, P.S.n_nleaves);
             flatprim = reinterpret_cast<const uint8_t*>(cur);
             __syncthreads();
         }
         if (TRAV == LT_TRAV_COMPAT) {
-            if (sizeof(R) == 4) {                           // float32: leaf bounds re-laid for slab_pairs_mask
-                build_slab_pairs(reinterpret_cast<float*>(cur), reinterpret_cast<const CompatLeaf<float>*>(cleaves), P.S.n_cleaves);
-                slabtab = reinterpret_cast<const float*>(cur);
-                cur += (slab_pairs_bytes(P.S.n_cleaves) + 15) / 16 * 16;
-            }
+            // leaf bounds re-laid for slab_pairs_mask (float32) / slab_pairs_filter (float64)
+            build_slab_pairs(reinterpret_cast<float*>(cur), cleaves, P.S.n_cleaves);
+            slabtab = reinterpret_cast<const float*>(cur);
+            cur += (slab_pairs_bytes(P.S.n_cleaves) + 15) / 16 * 16;
             if (compat_small(P.S.n_cleaves, P.S.n_cflat, P.S.n_tris)) {
                 build_flat_prims<R>(reinterpret_cast<uint8_t*>(cur), cleaves, P.S.n_cleaves);
                 flatprim = reinterpret_cast<const uint8_t*>(cur);
             }
             cur += 32;
-            if (sizeof(R) == 4) {                           // float32: per-octant descent chains
-                build_chains(reinterpret_cast<float*>(cur), reinterpret_cast<uint16_t*>(cur + LT_CHAIN_FLOATS * 4),
-                             reinterpret_cast<const CompatNode<float>*>(cnodes));
+            if (sizeof(R) == 4) {                           // float32: per-octant descent chains (as a float64 filter: measured, no gain)
+                build_chains(reinterpret_cast<float*>(cur), reinterpret_cast<uint16_t*>(cur + LT_CHAIN_FLOATS * 4), cnodes);
                 chain.tab = reinterpret_cast<const float*>(cur);
                 chain.meta = reinterpret_cast<const uint16_t*>(cur + LT_CHAIN_FLOATS * 4);
             }
@@ -428,11 +426,11 @@ __global__ void __launch_bounds__(LT_BLOCK) intersect_kernel(const IntersectPara
             build_flat_prims<R>(reinterpret_cast<uint8_t*>(smem), P.S.cleaves, P.S.n_cleaves);
             flatprim = reinterpret_cast<const uint8_t*>(smem);
         }
+        build_slab_pairs(reinterpret_cast<float*>(smem + 32), P.S.cleaves, P.S.n_cleaves);
+        slabtab = reinterpret_cast<const float*>(smem + 32);
         if (sizeof(R) == 4) {
-            build_slab_pairs(reinterpret_cast<float*>(smem + 32), reinterpret_cast<const CompatLeaf<float>*>(P.S.cleaves), P.S.n_cleaves);
-            slabtab = reinterpret_cast<const float*>(smem + 32);
             char* c2 = smem + 32 + (slab_pairs_bytes(P.S.n_cleaves) + 15) / 16 * 16;
-            build_chains(reinterpret_cast<float*>(c2), reinterpret_cast<uint16_t*>(c2 + LT_CHAIN_FLOATS * 4), reinterpret_cast<const CompatNode<float>*>(P.S.cnodes));
+            build_chains(reinterpret_cast<float*>(c2), reinterpret_cast<uint16_t*>(c2 + LT_CHAIN_FLOATS * 4), P.S.cnodes);
             chain.tab = reinterpret_cast<const float*>(c2);
             chain.meta = reinterpret_cast<const uint16_t*>(c2 + LT_CHAIN_FLOATS * 4);
         }

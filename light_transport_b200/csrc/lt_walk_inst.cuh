@@ -142,7 +142,7 @@ int launch_record(const WalkParams<R>& P, const RecParams& RP, int grid, cudaStr
 template <typename R>
 int launch_intersect(const IntersectParams<R>& P, int grid, cudaStream_t stream) {
     switch (P.traversal) {
-        case LT_TRAV_COMPAT: intersect_kernel<R, LT_TRAV_COMPAT><<<grid, LT_BLOCK, 32 + (sizeof(R) == 4 ? (size_t)((((P.S.n_cleaves + 1) >> 1) * LT_SLAB_PAIR_FLOATS * 4 + 15) / 16 * 16 + LT_CHAIN_BYTES) : 0), stream>>>(P); break;
+        case LT_TRAV_COMPAT: intersect_kernel<R, LT_TRAV_COMPAT><<<grid, LT_BLOCK, 32 + (size_t)((((P.S.n_cleaves + 1) >> 1) * LT_SLAB_PAIR_FLOATS * 4 + 16 + 15) / 16 * 16) + (sizeof(R) == 4 ? LT_CHAIN_BYTES : 0), stream>>>(P); break;
         case LT_TRAV_NEAREST: intersect_kernel<R, LT_TRAV_NEAREST><<<grid, LT_BLOCK, 0, stream>>>(P); break;
         case LT_TRAV_LBVH: intersect_kernel<R, LT_TRAV_LBVH><<<grid, LT_BLOCK, 0, stream>>>(P); break;
         case LT_TRAV_LBVH2: intersect_kernel<R, LT_TRAV_LBVH2><<<grid, LT_BLOCK, 0, stream>>>(P); break;

@@ -82,11 +82,9 @@ __global__ void __launch_bounds__(WfCfg<R>::NT, WfCfg<R>::MINB) walk_wavefront(c
     const float* slabtab = nullptr;
     const uint8_t* flatprim = nullptr;
     if (TRAV == LT_TRAV_COMPAT) {
-        if (sizeof(R) == 4) {
-            build_slab_pairs(reinterpret_cast<float*>(cur), reinterpret_cast<const CompatLeaf<float>*>(P.S.cleaves), P.S.n_cleaves);
-            slabtab = reinterpret_cast<const float*>(cur);
-            cur += (slab_pairs_bytes(P.S.n_cleaves) + 15) / 16 * 16;
-        }
+        build_slab_pairs(reinterpret_cast<float*>(cur), P.S.cleaves, P.S.n_cleaves);
+        slabtab = reinterpret_cast<const float*>(cur);
+        cur += (slab_pairs_bytes(P.S.n_cleaves) + 15) / 16 * 16;
         if (compat_small(P.S.n_cleaves, P.S.n_cflat, P.S.n_tris)) {
             build_flat_prims<R>(reinterpret_cast<uint8_t*>(cur), P.S.cleaves, P.S.n_cleaves);
             flatprim = reinterpret_cast<const uint8_t*>(cur);

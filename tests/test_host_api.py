@@ -160,3 +160,25 @@ def test_renderer_close_is_idempotent_and_safe_after_context_loss():
     r.close()
     with pytest.raises(host.LtError):
         r._bind()
+
+
+def test_renderer_cache_key_is_the_content():
+    """the key render_scene() caches uploaded scenes under: equal arrays -> equal key, any changed value or shape -> another"""
+    import copy
+    from light_transport_b200 import host
+    ps, nodes, _, _ = load_scene("lts_scene.npz")
+    k = host._content_key(ps, nodes)
+    assert k is not None and k == host._content_key(copy.deepcopy(ps), copy.deepcopy(nodes))
+    assert k != host._content_key(ps, None)
+    ps2 = copy.deepcopy(ps)
+    ps2.tri_v0[3, 1] += 1e-9
+    assert k != host._content_key(ps2, nodes)
+    n2 = copy.deepcopy(nodes)
+    n2.second[0] += 1
+    assert k != host._content_key(ps, n2)
+    keep = host.RENDERER_CACHE_HASH_BYTES
+    host.RENDERER_CACHE_HASH_BYTES = 64
+    try:
+        assert host._content_key(ps, nodes) is None          # large scenes are keyed by object identity instead
+    finally:
+        host.RENDERER_CACHE_HASH_BYTES = keep

@@ -3,6 +3,10 @@ import sys
 sys.path.insert(0, ".")
 import torch
 from light_transport_b200 import api, host, pack_scene, scenes, compat_bvh
+if "--lib" in sys.argv:
+    k = sys.argv.index("--lib")
+    host.LIB_PATH = sys.argv[k + 1]
+    del sys.argv[k:k + 2]
 objs, lights, cam, depth = scenes.lts_scene(api)
 ps = pack_scene(objs, lights)
 nodes = compat_bvh.build_compat_nodes(ps.tri_v0, ps.tri_v1, ps.tri_v2)
@@ -16,3 +20,4 @@ kw = dict(width=W, height=H, spp=spp, max_depth=16, camera=cam, f_distance=depth
 for _ in range(2):
     c = R.render(**kw)[2]
 print(c)
+print("Grays/s %.3f" % ((c["rays_ext"] + c["rays_shadow"]) / c["kernel_ns"]))

@@ -123,7 +123,8 @@ typedef struct {
     int64_t binary_bytes;        /* LT_BVH_KEEP_BINARY: binary nodes (64 B) + the same triangle records; else 0 */
 } lt_bvh_stats;
 /* lt_bvh_build flags */
-/* bits 8-9: triangles per leaf slot of the wide hierarchy, 1..3 (0 = default 3) */
+/* bits 8-9: triangles per leaf slot of the wide hierarchy, 1..3 (0 = default 3)
+ * bits 10-11: triangles per leaf of the binary tree kept by LT_BVH_KEEP_BINARY, 1..3, capped at the slot size (0 = default) */
 #define LT_BVH_KEEP_BINARY 1     /* also keep the binary (Karras) nodes for LT_TRAV_LBVH2 */
 
 int lt_init(int device, lt_ctx **out);

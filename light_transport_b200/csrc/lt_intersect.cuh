@@ -851,6 +851,15 @@ LT_DEVINL void lbvh2_begin(LbvhState<R>& s, int n_tris, R tlimit, bool live) {
 
 // Runs at most `max_steps` warp-voted steps (every lane of `amask` must call it, finished or idle lanes
 // with cur == LT_LBVH_DONE).  Returns when all lanes are done or the budget is used up.
+#ifndef LT_LDG256
+#define LT_LDG256 1
+#endif
+// one 256-bit read-only load (32-byte aligned address)
+LT_DEVINL void ldg256(const void* p, float4& a, float4& b) {
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+}
+
 template <typename R>
 LT_DEVINL void lbvh2_run(unsigned amask, LbvhState<R>& s, int* stack, int stride, const LbvhNode* __restrict__ nodes,
                          const WTri* __restrict__ wtris, const int32_t* __restrict__ leaf_prims, const TriRec<R>* __restrict__ tris, V3<R> o, V3<R> d,
@@ -858,7 +867,12 @@ LT_DEVINL void lbvh2_run(unsigned amask, LbvhState<R>& s, int* stack, int stride
     // (dropping stale stack entries at pop time — entry distance kept beside the node — was measured:
     //  fewer node visits but 6-9 % slower overall on both the 28- and the 1 M-triangle scene.
     //  prefetch.global.L1 of the children while the slab tests run: both children 3x slower, the chosen
-    //  child 1.4x slower, the pushed far child -1.5 %: the loads are latency-bound but L1 requests are not free.)
+    //  child 1.4x slower, the pushed far child -1.5 %: the loads are latency-bound but L1 requests are not free.
+    //  L1 policies on the loads, C3 probe, base 3235 Mrays/s: triangle records L1::no_allocate 3267 (noise); nodes with few
+    //  triangles below them (64 ... 16 k, a bit in the child reference) L1::no_allocate 1240 — LDG.E.NA.ENL2.256 is slow in
+    //  itself —, L1::evict_first 2820-2920, L1::evict_last 2770-2830, against 2970 for the same predicated pair without a hint.
+    //  The stack: ncu shows 47 % of the local-memory pops missing the L1 and pushes/pops as a third of the L1 sector traffic, yet
+    //  its first 4/8/12/16 entries in shared memory ([level][thread]) give 2950/3010/2990/2985 against 3135 all-local.)
     for (int step = 0; step < max_steps; ++step) {
         const bool at_node = s.cur >= 0, at_leaf = (s.cur < 0) & (s.cur != LT_LBVH_DONE);
         const unsigned nm = __ballot_sync(amask, at_node), lm = __ballot_sync(amask, at_leaf);
@@ -866,8 +880,15 @@ LT_DEVINL void lbvh2_run(unsigned amask, LbvhState<R>& s, int* stack, int stride
         if (__popc(nm) >= __popc(lm)) {
             if (at_node) {
                 const float4* p = reinterpret_cast<const float4*>(nodes + s.cur);
+#if LT_LDG256
+                float4 X, Y, Z, rw;                      // the 64-byte node in two 256-bit loads (sm_100: LDG.E.ENL2.256) instead of four
+                ldg256(p, X, Y);
+                ldg256(p + 2, Z, rw);
+                const int2 r = make_int2(__float_as_int(rw.x), __float_as_int(rw.y));
+#else
                 const float4 X = __ldg(p), Y = __ldg(p + 1), Z = __ldg(p + 2);
                 const int4 r = __ldg(reinterpret_cast<const int4*>(p + 3));
+#endif
                 R t0n, t1n;
                 bool h0, h1;
                 st.box_tests += 2;
@@ -881,7 +902,8 @@ LT_DEVINL void lbvh2_run(unsigned amask, LbvhState<R>& s, int* stack, int stride
                 else s.cur = LT_LBVH_DONE;
             }
         } else if (at_leaf) {
-            const uint32_t ti = (uint32_t)~s.cur;          // position in the leaf-ordered triangle arrays
+            const uint32_t lref = (uint32_t)~s.cur;        // position in the leaf-ordered triangle arrays | (triangles after this one) << 28
+            const uint32_t ti = lref & 0x0fffffffu, more = lref >> 28;
             R t;
             int k;
             st.tri_tests++;
@@ -891,7 +913,9 @@ LT_DEVINL void lbvh2_run(unsigned amask, LbvhState<R>& s, int* stack, int stride
                 s.prim = k;
                 s.leaf = (int)ti;
             }
-            if (s.sp > 0 && !(anyhit && s.prim >= 0)) { s.sp--; s.cur = stack[s.sp * stride]; }
+            if (anyhit && s.prim >= 0) s.cur = LT_LBVH_DONE;
+            else if (more) s.cur = ~(int)((ti + 1u) | ((more - 1u) << 28));
+            else if (s.sp > 0) { s.sp--; s.cur = stack[s.sp * stride]; }
             else s.cur = LT_LBVH_DONE;
         }
     }

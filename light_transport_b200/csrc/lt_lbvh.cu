@@ -282,20 +282,38 @@ __global__ void depth_kernel(int n, const int* __restrict__ parent_internal, con
 
 // ---- 6a. binary traversal nodes (LT_TRAV_LBVH2, flag LT_BVH_KEEP_BINARY) -----------------------------------------------
 // leaf refs point into the LEAF-ordered triangle arrays the collapse has produced (wpos: primitive -> position)
+// The binary tree as traversed (LT_TRAV_LBVH2): only Karras nodes with more than `leaf_max` triangles below them become nodes,
+// renumbered densely (`newidx` = exclusive scan of the used flags: the node array holds nothing that is never fetched);
+// a smaller subtree is ONE leaf reference ~(first position | (count-1) << 28) into the leaf-ordered triangle array, where
+// the 8-wide emit laid its triangles out contiguously (the same subtree is one leaf slot there).
+LT_DEVINL bool binary_used(int i, const int* rng_lo, const int* rng_hi, int leaf_max) { return i == 0 || rng_hi[i] - rng_lo[i] + 1 > leaf_max; }
+
+__global__ void mark_used_kernel(int n, const int* __restrict__ rng_lo, const int* __restrict__ rng_hi, int leaf_max, uint32_t* __restrict__ used) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n - 1) used[i] = binary_used(i, rng_lo, rng_hi, leaf_max) ? 1u : 0u;
+}
+
 __global__ void emit_kernel(const Box* __restrict__ prim_boxes, const uint32_t* __restrict__ sorted_prim, int n, const int* __restrict__ left,
-                            const int* __restrict__ right, const Box* __restrict__ node_boxes, const int32_t* __restrict__ wpos,
+                            const int* __restrict__ right, const int* __restrict__ rng_lo, const int* __restrict__ rng_hi, int leaf_max,
+                            const uint32_t* __restrict__ newidx, const Box* __restrict__ node_boxes, const int32_t* __restrict__ wpos,
                             LbvhNode* __restrict__ out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n - 1) return;
+    if (i >= n - 1 || !binary_used(i, rng_lo, rng_hi, leaf_max)) return;
     int c0 = left[i], c1 = right[i];
     Box b0 = c0 >= 0 ? node_boxes[c0] : prim_boxes[sorted_prim[~c0]];
     Box b1 = c1 >= 0 ? node_boxes[c1] : prim_boxes[sorted_prim[~c1]];
+    auto ref = [&](int c) -> int {
+        if (c < 0) return ~wpos[sorted_prim[~c]];
+        const int cnt = rng_hi[c] - rng_lo[c] + 1;
+        if (cnt > leaf_max) return (int)newidx[c];
+        return ~(wpos[sorted_prim[rng_lo[c]]] | ((cnt - 1) << 28));
+    };
     LbvhNode nd;
     nd.x = make_float4(b0.lo[0], b1.lo[0], b0.hi[0], b1.hi[0]);
     nd.y = make_float4(b0.lo[1], b1.lo[1], b0.hi[1], b1.hi[1]);
     nd.z = make_float4(b0.lo[2], b1.lo[2], b0.hi[2], b1.hi[2]);
-    nd.d = make_int4(c0 >= 0 ? c0 : ~wpos[sorted_prim[~c0]], c1 >= 0 ? c1 : ~wpos[sorted_prim[~c1]], 0, 0);
-    out[i] = nd;
+    nd.d = make_int4(ref(c0), ref(c1), 0, 0);
+    out[newidx[i]] = nd;
 }
 
 // ---- 6b. collapse into the 8-wide hierarchy -----------------------------------------------------------------------
@@ -642,10 +660,21 @@ static int bvh_build_body(lt_scene* s, int flags, lt_bvh_stats* out) {
     }
     const int n_wide = level_start;
     if (tri_cursor != n) { free_hierarchy(s); set_error("wide-BVH collapse placed %d of %d triangles", tri_cursor, n); return LT_E_OVERFLOW; }
+    int n_binary = 0;
     if (flags & LT_BVH_KEEP_BINARY) {
-        LT_CUDA_OK(lt_dev_malloc(&s->lbvh_nodes, (size_t)(n - 1) * sizeof(LbvhNode)));
-        emit_kernel<<<iblocks, LB_THREADS, 0, st>>>(prim_boxes.p, vi, n, left.p, right.p, node_boxes.p, wpos.p, s->lbvh_nodes);
-        s->n_lbvh_nodes = n - 1;
+        if (n >= (1 << 28)) { free_hierarchy(s); set_error("LT_BVH_KEEP_BINARY: at most 2^28 - 1 triangles"); return LT_E_OVERFLOW; }
+        const int bleaf = ((flags >> 10) & 3) ? ((flags >> 10) & 3) : std::min(leaf_max, LT_LBVH2_LEAF_MAX);   // never above the slots' size
+        mark_used_kernel<<<iblocks, LB_THREADS, 0, st>>>(n, rng_lo.p, rng_hi.p, std::min(bleaf, leaf_max), cnt_int.p);
+        LT_CUDA_OK(cudaMemsetAsync(cnt_tri.p, 0, (size_t)(n - 1) * sizeof(uint32_t), st));
+        scan2_kernel<<<1, 1024, 0, st>>>(cnt_int.p, cnt_tri.p, n - 1, totals.p);
+        uint32_t tot[2];
+        LT_CUDA_OK(cudaMemcpyAsync(tot, totals.p, sizeof tot, cudaMemcpyDeviceToHost, st));
+        LT_CUDA_OK(cudaStreamSynchronize(st));
+        n_binary = (int)tot[0];
+        LT_CUDA_OK(lt_dev_malloc(&s->lbvh_nodes, (size_t)n_binary * sizeof(LbvhNode)));
+        emit_kernel<<<iblocks, LB_THREADS, 0, st>>>(prim_boxes.p, vi, n, left.p, right.p, rng_lo.p, rng_hi.p, std::min(bleaf, leaf_max), cnt_int.p,
+                                                    node_boxes.p, wpos.p, s->lbvh_nodes);
+        s->n_lbvh_nodes = n_binary;
     }
     LT_CUDA_OK(lt_dev_malloc(&s->wnodes, (size_t)n_wide * sizeof(WNode)));
     LT_CUDA_OK(cudaMemcpyAsync(s->wnodes, wtmp.p, (size_t)n_wide * sizeof(WNode), cudaMemcpyDeviceToDevice, st));
@@ -672,7 +701,7 @@ static int bvh_build_body(lt_scene* s, int flags, lt_bvh_stats* out) {
     stats.sort_ms = ms_sort;
     stats.collapse_ms = ms_collapse;
     stats.bytes = (int64_t)n_wide * (int64_t)sizeof(WNode) + (int64_t)n * (int64_t)sizeof(WTri);
-    stats.binary_bytes = (flags & LT_BVH_KEEP_BINARY) ? (int64_t)(n - 1) * (int64_t)sizeof(LbvhNode) + (int64_t)n * (int64_t)sizeof(WTri) : 0;
+    stats.binary_bytes = (flags & LT_BVH_KEEP_BINARY) ? (int64_t)n_binary * (int64_t)sizeof(LbvhNode) + (int64_t)n * (int64_t)sizeof(WTri) : 0;
     for (int k = 0; k < 3; ++k) { stats.root_bmin[k] = root.lo[k]; stats.root_bmax[k] = root.hi[k]; }
     const double ra = (double)box_area(root);
     stats.sah_cost = ra > 0 ? cost / ra : 0.0;

@@ -95,6 +95,10 @@ struct alignas(16) WTri {
 };
 static_assert(sizeof(WTri) == 48, "WTri must be three 128-bit words");
 #define LT_WBVH_LEAF_MAX 3        // triangles per leaf slot (unary count in 3 bits)
+#ifndef LT_LBVH2_LEAF_MAX
+#define LT_LBVH2_LEAF_MAX 2       // triangles per leaf of the binary tree (<= the slot size; lt_bvh_build flags bits 10-11 override);
+                                  // C3 probe, 1/2/3: 3050 / 3198 / 3058 Mrays/s, 112 / 85 / 79 MB, 2.24 / 2.45 / 4.16 triangle tests per ray
+#endif
 #define LT_WBVH_MAX_DEPTH 28      // wide levels the traversal stack (shared memory, 8 B per level and lane) can hold
 
 template <typename R>

@@ -212,11 +212,11 @@ class Renderer:
         _check(lib().lt_scene_set_compat_bvh(self._scene, C.byref(d)))
         self.has_compat = True
 
-    def build_lbvh(self, keep_binary=False, leaf_max=0):
+    def build_lbvh(self, keep_binary=False, leaf_max=0, binary_leaf=0):
         """GPU LBVH build (Morton, radix sort, Karras, refit) + collapse into the 8-wide compressed hierarchy."""
         self._bind()
         st = LtBvhStats()
-        _check(lib().lt_bvh_build(self._scene, C.c_int((1 if keep_binary else 0) | ((int(leaf_max) & 3) << 8)), C.byref(st)))
+        _check(lib().lt_bvh_build(self._scene, C.c_int((1 if keep_binary else 0) | ((int(leaf_max) & 3) << 8) | ((int(binary_leaf) & 3) << 10)), C.byref(st)))
         self.lbvh_stats = dict(n_prims=st.n_prims, n_nodes=st.n_nodes, max_depth=st.max_depth, binary_depth=st.binary_depth,
                                build_ms=st.build_ms, sort_ms=st.sort_ms, collapse_ms=st.collapse_ms, sah_cost=st.sah_cost,
                                bytes=st.bytes, binary_bytes=st.binary_bytes, root_bmin=list(st.root_bmin), root_bmax=list(st.root_bmax))

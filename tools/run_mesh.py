@@ -14,6 +14,7 @@ ap.add_argument("--ny", type=int, default=500)
 ap.add_argument("--l2", action="store_true", help="also run the L2 / FP peaks micro-benchmarks")
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--leaf", type=int, default=0)
+ap.add_argument("--bleaf", type=int, default=0, help="triangles per leaf of the binary tree (0 = library default)")
 ap.add_argument("--l2win", action="store_true")
 ap.add_argument("--trav", default="lbvh2", choices=["lbvh", "lbvh2"])
 a = ap.parse_args()
@@ -24,7 +25,7 @@ if a.lib:
 objs, lights, cam, depth = scenes.lts_scene(api)
 ps = from_arrays(scenes.heightfield(nx=a.nx, ny=a.ny), base=pack_scene(objs, lights))
 R = host.Renderer(ps, None)
-print("lbvh:", R.build_lbvh(keep_binary=True, leaf_max=a.leaf))
+print("lbvh:", R.build_lbvh(keep_binary=True, leaf_max=a.leaf, binary_leaf=a.bleaf))
 film = torch.zeros(1080 * 1920 * 3, dtype=torch.float64, device="cuda")
 kw = dict(width=1920, height=1080, spp=a.spp, max_depth=8, camera=cam, f_distance=depth, seed=3, semantics="iterative", traversal=a.trav,
           real="f32", film=film)

@@ -47,6 +47,26 @@ LT_DEVINL bool tri_intersect(const TriRec<R>& T, V3<R> o, V3<R> d, R& t_out) {
     return !miss & (t > eps);
 }
 
+// float32 walk on the shared-memory copy (TriPad, see stage_tris_padded): the same test from the triangle's plane and its
+// dual edge vectors.  With det = d.n, t' = (a - o).n and P' = det (o - a) + t' d (= det x the hit point relative to a):
+// u' = P'.n1 = det u, v' = P'.n2 = det v, so "u >= 0, v >= 0, u + v <= 1" are sign agreements with det (u <= 1 follows) and
+// t = t' / det.  34 instructions instead of 55: no cross products per ray.  A NaN (degenerate triangle) fails every comparison.
+#if LT_TRI_PLANES
+LT_DEVINL bool tri_intersect(const TriPad& T, V3<float> o, V3<float> d, float& t_out) {
+    const float eps = 0.0000001f;
+    const V3<float> tv = mk<float>(o.x - T.v0[0], o.y - T.v0[1], o.z - T.v0[2]);
+    const V3<float> n = mk<float>(T.gn[0], T.gn[1], T.gn[2]);
+    const float det = dot(d, n);
+    const float tp = -dot(tv, n);
+    const V3<float> P = mk<float>(fmaf(det, tv.x, tp * d.x), fmaf(det, tv.y, tp * d.y), fmaf(det, tv.z, tp * d.z));
+    const float u = dot(P, mk<float>(T.n1[0], T.n1[1], T.n1[2])), v = dot(P, mk<float>(T.n2[0], T.n2[1], T.n2[2]));
+    const float w = det - u - v;
+    const float t = tp / det;
+    t_out = t;
+    return (u * det >= 0.0f) & (v * det >= 0.0f) & (w * det >= 0.0f) & (fabsf(det) > T.thr) & (t > eps);
+}
+#endif
+
 // R/src/intersects.py:178-196 intersect_bounds on [0, inf); gamma(3) from float32 epsilon (Q10),
 // evaluated in the working precision like the reference evaluates it in float64.  The reference
 // returns False as soon as t0 > t1; t0 only grows and t1 only shrinks (a NaN candidate never

@@ -21,9 +21,30 @@ namespace lt {
 // float32 triangle records re-laid with an 80-byte stride (TriPad, lt_scene.cuh)
 LT_DEVINL const TriPad* stage_tris_padded(char*& cursor, const TriRec<float>* src, int n) {
     TriPad* dst = reinterpret_cast<TriPad*>(cursor);
+#if LT_TRI_PLANES
+    // once per CTA and triangle, in float64 (layout and meaning: TriPad in lt_scene.cuh)
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const TriRec<float> S = src[i];
+        const double ab[3] = {S.ab[0], S.ab[1], S.ab[2]}, ac[3] = {S.ac[0], S.ac[1], S.ac[2]};
+        const double N[3] = {ab[1] * ac[2] - ab[2] * ac[1], ab[2] * ac[0] - ab[0] * ac[2], ab[0] * ac[1] - ab[1] * ac[0]};
+        const double nn = N[0] * N[0] + N[1] * N[1] + N[2] * N[2], len = sqrt(nn);
+        const double n1[3] = {ac[1] * N[2] - ac[2] * N[1], ac[2] * N[0] - ac[0] * N[2], ac[0] * N[1] - ac[1] * N[0]};
+        const double n2[3] = {N[1] * ab[2] - N[2] * ab[1], N[2] * ab[0] - N[0] * ab[2], N[0] * ab[1] - N[1] * ab[0]};
+        TriPad T;
+        for (int c = 0; c < 3; ++c) {
+            T.v0[c] = S.v0[c]; T.n[c] = S.n[c];
+            T.gn[c] = (float)(N[c] / len); T.n1[c] = (float)(n1[c] / nn); T.n2[c] = (float)(n2[c] / nn);
+        }
+        // R/src/intersects.py:60-66 rejects |d.n| <= eps and |det| < eps with det = -(d.n) |N|: one bound on |d.n|
+        T.thr = (float)fmax(1e-7, 1e-7 / len);
+        T.mat = S.mat; T.is_light = S.is_light; T.pad0 = T.pad1 = 0.0f;
+        dst[i] = T;
+    }
+#else
     const int4* s4 = reinterpret_cast<const int4*>(src);
     int4* d4 = reinterpret_cast<int4*>(dst);
     for (int i = threadIdx.x; i < 4 * n; i += blockDim.x) d4[5 * (i >> 2) + (i & 3)] = __ldg(s4 + i);
+#endif
     cursor += (size_t)n * sizeof(TriPad);
     return dst;
 }

@@ -26,9 +26,28 @@ struct alignas(16) TriRec {
 // collide on 128-bit loads (record stride 16 words: the 16-byte chunk a lane reads falls in bank group (4k + c) mod 8, two
 // groups for a whole quarter-warp; ncu round 1: 23 % of the shared wavefronts were conflict replays).  Stride 20 words puts
 // triangle k's chunk c in group (5k + c) mod 8 - eight distinct groups for k mod 8 distinct.
+#ifndef LT_TRI_PLANES
+#define LT_TRI_PLANES 1
+#endif
+#if LT_TRI_PLANES
+// ... and since the copy is made per CTA anyway it holds the triangle in the form the float32 test wants (tri_intersect(const
+// TriPad&)): the geometric unit normal `gn`, the dual edge vectors n1 = ac x N / |N|^2, n2 = N x ab / |N|^2 (N = ab x ac, so
+// n1.ab = n2.ac = 1 and n1.ac = n2.ab = 0) and the parallel-ray bound `thr`; the test reads the first four 16-byte chunks,
+// shading the last (`n` is the record's own normal, which a mesh may have smoothed).
+struct alignas(16) TriPad {
+    float v0[3], thr;
+    float gn[3];
+    int32_t mat;
+    float n1[3];
+    int32_t is_light;
+    float n2[3], pad0;
+    float n[3], pad1;
+};
+#else
 struct alignas(16) TriPad : TriRec<float> {
     float pad80[4];
 };
+#endif
 static_assert(sizeof(TriPad) == 80, "TriPad must be 80 bytes");
 
 template <typename R>

@@ -54,6 +54,14 @@ template <typename R> LT_DEVINL HitRec<R> hit_record(const TriRec<R>& t) {
     return h;
 }
 
+#if LT_TRI_PLANES
+LT_DEVINL HitRec<float> hit_record(const TriPad& t) {
+    HitRec<float> h;
+    h.n = mk<float>(t.n[0], t.n[1], t.n[2]); h.mat = t.mat; h.is_light = t.is_light; h.valid = true;
+    return h;
+}
+#endif
+
 template <typename R>
 struct Frame {
     R T[3], W[3];

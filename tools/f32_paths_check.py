@@ -4,6 +4,10 @@ sys.path.insert(0, "."); sys.path.insert(0, "tests")
 import numpy as np
 from conftest import load_scene
 from light_transport_b200 import host
+if "--lib" in sys.argv:
+    k = sys.argv.index("--lib")
+    host.LIB_PATH = sys.argv[k + 1]
+    del sys.argv[k:k + 2]
 ps, nodes, cam, f = load_scene("lts_scene.npz")
 R = host.Renderer(ps, nodes, build_lbvh="binary")
 for sem in ("reference", "iterative"):

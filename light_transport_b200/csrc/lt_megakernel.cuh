@@ -98,6 +98,9 @@ LT_DEVINL void flush_film_warp(double* film, int32_t pix, double acc[3]) {
 #ifndef LT_MIN_BLOCKS_F32_LBVH2
 #define LT_MIN_BLOCKS_F32_LBVH2 8         // binary tree, memory-latency bound: C3 probe 5: 2.29, 6: 2.53, 7: 2.64, 8: 2.74, 10: 2.73, 12: 2.72 Grays/s
 #endif
+// (float64: the kernel is 110 KB of SASS and a third of its stall samples are instruction fetch (profiles/r02_walk_compat_f64_*);
+//  moving normalize / slab / tri_intersect out of line (__noinline__, one copy each) made it slower, 6.6 -> 5.6 Grays/s: the
+//  calls' argument traffic and generic loads cost more than the fetch misses they remove.)
 #ifndef LT_MIN_BLOCKS_F64
 #define LT_MIN_BLOCKS_F64 4          // C2 float64, resident CTAs 2: 4.96, 3: 6.23, 4: 6.52, 5: 6.25, 6: 6.08 Grays/s (before the float32 leaf filter)
 #endif

@@ -503,6 +503,25 @@ def sub_record(name, host, local, stream, flush, *, steps, warmup, real="f32", t
     return out
 
 
+def strong_record(host, local, stream, flush, rank, world):
+    """C5 (north_star's scaling config: fixed 4096^2 x 4096 spp job split over the ranks by sample index) as a sub-record of the
+    default line at EVERY N, so that the driver's scaling run records strong scaling too.  Collective: all ranks call it."""
+    wl = CONFIGS["c5"]
+    objs, lights, ps, nodes, cam, depth = scene_arrays(wl["scene"])
+    R = host.Renderer(ps, nodes, device=local)
+    R.set_stream(stream.cuda_stream)
+    kw = dict(width=wl["width"], height=wl["height"], traversal=wl["traversal"], real="f32", scheduler="megakernel", rank=rank, world=world,
+              stream=stream, flush=flush)
+    run_walk("c5", wl, R, ps, nodes, cam, depth, spp=max(64, world), steps=1, warmup=2, **kw)          # warm-up at 1/64 of the job
+    r = run_walk("c5", wl, R, ps, nodes, cam, depth, spp=wl["spp"], steps=1, warmup=0, **kw)
+    R.close()
+    return {"workload": f"C5: {SCENE_DESC[wl['scene']]}, {wl['width']}x{wl['height']}, {wl['spp']} spp IN TOTAL over {world} GPU(s), max depth "
+                        f"{wl['max_depth']}, {wl['semantics']} semantics, {wl['traversal']} traversal, f32; one lt_film_reduce per pass",
+            "value": r["value"], "unit": "Mrays/s", "n_gpus": world, "scaling": "strong", "ms_per_step": r["ms_per_step"], "steps": 1,
+            "warmup": "3 passes at 1/64 of the samples", "dtype": "f32", "mpaths_per_s": r["mpaths_per_s"],
+            "traversed_mrays_per_s": r["traversed_mrays_per_s"], "rays_per_path": r["rays_per_path"]}
+
+
 def main():
     global _REAL_STDOUT
     args = parse()
@@ -544,8 +563,14 @@ def main():
     e2e = run_e2e(WORKLOAD, ps, nodes, lights, cam, depth, width=args.width, height=args.height, spp_total=r["spp_total"], traversal=args.traversal,
                   real=args.real, scheduler=args.scheduler, steps=max(5, args.steps) if r["ms_per_step"] < 2000 else 2, world=world, local=local)
 
+    full = args.size is None and args.spp == CONFIGS[args.config]["spp"]
+    c5_strong = None
+    if args.config == "c2" and not args.no_extra and full:
+        try:                                  # every rank takes part (film reduce); a failure must not cost the headline line
+            c5_strong = strong_record(host, local, stream, flush, rank, world)
+        except Exception as e:                # noqa: BLE001
+            c5_strong = {"error": f"{type(e).__name__}: {e}"}
     if rank == 0:
-        full = args.size is None and args.spp == CONFIGS[args.config]["spp"]
         key = f"{args.config}:{args.traversal}:{args.scheduler}:{args.real}" if full else "-"
         out = {"metric": METRIC, "value": r["value"], "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": WORKLOAD["scaling"], "vs_baseline": None,
@@ -569,6 +594,8 @@ def main():
             out["time_to_rmse"] = time_to_rmse(R, cam, depth, args)
     R.close()
     if rank == 0:
+        if c5_strong is not None:
+            out["configs"] = {"c5_strong": c5_strong}
         if world == 1 and args.config == "c2" and not args.no_extra and full:
             # ---- sub-records: the float64 arm of the headline config and the other BASELINE configs, same process, same clocks
             def guarded(fn):          # a failing sub-record must not cost the headline line
@@ -596,6 +623,7 @@ def main():
                 return rec
 
             extra["c4b"] = guarded(medium_record)
+            extra["c5_strong"] = c5_strong
             out["configs"] = extra
             out["peaks"] = {k: v for k, v in peaks(None).items() if k in ("fp32_tflops", "fp64_tflops", "l2_gather_gbs", "l2_stream_gbs", "hbm_gbs", "hbm_source")}
         emit(out)

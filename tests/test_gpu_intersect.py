@@ -124,6 +124,34 @@ def test_lbvh_mesh_vs_oracle(oracle):
     R.close()
 
 
+@pytest.mark.parametrize("binary_leaf,leaf_max", [(1, 3), (2, 3), (3, 3), (2, 2), (3, 1)])
+def test_binary_tree_leaf_sizes(binary_leaf, leaf_max):
+    """The binary tree kept for `lbvh2` holds only nodes with more than `binary_leaf` triangles below them (densely renumbered)
+    and multi-triangle leaf references (position | count) into the 8-wide hierarchy's leaf order: every leaf size, including
+    the cap at the slot size, gives the all-primitive scan's answer bit for bit — closest hits and any-hit shadow walks."""
+    from light_transport_b200 import host, scenes, _pack
+    base, _, cam, f = load_scene("lts_scene.npz")
+    ps = _pack.from_arrays(scenes.heightfield(nx=60, ny=40), base=base)
+    R = host.Renderer(ps, None)
+    st = R.build_lbvh(keep_binary=True, leaf_max=leaf_max, binary_leaf=binary_leaf)
+    eff = min(binary_leaf, leaf_max)
+    n_nodes = (st["binary_bytes"] - 48 * ps.n_tris) // 64
+    assert (n_nodes == ps.n_tris - 1) if eff == 1 else (ps.n_tris / (2 * eff) < n_nodes < ps.n_tris - 1)
+    rng = np.random.default_rng(11)
+    n = 20000
+    o = np.concatenate([np.tile(cam, (n // 2, 1)), rng.uniform(-7, 7, (n // 2, 3))])
+    d = rng.normal(size=(n, 3)); d[: n // 2, 2] = -np.abs(d[: n // 2, 2]) - 0.5
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    p_b, t_b, _ = R.intersect(o, d, "lbvh2", "f64")
+    p_n, t_n, _ = R.intersect(o, d, "nearest", "f64")
+    assert np.array_equal(p_b, p_n) and np.array_equal(t_b, t_n) and (p_b >= 28).mean() > 0.2
+    kw = dict(width=48, height=32, spp=4, max_depth=6, camera=cam, f_distance=f, semantics="iterative", seed=9, real="f64", return_samples=True)
+    _, s_b, c_b = R.render(traversal="lbvh2", **kw)
+    _, s_n, c_n = R.render(traversal="lbvh", **kw)             # the 8-wide hierarchy: same semantics, different tree
+    assert np.array_equal(s_b, s_n) and c_b["rays_shadow"] == c_n["rays_shadow"] and c_b["rays_ext"] == c_n["rays_ext"]
+    R.close()
+
+
 def test_compat_beyond_the_small_scene_paths(oracle):
     """COMPAT on a scene with more than 32 leaves / referenced primitives (the Cornell scene + a 4x4 displaced grid = 60
     triangles): the kernels' small-scene tables (32-bit masks, two tests per round, descent chains) do not apply and the

@@ -417,6 +417,25 @@ def run_medium(args, rank, world, local, photons=None, steps=None, warmup=None, 
                "gpu_launches": steps, "mean_collisions": float((th.cpu().numpy() * np.arange(len(hist))).sum() / max(float(th.sum()), 1)),
                "parity": "unpinned by the reference (it has no volume walk, only R/src/medium_samples.py:14-16); pinned by the oracle + analytic expectations",
                "roofline": None}
+        try:
+            # the medium walk touches no memory to speak of (tallies in shared memory): its bound is the FP32 pipe.  Algorithmic
+            # work of one flight segment + collision: 75 flops (free path 2, move 6, |x|^2 5, shell 3,
+            # weight/roulette 7, Henyey-Greenstein cosine 10, sin/cos 5, rotation 27, renormalisation 10; a transcendental = 1)
+            if not _PEAKS:
+                from light_transport_b200 import host as _h
+                _o, _l, _ps, _nodes, _c, _d = scene_arrays("lts")
+                _R = _h.Renderer(_ps, _nodes, device=local)
+                peaks(_R)
+                _R.close()
+            pk = _PEAKS["fp64_tflops" if args.real == "f64" else "fp32_tflops"]
+            ach = 75.0 * float(ts[0]) / (float(tm[0]) * 1e-3) / 1e12
+            out["roofline"] = {"bound": "fp64" if args.real == "f64" else "fp32", "achieved": ach, "peak": pk, "unit": "TFLOP/s", "frac": ach / pk,
+                               "traffic": None, "kernel": "lt::medium_kernel", "kernel_ms_per_launch": float(tm[0]) / steps,
+                               "flops_model": "75 flops per flight segment (DESIGN.md section 4); Philox4x32-10 (about 100 integer operations per "
+                                              "segment) and the tallies are not counted",
+                               "peak_source": "FMA micro-benchmark run in this process (lt_measure_fp32_peak / lt_measure_fp64_peak)"}
+        except Exception as e:            # noqa: BLE001
+            out["roofline"] = {"error": f"{type(e).__name__}: {e}"}
         if world == 1 and not args.no_cpu_baseline:
             from oracle import oracle as O
             t0 = time.perf_counter()

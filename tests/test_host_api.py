@@ -182,3 +182,12 @@ def test_renderer_cache_key_is_the_content():
         assert host._content_key(ps, nodes) is None          # large scenes are keyed by object identity instead
     finally:
         host.RENDERER_CACHE_HASH_BYTES = keep
+
+
+def test_pin_array_declines_what_it_cannot_pin():
+    """arrays too small to matter, too large, or not contiguous are left alone without touching the device library"""
+    from light_transport_b200 import host
+    assert host.pin_array(np.zeros(10)) is False
+    assert host.pin_array(np.zeros((512, 512))[:, ::2]) is False
+    assert host.pin_array([1.0, 2.0]) is False
+    assert not host._pinned

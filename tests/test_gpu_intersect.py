@@ -152,6 +152,39 @@ def test_binary_tree_leaf_sizes(binary_leaf, leaf_max):
     R.close()
 
 
+@pytest.mark.parametrize("seed,n_soup", [(1, 300), (2, 3000), (3, 20000)])
+def test_hierarchies_on_triangle_soup_with_ties(seed, n_soup):
+    """Unstructured input for the hierarchy walks: random triangles of mixed sizes, exact duplicates (tie on t: the lowest
+    primitive index must win whatever leaf either copy sits in), zero-area triangles (never hit) and a few scene-sized ones.
+    Both hierarchies, every binary leaf size: ids and t of the all-primitive scan, bit for bit in float64."""
+    from light_transport_b200 import host, _pack
+    base, _, cam, f = load_scene("lts_scene.npz")
+    rng = np.random.default_rng(seed)
+    c = rng.uniform(-6, 6, (n_soup, 1, 3))
+    size = np.where(rng.random((n_soup, 1, 1)) < 0.02, 6.0, rng.choice([0.05, 0.3, 1.0], (n_soup, 1, 1)))
+    v = c + size * rng.normal(size=(n_soup, 3, 3))
+    n_dup, n_deg = n_soup // 10, n_soup // 50
+    v[rng.choice(n_soup, n_dup, replace=False)] = v[rng.choice(n_soup, n_dup)]            # exact duplicates
+    deg = rng.choice(n_soup, n_deg, replace=False)
+    v[deg, 2] = v[deg, 1]                                                                   # zero area
+    with np.errstate(invalid="ignore", divide="ignore"):
+        ps = _pack.from_arrays(v, base=base)
+    R = host.Renderer(ps, None)
+    n = 30000
+    o = rng.uniform(-7, 7, (n, 3))
+    d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    o[: n // 3] = np.asarray(cam, dtype=np.float64)[:3]
+    p_n, t_n, _ = R.intersect(o, d, "nearest", "f64")
+    assert (p_n >= 28).mean() > 0.15 and not np.isin(p_n, 28 + deg).any()
+    for leaf_max, binary_leaf in ((3, 2), (3, 3), (1, 1), (2, 1)):
+        R.build_lbvh(keep_binary=True, leaf_max=leaf_max, binary_leaf=binary_leaf)
+        for trav in ("lbvh", "lbvh2"):
+            p, t, _ = R.intersect(o, d, trav, "f64")
+            assert np.array_equal(p, p_n), f"{trav} leaf {leaf_max}/{binary_leaf}: {(p != p_n).sum()} ids differ"
+            assert np.array_equal(t, t_n)
+    R.close()
+
+
 def test_compat_beyond_the_small_scene_paths(oracle):
     """COMPAT on a scene with more than 32 leaves / referenced primitives (the Cornell scene + a 4x4 displaced grid = 60
     triangles): the kernels' small-scene tables (32-bit masks, two tests per round, descent chains) do not apply and the

@@ -611,6 +611,13 @@ def main():
                                       "cores the box happens to have"}
         if world == 1 and not args.no_rmse and args.config == "c2":
             out["time_to_rmse"] = time_to_rmse(R, cam, depth, args)
+            if "cpu_baseline" in out:
+                # the CPU counterpart, DERIVED: the same number of samples (the estimator is the same, so is its variance per sample)
+                # at the port's measured ray rate — not a separately timed run
+                t = out["time_to_rmse"]
+                cpu_rays = t["film"][0] * t["film"][1] * t["spp"] * r["rays_per_path"]
+                t["cpu_port_seconds_derived"] = cpu_rays / (out["cpu_baseline"]["value"] * 1e6)
+                t["cpu_port_note"] = "derived: film x spp x rays/path of this run / cpu_baseline.value (same estimator, same spp to reach the target)"
     R.close()
     if rank == 0:
         if c5_strong is not None:

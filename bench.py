@@ -356,19 +356,35 @@ def run_e2e(wl, ps, nodes, lights, cam, depth, *, width, height, spp_total, trav
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    t0 = time.perf_counter()
-    e_rays = 0
-    for i in range(steps):
-        img, info = lt.render_scene(sc, ps, nodes, spp=spp_total, seed=500 + i, return_info=True, **kw)
-        e_rays += info["rays_ext"] + info["rays_shadow"]
-    torch.cuda.synchronize()
-    et = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
-    er = torch.tensor([float(e_rays)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(et, op=dist.ReduceOp.MAX)
-        dist.all_reduce(er, op=dist.ReduceOp.SUM)
-    return {"value": float(er[0]) / float(et[0]) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(height * width * 3 * 8),
-            "api": "light_transport_b200.render_scene(scene, primitives, bvh, spp=, rng='philox')", "steps": steps}
+    from light_transport_b200 import host as _host
+
+    def timed(clear):
+        """`steps` calls; clear=True drops the cached uploaded scene before every call, inside the timed region"""
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        e_rays = 0
+        for i in range(steps):
+            if clear:
+                _host.clear_renderer_cache()
+            img, info = lt.render_scene(sc, ps, nodes, spp=spp_total, seed=500 + i, return_info=True, **kw)
+            e_rays += info["rays_ext"] + info["rays_shadow"]
+        torch.cuda.synchronize()
+        et = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        er = torch.tensor([float(e_rays)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(et, op=dist.ReduceOp.MAX)
+            dist.all_reduce(er, op=dist.ReduceOp.SUM)
+        return float(er[0]) / float(et[0]) / 1e6
+
+    strict = timed(True)          # every call uploads the scene (and builds its hierarchy): the contract's "inputs copied every step"
+    cached = timed(False)         # what a caller's loop over the same scene gets: render_scene keeps the uploaded scene
+    return {"value": strict, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(height * width * 3 * 8),
+            "api": "light_transport_b200.render_scene(scene, primitives, bvh, spp=, rng='philox')", "steps": steps,
+            "value_scene_cached": cached,
+            "note": "value: the uploaded-scene cache is cleared before every call inside the timed region (scene H2D + hierarchy build every "
+                    "step); value_scene_cached: repeated calls on the same scene, H2D per step is then the launch parameters only"}
 
 
 def run_medium(args, rank, world, local, photons=None, steps=None, warmup=None, emit_line=True):

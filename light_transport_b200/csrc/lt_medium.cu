@@ -54,20 +54,24 @@ LT_DEVINL void medium_rand4<float>(const MediumDev& P, uint64_t photon, uint32_t
     u01(o[1], 0u, u[2]); u01(o[3], 0u, u[3]);
 }
 
-// Tallies go to shared memory with one native atomic per event (64-bit integer adds).  Round 1 summed the lanes of a
-// match_any group first and issued one atomic per distinct bin — needed while the radial bins were doubles (CAS loops); with
-// fixed-point bins that loop (15 % of the kernel's instructions) is gone: 52.4 -> see DESIGN.md.
+// Tallies go to shared memory with native 32-bit atomics (see the kernel).  Round 1 summed the lanes of a match_any group first
+// and issued one atomic per distinct bin — needed while the radial bins were doubles (CAS loops); with fixed-point bins that
+// loop (15 % of the kernel's instructions) is gone.
 #define LM_FIXED_ONE 4294967296.0
 
 template <typename R>
 __global__ void __launch_bounds__(LM_BLOCK) medium_kernel(const MediumDev P) {
     extern __shared__ __align__(16) char smem[];
-    unsigned long long* sh_hist = reinterpret_cast<unsigned long long*>(smem);              // [D+1]
-    // radial bins in 32.32 fixed point: a deposit is a weight in [0, 1], integer sums are native shared-memory atomics (a double
-    // add is a CAS loop) and order-independent; 2^32 unit deposits fit per CTA and bin (the host splits larger jobs)
-    unsigned long long* sh_rbins = reinterpret_cast<unsigned long long*>(smem + sizeof(unsigned long long) * (P.max_depth + 1));
-    for (int k = threadIdx.x; k <= P.max_depth; k += blockDim.x) sh_hist[k] = 0ull;
-    for (int k = threadIdx.x; k < P.n_rbins; k += blockDim.x) sh_rbins[k] = 0ull;
+    // tallies of the CTA in shared memory, 32-bit words: 64-bit shared-memory atomic adds are CAS loops on this part (measured: 9 %
+    // of the instructions, 24 % of the stall samples), 32-bit ones are native.  Collision-count histogram: 32-bit counts (the host
+    // keeps a CTA below 2^31 collisions per launch).  Radial bins: 32.32 fixed point — a deposit is a weight in [0, 1] — held as a
+    // low and a high word: the low word is added with the returning atomic, whose old value tells this very add whether it wrapped,
+    // and the wrap goes to the high word; integer sums are exact to 2^-33 per deposit and order-independent.
+    unsigned* sh_hist = reinterpret_cast<unsigned*>(smem);                                   // [D+1]
+    unsigned* sh_rlo = sh_hist + ((P.max_depth + 2) & ~1);                                   // [NB]
+    unsigned* sh_rhi = sh_rlo + P.n_rbins;                                                   // [NB]
+    for (int k = threadIdx.x; k <= P.max_depth; k += blockDim.x) sh_hist[k] = 0u;
+    for (int k = threadIdx.x; k < P.n_rbins; k += blockDim.x) { sh_rlo[k] = 0u; sh_rhi[k] = 0u; }
     __syncthreads();
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -159,14 +163,23 @@ __global__ void __launch_bounds__(LM_BLOCK) medium_kernel(const MediumDev P) {
                 }
             }
             // ---- tallies: shared-memory staging, warp-aggregated atomics
-            if (deposit) atomicAdd(sh_rbins + shell, __double2ull_rn(dep * LM_FIXED_ONE));
-            if (fin) atomicAdd(sh_hist + min(k, D), 1ull);
+            if (deposit) {
+                const unsigned long long fx = __double2ull_rn(dep * LM_FIXED_ONE);
+                const unsigned xl = (unsigned)fx, xh = (unsigned)(fx >> 32);
+                const unsigned old = atomicAdd(sh_rlo + shell, xl);
+                const unsigned up = xh + ((old + xl) < old ? 1u : 0u);
+                if (up) atomicAdd(sh_rhi + shell, up);
+            }
+            if (fin) atomicAdd(sh_hist + min(k, D), 1u);
             if (fin) alive = false;
         }
     }
     __syncthreads();
-    for (int kk = threadIdx.x; kk <= D; kk += blockDim.x) if (sh_hist[kk]) atomicAdd(P.hist + kk, sh_hist[kk]);
-    for (int kk = threadIdx.x; kk < NB; kk += blockDim.x) if (sh_rbins[kk]) atomicAdd(P.rbins + kk, (double)sh_rbins[kk] * (1.0 / LM_FIXED_ONE));
+    for (int kk = threadIdx.x; kk <= D; kk += blockDim.x) if (sh_hist[kk]) atomicAdd(P.hist + kk, (unsigned long long)sh_hist[kk]);
+    for (int kk = threadIdx.x; kk < NB; kk += blockDim.x) {
+        const unsigned long long v = ((unsigned long long)sh_rhi[kk] << 32) | sh_rlo[kk];
+        if (v) atomicAdd(P.rbins + kk, (double)v * (1.0 / LM_FIXED_ONE));
+    }
     double tv[6] = {t_esc, t_abs, t_trunc, t_rrk, t_rrg, t_mu};
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
@@ -216,7 +229,7 @@ extern "C" int lt_medium_walk(lt_ctx* ctx, const lt_medium_params* p, uint64_t n
     P.max_depth = D; P.mode = p->mode; P.rr_start = p->rr_start; P.n_rbins = NB;
     P.seed = p->seed; P.first_photon = p->first_photon; P.n_photons = n_photons;
     P.hist = d_hist; P.rbins = d_rbins; P.totals = d_tot; P.counts = d_cnt;
-    const size_t smem = sizeof(unsigned long long) * (D + 1) + sizeof(double) * std::max(NB, 1);
+    const size_t smem = sizeof(unsigned) * ((D + 2) & ~1) + 2 * sizeof(unsigned) * std::max(NB, 1);
     int bps = 0;
     if (p->real == LT_REAL_F64) LT_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, medium_kernel<double>, LM_BLOCK, smem));
     else LT_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, medium_kernel<float>, LM_BLOCK, smem));

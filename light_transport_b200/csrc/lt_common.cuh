@@ -17,6 +17,7 @@ void set_error(const char* fmt, ...);
         cudaError_t e__ = (expr);                                                                 \
         if (e__ != cudaSuccess) {                                                                 \
             lt::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            cudaGetLastError(); /* a recoverable error must not resurface in a later call's launch check */ \
             return LT_E_CUDA;                                                                     \
         }                                                                                         \
     } while (0)

@@ -500,3 +500,20 @@ def test_render_scene_keeps_the_uploaded_scene_and_pins_the_image(R_lts):
     assert addr not in host._pinned                                              # unregistered with the array
     host.clear_renderer_cache()
     assert not host._renderer_cache
+
+
+def test_recoverable_cuda_error_does_not_poison_later_calls(R_lts):
+    """a refused call (registering the same host range twice) reports its error once; the next launch check must not see it"""
+    import ctypes as C
+    from light_transport_b200 import host
+    ps, nodes, cam, f = load_scene("lts_scene.npz")
+    a = np.zeros(1 << 16)
+    L, ctx = host.lib(), host._get_ctx(0)
+    ptr, n = C.c_void_p(a.ctypes.data), C.c_size_t(a.nbytes)
+    assert L.lt_host_register(ctx, ptr, n) == 0
+    try:
+        assert L.lt_host_register(ctx, ptr, n) != 0 and b"cudaHostRegister" in L.lt_last_error()
+        _, s, c = R_lts.render(width=16, height=16, spp=2, max_depth=4, camera=cam, f_distance=f, seed=1, real="f32", return_samples=True)
+        assert c["paths"] == 16 * 16 * 2 and np.isfinite(s).all()
+    finally:
+        assert L.lt_host_unregister(ctx, ptr) == 0

@@ -398,6 +398,68 @@ __global__ void scan2_kernel(uint32_t* __restrict__ a, uint32_t* __restrict__ b,
     if (threadIdx.x == 0) { totals[0] = carry[0]; totals[1] = carry[1]; }
 }
 
+// ---- the same scan over many CTAs: tile sums -> scan of the sums (the kernel above) -> per-tile scan with the tile's offset.
+// `b` may be null (one array).  Used above SC_MIN elements; below that one CTA is faster than three launches.
+#define SC_THREADS 256
+#define SC_ITEMS 16
+#define SC_TILE (SC_THREADS * SC_ITEMS)
+#define SC_MIN 32768
+__global__ void scan_tile_sums_kernel(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, int total, uint32_t* __restrict__ sums, int nblk) {
+    __shared__ uint32_t ws[2][SC_THREADS / 32];
+    const int base = blockIdx.x * SC_TILE;
+    uint32_t sa = 0, sb = 0;
+    for (int k = threadIdx.x; k < SC_TILE; k += SC_THREADS) {
+        const int i = base + k;
+        if (i < total) { sa += a[i]; if (b) sb += b[i]; }
+    }
+    for (int o = 16; o > 0; o >>= 1) { sa += __shfl_xor_sync(0xffffffffu, sa, o); sb += __shfl_xor_sync(0xffffffffu, sb, o); }
+    if ((threadIdx.x & 31) == 0) { ws[0][threadIdx.x >> 5] = sa; ws[1][threadIdx.x >> 5] = sb; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t ta = 0, tb = 0;
+        for (int w = 0; w < SC_THREADS / 32; ++w) { ta += ws[0][w]; tb += ws[1][w]; }
+        sums[blockIdx.x] = ta;
+        sums[nblk + blockIdx.x] = tb;
+    }
+}
+
+__global__ void scan_tile_apply_kernel(uint32_t* __restrict__ a, uint32_t* __restrict__ b, int total, const uint32_t* __restrict__ sums, int nblk) {
+    __shared__ uint32_t ws[2][SC_THREADS / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int base = blockIdx.x * SC_TILE + threadIdx.x * SC_ITEMS;          // each thread owns SC_ITEMS consecutive elements
+    uint32_t va[SC_ITEMS], vb[SC_ITEMS], sa = 0, sb = 0;
+#pragma unroll
+    for (int k = 0; k < SC_ITEMS; ++k) {
+        const int i = base + k;
+        va[k] = i < total ? a[i] : 0u;
+        vb[k] = (b && i < total) ? b[i] : 0u;
+        sa += va[k]; sb += vb[k];
+    }
+    uint32_t xa = sa, xb = sb;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t ya = __shfl_up_sync(0xffffffffu, xa, o), yb = __shfl_up_sync(0xffffffffu, xb, o);
+        if (lane >= o) { xa += ya; xb += yb; }
+    }
+    if (lane == 31) { ws[0][wid] = xa; ws[1][wid] = xb; }
+    __syncthreads();
+    uint32_t ra = sums[blockIdx.x] + xa - sa, rb = sums[nblk + blockIdx.x] + xb - sb;
+    for (int w = 0; w < wid; ++w) { ra += ws[0][w]; rb += ws[1][w]; }
+#pragma unroll
+    for (int k = 0; k < SC_ITEMS; ++k) {
+        const int i = base + k;
+        if (i < total) { a[i] = ra; ra += va[k]; if (b) { b[i] = rb; rb += vb[k]; } }
+    }
+}
+
+// exclusive scan in place of a[0..total) (and b, if given) for total > SC_MIN; totals[0..1] = the sums.
+// `sums`: 2 * ceil(total / SC_TILE) words of scratch.
+static void scan_multi(uint32_t* a, uint32_t* b, int total, uint32_t* totals, uint32_t* sums, cudaStream_t st) {
+    const int nblk = (total + SC_TILE - 1) / SC_TILE;
+    scan_tile_sums_kernel<<<nblk, SC_THREADS, 0, st>>>(a, b, total, sums, nblk);
+    scan2_kernel<<<1, 1024, 0, st>>>(sums, sums + nblk, nblk, totals);
+    scan_tile_apply_kernel<<<nblk, SC_THREADS, 0, st>>>(a, b, total, sums, nblk);
+}
+
 struct RawTris {
     const double *v0, *v1, *v2;
     const int32_t* mat;
@@ -598,7 +660,7 @@ static int bvh_build_body(lt_scene* s, int flags, lt_bvh_stats* out) {
     Tmp<Box> prim_boxes, node_boxes;
     Tmp<float> block_cb, cb;
     Tmp<uint64_t> keys_a, keys_b;
-    Tmp<uint32_t> vals_a, vals_b, hist, cnt_int, cnt_tri, totals;
+    Tmp<uint32_t> vals_a, vals_b, hist, cnt_int, cnt_tri, totals, sums;
     Tmp<int> left, right, par_i, par_l, arrive, maxd, rng_lo, rng_hi, wb, slots, wpos;
     Tmp<WNode> wtmp;
     Tmp<double> sah;
@@ -611,6 +673,7 @@ static int bvh_build_body(lt_scene* s, int flags, lt_bvh_stats* out) {
     LT_CUDA_OK(arrive.alloc(n)); LT_CUDA_OK(maxd.alloc(1));
     LT_CUDA_OK(wb.alloc(n)); LT_CUDA_OK(wpos.alloc(n)); LT_CUDA_OK(slots.alloc(8 * (size_t)n)); LT_CUDA_OK(cnt_int.alloc(n)); LT_CUDA_OK(cnt_tri.alloc(n));
     LT_CUDA_OK(totals.alloc(2)); LT_CUDA_OK(wtmp.alloc(n)); LT_CUDA_OK(sah.alloc(1));
+    LT_CUDA_OK(sums.alloc(2 * (std::max<size_t>((size_t)n, 256 * (size_t)tiles) / SC_TILE + 2)));
     LT_CUDA_OK(cudaMemsetAsync(arrive.p, 0, (size_t)n * sizeof(int), st));
     LT_CUDA_OK(cudaMemsetAsync(maxd.p, 0, sizeof(int), st));
     LT_CUDA_OK(cudaMemsetAsync(sah.p, 0, sizeof(double), st));
@@ -627,7 +690,8 @@ static int bvh_build_body(lt_scene* s, int flags, lt_bvh_stats* out) {
     for (int pass = 0; pass < 8; ++pass) {           // 63-bit codes + the size-class bit: 8 digits of 8 bits
         int shift = pass * 8;
         rs_hist_kernel<<<tiles, LB_THREADS, 0, st>>>(ki, n, shift, hist.p);
-        rs_scan_kernel<<<1, LB_THREADS, 0, st>>>(hist.p, 256 * tiles);
+        if (256 * tiles <= SC_MIN) rs_scan_kernel<<<1, LB_THREADS, 0, st>>>(hist.p, 256 * tiles);
+        else scan_multi(hist.p, nullptr, 256 * tiles, totals.p, sums.p, st);
         rs_scatter_kernel<<<tiles, LB_THREADS, 0, st>>>(ki, vi, n, shift, hist.p, ko, vo);
         std::swap(ki, ko);
         std::swap(vi, vo);
@@ -646,7 +710,8 @@ static int bvh_build_body(lt_scene* s, int flags, lt_bvh_stats* out) {
     while (level_n > 0) {
         const int lb = (level_n + LB_THREADS - 1) / LB_THREADS;
         collapse_kernel<<<lb, LB_THREADS, 0, st>>>(tv, wb.p, level_start, level_n, slots.p, cnt_int.p, cnt_tri.p);
-        scan2_kernel<<<1, 1024, 0, st>>>(cnt_int.p, cnt_tri.p, level_n, totals.p);
+        if (level_n <= SC_MIN) scan2_kernel<<<1, 1024, 0, st>>>(cnt_int.p, cnt_tri.p, level_n, totals.p);
+        else scan_multi(cnt_int.p, cnt_tri.p, level_n, totals.p, sums.p, st);
         emit_wide_kernel<<<lb, LB_THREADS, 0, st>>>(tv, raw, wb.p, level_start, level_n, level_start + level_n, tri_cursor, slots.p, cnt_int.p,
                                                     cnt_tri.p, wtmp.p, s->wtris, s->wleaf_prims, wpos.p, sah.p);
         uint32_t tot[2];
@@ -665,8 +730,12 @@ static int bvh_build_body(lt_scene* s, int flags, lt_bvh_stats* out) {
         if (n >= (1 << 28)) { free_hierarchy(s); set_error("LT_BVH_KEEP_BINARY: at most 2^28 - 1 triangles"); return LT_E_OVERFLOW; }
         const int bleaf = ((flags >> 10) & 3) ? ((flags >> 10) & 3) : std::min(leaf_max, LT_LBVH2_LEAF_MAX);   // never above the slots' size
         mark_used_kernel<<<iblocks, LB_THREADS, 0, st>>>(n, rng_lo.p, rng_hi.p, std::min(bleaf, leaf_max), cnt_int.p);
-        LT_CUDA_OK(cudaMemsetAsync(cnt_tri.p, 0, (size_t)(n - 1) * sizeof(uint32_t), st));
-        scan2_kernel<<<1, 1024, 0, st>>>(cnt_int.p, cnt_tri.p, n - 1, totals.p);
+        if (n - 1 <= SC_MIN) {
+            LT_CUDA_OK(cudaMemsetAsync(cnt_tri.p, 0, (size_t)(n - 1) * sizeof(uint32_t), st));
+            scan2_kernel<<<1, 1024, 0, st>>>(cnt_int.p, cnt_tri.p, n - 1, totals.p);
+        } else {
+            scan_multi(cnt_int.p, nullptr, n - 1, totals.p, sums.p, st);
+        }
         uint32_t tot[2];
         LT_CUDA_OK(cudaMemcpyAsync(tot, totals.p, sizeof tot, cudaMemcpyDeviceToHost, st));
         LT_CUDA_OK(cudaStreamSynchronize(st));
